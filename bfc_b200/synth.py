@@ -1,0 +1,105 @@
+"""Synthetic read generator (SURVEY.md §8(d) / Appendix C recipe).
+
+genome  = i.i.d. uniform ACGT of length G from numpy PCG64(seed)
+reads   = N reads of length L, start uniform, strand uniform, per-base substitution
+          error p (uniform over the 3 other bases), quality: error bases Q in U[2,19],
+          others Q in U[25,40] (Phred+33), N-rate `n_rate`
+records = "@r<i>\n<seq>\n+\n<qual>\n"
+
+Optionally a fraction of the genome is made of diverged repeat copies
+(`repeat_frac`), which gives the correction search real branching.
+
+Pure host code (numpy).  Used by the tests, by tools/make_golden.py and by the
+reference arm of bench.py.  The device-side generator used for the HBM-resident
+bench lives in csrc/ (bfcg_synth_*), it follows the same distribution but not the
+same PRNG stream.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+_ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+def make_genome(G: int, seed: int, repeat_frac: float = 0.0, repeat_div: float = 0.015) -> np.ndarray:
+    """Return the genome as base codes 0..3 (uint8)."""
+    rng = np.random.default_rng(seed)
+    g = rng.integers(0, 4, size=G, dtype=np.uint8)
+    if repeat_frac > 0:
+        # copy random 2 kb segments elsewhere with `repeat_div` divergence
+        seg = 2000 if G >= 20000 else max(50, G // 20)
+        n_seg = int(G * repeat_frac / seg)
+        for _ in range(n_seg):
+            a = int(rng.integers(0, G - seg))
+            b = int(rng.integers(0, G - seg))
+            s = g[a:a + seg].copy()
+            m = rng.random(seg) < repeat_div
+            s[m] = (s[m] + rng.integers(1, 4, size=int(m.sum()), dtype=np.uint8)) & 3
+            g[b:b + seg] = s
+    return g
+
+
+def make_reads(genome: np.ndarray, N: int, L: int, seed: int, err: float = 0.01, n_rate: float = 2e-4):
+    """Return (seq, qual): two uint8 arrays of shape (N, L) holding ASCII."""
+    rng = np.random.default_rng(seed + 0x5eed)
+    G = genome.shape[0]
+    start = rng.integers(0, G - L + 1, size=N)
+    strand = rng.integers(0, 2, size=N, dtype=np.uint8)
+    idx = start[:, None] + np.arange(L)[None, :]
+    codes = genome[idx]
+    rc = (3 - codes[:, ::-1])
+    codes = np.where(strand[:, None] == 1, rc, codes).astype(np.uint8)
+    emask = rng.random((N, L)) < err
+    sub = rng.integers(1, 4, size=(N, L), dtype=np.uint8)
+    codes = np.where(emask, (codes + sub) & 3, codes).astype(np.uint8)
+    q_ok = rng.integers(25, 41, size=(N, L), dtype=np.uint8)
+    q_err = rng.integers(2, 20, size=(N, L), dtype=np.uint8)
+    qual = (np.where(emask, q_err, q_ok) + 33).astype(np.uint8)
+    seq = _ACGT[codes]
+    nmask = rng.random((N, L)) < n_rate
+    seq = np.where(nmask, np.uint8(ord("N")), seq).astype(np.uint8)
+    return seq, qual
+
+
+def fastq_bytes(seq: np.ndarray, qual: np.ndarray | None, first_index: int = 0, prefix: str = "r") -> bytes:
+    """Serialise to FASTQ (or FASTA when qual is None)."""
+    N, L = seq.shape
+    out = []
+    hdr = b"@" if qual is not None else b">"
+    for i in range(N):
+        out.append(hdr + f"{prefix}{first_index + i}\n".encode())
+        out.append(seq[i].tobytes())
+        if qual is not None:
+            out.append(b"\n+\n")
+            out.append(qual[i].tobytes())
+        out.append(b"\n")
+    return b"".join(out)
+
+
+def write_fastq(path: str, G: int, N: int, L: int, seed: int, err: float = 0.01, n_rate: float = 2e-4,
+                repeat_frac: float = 0.0, chunk: int = 200_000) -> None:
+    """Write a synthetic FASTQ file (streamed in chunks so that large N stays cheap)."""
+    genome = make_genome(G, seed, repeat_frac)
+    with open(path, "wb") as fp:
+        done = 0
+        while done < N:
+            n = min(chunk, N - done)
+            seq, qual = make_reads(genome, n, L, seed + 7919 * (done // chunk), err, n_rate)
+            fp.write(fastq_bytes(seq, qual, first_index=done))
+            done += n
+
+
+def concat_batch(seq: np.ndarray, qual: np.ndarray | None):
+    """(N, L) ASCII arrays -> the flat host batch the C-ABI takes:
+    `seq`/`qual` byte streams where every read is followed by one 0 byte, and
+    `offsets` (N+1 uint64) giving each read's start in the stream."""
+    N, L = seq.shape
+    s = np.zeros((N, L + 1), dtype=np.uint8)
+    s[:, :L] = seq
+    q = None
+    if qual is not None:
+        q = np.zeros((N, L + 1), dtype=np.uint8)
+        q[:, :L] = qual
+        q = q.reshape(-1)
+    offsets = (np.arange(N + 1, dtype=np.uint64) * np.uint64(L + 1))
+    return s.reshape(-1), q, offsets
