@@ -162,7 +162,7 @@ def parse_fastx(data: bytes):
         if ln[:1] == b"@":
             hdr = ln[1:]
             seq = lines[i + 1]
-            qual = lines[i + 3]
+            qual = lines[i + 3] or None  # kseq: an empty quality string means "no quality" (bseq.c:68)
             i += 4
         elif ln[:1] == b">":
             hdr = ln[1:]
@@ -222,12 +222,15 @@ def format_corrected(recs, seq: np.ndarray, qual, off: np.ndarray, aux: np.ndarr
 def format_trimmed(recs, seq, qual, off, keep, tstart, tend, no_qual=False) -> bytes:
     """The step-2 printer of the reference in `-1` mode (correct.c:605-611)."""
     out = []
-    for i, r in enumerate(recs):
+    sticky = None  # kseq never clears comment.s, and bseq_read strdup()s whatever is there
+    for i, r in enumerate(recs):  # (bseq.c:66, kseq.h:190): a comment persists until replaced
+        if r[1]:
+            sticky = r[1]
         if not keep[i]:
             continue
         o = int(off[i])
         is_fq = r[3] is not None and not no_qual
-        hdr = (b"@" if is_fq else b">") + r[0] + (b"\t" + r[1] if r[1] else b"")
+        hdr = (b"@" if is_fq else b">") + r[0] + (b"\t" + sticky if sticky else b"")
         s, e = o + int(tstart[i]), o + int(tend[i])
         out.append(hdr + b"\n" + seq[s:e].tobytes() + b"\n")
         if is_fq:

@@ -1,0 +1,189 @@
+#!/usr/bin/env python
+"""Generate tests/golden/ from the UNMODIFIED reference (oracle/_ref, built by
+`make -C oracle ref` from /root/reference).  Run in the build container only; the
+GPU box has no /root/reference, it consumes the committed fixtures.
+
+For every case:
+  in.fq.gz          the input (synthetic, or hand-made edge cases)
+  case.json         CLI arguments (k, b, ...), sizes, digests
+  corrected.fq.gz   stdout of `bfc -t1 <args> in.fq`              (normal mode)
+  table.npz         `-E -d` dump parsed to sorted (sub, key) arrays (normal mode)
+  trimmed.fq.gz     stdout of `bfc -1 -t1 <args> in.fq`
+  digests of the first Bloom filter / bf_high bytes (sha256) obtained through the
+  `--wrap=bfc_bf_destroy` hook (oracle/ref_hooks.c)
+plus kat.json: known-answer vectors for the k-mer/hash/Bloom/table primitives taken
+from the reference's own functions (oracle/_ref/libbfcref.so).
+"""
+import ctypes as C
+import gzip
+import hashlib
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import orc  # noqa: E402
+from bfc_b200 import synth  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+EDGE = b"""@short_read some comment
+ACGTACGTAC
++
+IIIIIIIIII
+@empty
+
++
+
+@many_n
+ACGTNNNNNNNNNNACGTACGTTTGACCANNNNNGGGT
++
+IIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIII
+>fasta_multi line comment
+ACGTTGCATGGCCATTAGCGGATCCTTAGACCAGTTTGACGG
+CATCAAGTCCGATTACGGATCGATTTCCAGGA
+@lower
+acgttgcatggccattagcggatccttagaccagtttgacggcatcaagtccgattacggatcgatttccagga
++
+IIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIII
+"""
+
+
+def sha(a: np.ndarray) -> str:
+    return hashlib.sha256(a.tobytes()).hexdigest()
+
+
+def gz_write(path, data: bytes):
+    with open(path, "wb") as raw:  # mtime=0 -> reproducible bytes
+        with gzip.GzipFile(fileobj=raw, mode="wb", mtime=0, compresslevel=9) as fp:
+            fp.write(data)
+
+
+def synth_case(name, G, N, L, seed, k, b, err=0.01, repeat=0.0, extra_edge=False, extra_args=()):
+    d = os.path.join(GOLD, name)
+    os.makedirs(d, exist_ok=True)
+    tmp = tempfile.mkdtemp()
+    fq = os.path.join(tmp, "in.fq")
+    synth.write_fastq(fq, G, N, L, seed, err=err, repeat_frac=repeat)
+    data = open(fq, "rb").read()
+    if extra_edge:
+        # edge records carrying genome-derived sequence so that some of them are correctable
+        data = EDGE + data
+        # duplicate the first 200 records without quality (FASTA) and in lower case
+        recs = orc.parse_fastx(data)
+        extra = []
+        for r in recs[10:110]:
+            extra.append(b">" + r[0] + b"_fa\n" + r[2] + b"\n")
+        for r in recs[110:160]:
+            extra.append(b"@" + r[0] + b"_lc\n" + r[2].lower() + b"\n+\n" + r[3] + b"\n")
+        data += b"".join(extra)
+        open(fq, "wb").write(data)
+    gz_write(os.path.join(d, "in.fq.gz"), data)
+    args = ["-k", str(k), "-b", str(b)] + list(extra_args)
+    meta = dict(name=name, k=k, b=b, extra_args=list(extra_args), n_records=len(orc.parse_fastx(data)),
+                generator=dict(G=G, N=N, L=L, seed=seed, err=err, repeat=repeat, edge=extra_edge))
+    # normal mode
+    pre = os.path.join(tmp, "bloom")
+    out = orc.ref_run(args + ["-t1", fq], binary="bfc_bloomdump", env={"BFC_REF_BLOOM_DUMP": pre})
+    gz_write(os.path.join(d, "corrected.fq.gz"), out)
+    _, _, bb = orc.read_bloom_dump(pre + ".0")
+    meta["bloom_sha256"] = sha(bb)
+    meta["bloom_popcount"] = int(np.unpackbits(bb).sum())
+    dump = os.path.join(tmp, "dump")
+    orc.ref_run(args + ["-t1", "-E", "-d", dump, fq])
+    rk, rl, sub, key = orc.parse_ref_dump(dump)
+    np.savez_compressed(os.path.join(d, "table.npz"), sub=sub, key=key)
+    meta["table_k"], meta["table_l_pre"], meta["table_n"] = rk, rl, int(len(key))
+    meta["corrected_sha256"] = hashlib.sha256(out).hexdigest()
+    # the stock binary must agree with the hooked one
+    assert orc.ref_run(args + ["-t1", fq]) == out
+    # trim mode
+    pre = os.path.join(tmp, "tbloom")
+    tout = orc.ref_run(args + ["-1", "-t1", fq], binary="bfc_bloomdump", env={"BFC_REF_BLOOM_DUMP": pre})
+    gz_write(os.path.join(d, "trimmed.fq.gz"), tout)
+    _, _, t0 = orc.read_bloom_dump(pre + ".0")
+    _, _, t1 = orc.read_bloom_dump(pre + ".1")
+    assert sha(t0) == meta["bloom_sha256"]
+    meta["bf_high_sha256"] = sha(t1)
+    meta["bf_high_popcount"] = int(np.unpackbits(t1).sum())
+    meta["trimmed_sha256"] = hashlib.sha256(tout).hexdigest()
+    json.dump(meta, open(os.path.join(d, "case.json"), "w"), indent=1, sort_keys=True)
+    print(name, "records", meta["n_records"], "table", meta["table_n"], "bloom bits", meta["bloom_popcount"])
+
+
+def kat():
+    R = orc.reflib()
+    g = b"ACGTTGCATGGCCATTAGCGGATCCTTAGACCAGTTTGACGGCATCAAGTCCGATTACGGATCGATTTCCAGGA"
+    code = {65: 0, 67: 1, 71: 2, 84: 3}
+    out = dict(sequence=g.decode(), kmers=[], hash64=[], bloom=[], table=[], change=[])
+    rng = np.random.default_rng(7)
+    for k in (9, 17, 21, 23, 31, 32, 33, 34, 37, 50, 51, 55, 62, 63):
+        for start in (0, 3, 10):
+            x = (C.c_uint64 * 4)(0, 0, 0, 0)
+            for ch in g[start:start + k]:
+                R.ref_kmer_append(k, x, code[ch])
+            y = (C.c_uint64 * 2)()
+            h = R.ref_kmer_hash(k, x, y)
+            out["kmers"].append(dict(k=k, start=start, x=[int(v) for v in x], hash=int(h), y=[int(v) for v in y]))
+            d, c = int(rng.integers(0, k)), int(rng.integers(0, 4))
+            x2 = (C.c_uint64 * 4)(*x)
+            R.ref_kmer_change(k, x2, d, c)
+            out["change"].append(dict(k=k, start=start, d=d, c=c, x=[int(v) for v in x2]))
+    for k in (9, 21, 33, 47, 63):
+        m = (1 << k) - 1
+        for v in rng.integers(0, 1 << 62, size=8, dtype=np.uint64):
+            v = int(v) & m
+            h = int(R.ref_hash_64(v, m))
+            assert int(R.ref_hash_64_inv(h, m)) == v
+            out["hash64"].append(dict(k=k, key=v, hash=h))
+    # Bloom: sequence of inserts with return values + final bytes digest
+    for n_shift, n_hashes in ((20, 4), (12, 4), (14, 7), (11, 40)):
+        bf = R.bfc_bf_init(n_shift, n_hashes)
+        hs = [int(v) for v in rng.integers(0, 1 << 63, size=600, dtype=np.uint64)]
+        hs = [0x0123456789abcdef, 0x0123456789abcdef] + hs + hs[:50]
+        rets = [int(R.bfc_bf_insert(bf, h)) for h in hs]
+        gets = [int(R.bfc_bf_get(bf, h ^ (i & 1))) for i, h in enumerate(hs[:100])]
+        b = np.ctypeslib.as_array(bf.contents.b, shape=(1 << (n_shift - 3),)).copy()
+        out["bloom"].append(dict(n_shift=n_shift, n_hashes=n_hashes, hashes=hs, insert_ret=rets, get_ret=gets,
+                                 bytes_sha256=sha(b), nonzero={str(int(i)): int(b[i]) for i in np.nonzero(b)[0][:64]}))
+        R.bfc_bf_destroy(bf)
+    # table: insert/get with saturation
+    for k, l_pre in ((21, 20), (31, 20), (32, 20), (33, 20), (37, 20), (51, 20), (55, 20), (63, 20), (17, 10)):
+        ch = R.bfc_ch_init(k, l_pre)
+        m = (1 << k) - 1
+        ys = [[int(a) & m, int(b) & m] for a, b in rng.integers(0, 1 << 63, size=(40, 2), dtype=np.uint64)]
+        ops = []
+        for i, y in enumerate(ys):
+            yy = (C.c_uint64 * 2)(*y)
+            g0 = int(R.bfc_ch_get(ch, yy))
+            reps = 1 + (i % 5) + (300 if i == 7 else 0)
+            for j in range(reps):
+                R.bfc_ch_insert(ch, yy, (i + j) & 1 if i != 7 else 1, 1)
+            ops.append(dict(y=y, get_before=g0, n_insert=reps, get_after=int(R.bfc_ch_get(ch, yy))))
+        cnt = (C.c_uint64 * 256)()
+        high = (C.c_uint64 * 64)()
+        mode = int(R.bfc_ch_hist(ch, cnt, high))
+        out["table"].append(dict(k=k, l_pre=l_pre, ops=ops, count=int(R.bfc_ch_count(ch)), mode=mode,
+                                 cnt_hist={str(i): int(v) for i, v in enumerate(cnt) if v},
+                                 high_hist={str(i): int(v) for i, v in enumerate(high) if v}))
+        R.bfc_ch_destroy(ch)
+    json.dump(out, open(os.path.join(GOLD, "kat.json"), "w"), indent=0)
+    print("kat.json written")
+
+
+if __name__ == "__main__":
+    if not orc.have_ref():
+        orc.build_oracle(ref=True)
+    os.makedirs(GOLD, exist_ok=True)
+    kat()
+    synth_case("k21_small", 20000, 3000, 100, 11, 21, 20)
+    synth_case("k31_edge", 20000, 2500, 100, 12, 31, 21, repeat=0.2, extra_edge=True)
+    synth_case("k33_rep", 15000, 1500, 150, 13, 33, 20, err=0.02, repeat=0.3)
+    synth_case("k55_rep", 12000, 1200, 150, 14, 55, 19, repeat=0.3)
+    synth_case("k63_h7", 12000, 1000, 150, 15, 63, 19, extra_args=("-H", "7"))
+    synth_case("k32_even", 12000, 1000, 100, 16, 32, 19, extra_args=("-c", "2", "-q", "30"))
