@@ -1,0 +1,308 @@
+// common.cuh -- shared by every translation unit of libbfc_b200 (sm_100a only).
+//
+// Device-side views of the two HBM-resident structures of the count/correct path
+// (blocked Bloom filter, counting table) with the inline device functions that
+// touch them, plus the host-side runtime singleton (stream, scratch arena, error
+// string, kernel timing).  No -rdc: everything device-side here is inline.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/bfc_b200.h"
+
+// ------------------------------------------------------------------ host runtime
+
+struct BfcgRuntime {
+	int dev;
+	bool ready;
+	cudaStream_t stream;
+	cudaEvent_t ev0, ev1;
+	bool timing;
+	uint64_t n_launches;
+	char err[512];
+	// grow-only device scratch arena (one allocation, carved per call)
+	uint8_t *arena;
+	size_t arena_bytes;
+	// grow-only pinned staging buffers for host batches
+	uint8_t *pin[2];
+	size_t pin_bytes[2];
+	int sm_count;
+};
+
+BfcgRuntime &bfcg_rt();
+int bfcg_rt_init();                       // lazily selects the device, creates the stream; BFCG_OK or error
+int bfcg_fail(const char *func, const char *what, cudaError_t e);
+void *bfcg_arena(size_t bytes);           // returns device scratch of at least `bytes` (contents undefined)
+uint8_t *bfcg_pinned(int which, size_t bytes);
+
+#define BFCG_CUDA(call)                                                        \
+	do {                                                                       \
+		cudaError_t e_ = (call);                                               \
+		if (e_ != cudaSuccess) return bfcg_fail(__func__, #call, e_);          \
+	} while (0)
+
+#define BFCG_LAUNCH_CHECK()                                                    \
+	do {                                                                       \
+		++bfcg_rt().n_launches;                                                \
+		cudaError_t e_ = cudaGetLastError();                                   \
+		if (e_ != cudaSuccess) return bfcg_fail(__func__, "kernel launch", e_);\
+	} while (0)
+
+struct BfcgTimer { // accumulates device time of the enclosed stream work into stats->kernel_ms
+	bfcg_stats_t *st;
+	bool on;
+	uint64_t launches0;
+	explicit BfcgTimer(bfcg_stats_t *s) : st(s), on(bfcg_rt().timing && s), launches0(bfcg_rt().n_launches) {
+		if (on) cudaEventRecord(bfcg_rt().ev0, bfcg_rt().stream);
+	}
+	void stop() { // call after the work is enqueued; synchronises the stream
+		if (on) {
+			float ms = 0;
+			cudaEventRecord(bfcg_rt().ev1, bfcg_rt().stream);
+			cudaEventSynchronize(bfcg_rt().ev1);
+			cudaEventElapsedTime(&ms, bfcg_rt().ev0, bfcg_rt().ev1);
+			st->kernel_ms += ms;
+		}
+		if (st) st->n_launches += bfcg_rt().n_launches - launches0;
+	}
+};
+
+// ------------------------------------------------------------------ host structs
+
+struct bfc_ch_s {
+	int k, l_pre;             // l_pre after the adjustment of reference htab.c:24-26
+	int rbits;                // log2(slots per region); capacity = 2^(l_pre + rbits) slots
+	unsigned long long *slots;
+	unsigned long long *counters; // device, 8 words: [0] n_entries, [1] n_deferred, [2] rehash failures
+	unsigned long long *deferred; // device: 2 words per deferred insert (y0 | is_high<<63, y1)
+	uint64_t def_cap;
+};
+
+// ------------------------------------------------------------------ device views
+
+struct BloomView {
+	uint32_t *w;      // 16 words per 64-byte block
+	int n_shift, n_hashes;
+};
+
+struct TabView {
+	unsigned long long *slots;
+	unsigned long long *counters;
+	unsigned long long *deferred;
+	unsigned long long def_cap;
+	int k, l_pre, rbits;
+};
+
+static inline BloomView bloom_view(const bfc_bf_t *b)
+{
+	BloomView v;
+	v.w = (uint32_t*)b->b, v.n_shift = b->n_shift, v.n_hashes = b->n_hashes;
+	return v;
+}
+
+static inline TabView tab_view(const bfc_ch_s *c)
+{
+	TabView v;
+	v.slots = c->slots, v.counters = c->counters, v.deferred = c->deferred, v.def_cap = c->def_cap;
+	v.k = c->k, v.l_pre = c->l_pre, v.rbits = c->rbits;
+	return v;
+}
+
+// table growth policy (htab.cu): make room for `extra` more distinct keys at load <= 1/2
+int bfcg_tab_reserve(bfc_ch_s *ch, uint64_t extra);
+// re-apply inserts that found their region full (after growing); htab.cu
+int bfcg_tab_drain_deferred(bfc_ch_s *ch);
+
+#ifdef __CUDACC__
+
+// ------------------------------------------------------------------ base codes
+
+// reference bseq.c:9-26 minus one: A/a 0, C/c 1, G/g 2, T/t 3, anything else 4
+__device__ __forceinline__ int base_code(uint8_t ch)
+{
+	const uint32_t u = ch & 0xDFu; // fold case
+	return u == 'A' ? 0 : u == 'C' ? 1 : u == 'G' ? 2 : u == 'T' ? 3 : 4;
+}
+
+// ------------------------------------------------------------------ Bloom probes
+
+struct BloomProbe {
+	uint64_t blk; // block index
+	int h1, h2;
+};
+
+// reference bbf.c:27-33
+__device__ __forceinline__ BloomProbe bloom_locate(uint64_t hash, int n_shift)
+{
+	BloomProbe p;
+	const int x = n_shift - BFC_BLK_SHIFT;
+	p.blk = hash & ((1ULL << x) - 1);
+	p.h1 = (int)(hash >> x) & BFC_BLK_MASK;
+	p.h2 = (int)(hash >> n_shift) & BFC_BLK_MASK;
+	if ((p.h2 & 31) == 0) p.h2 = (p.h2 + 1) & BFC_BLK_MASK;
+	return p;
+}
+
+// number of probe bits set in the block at `w` (16 words); the reference's probe walk
+// (bbf.c:35-42 / 54-61): positions < 8 belong to the lock byte and do not count.
+template <bool CG>
+__device__ __forceinline__ int bloom_count_set(const uint32_t *w, const BloomProbe &p, int n_hashes)
+{
+	int z = p.h1, done = 0, cnt = 0;
+	while (done < n_hashes) {
+		if (z >= 8) {
+			const uint32_t v = CG ? __ldcg(w + (z >> 5)) : w[z >> 5];
+			cnt += (v >> (z & 31)) & 1;
+			++done;
+		}
+		z = (z + p.h2) & BFC_BLK_MASK;
+	}
+	return cnt;
+}
+
+// set all probe bits with L2 atomics (order-free: used where only the union matters)
+__device__ __forceinline__ void bloom_set_atomic(uint32_t *w, const BloomProbe &p, int n_hashes)
+{
+	int z = p.h1, done = 0;
+	while (done < n_hashes) {
+		if (z >= 8) {
+			atomicOr(w + (z >> 5), 1u << (z & 31));
+			++done;
+		}
+		z = (z + p.h2) & BFC_BLK_MASK;
+	}
+}
+
+// ------------------------------------------------------------------ counting table
+
+// reference htab.c:45-58: (sub-table index, 50-bit key) of a hashed k-mer
+__device__ __forceinline__ void tab_subkey(int k, int l_pre, uint64_t y0, uint64_t y1, uint32_t &sub, uint64_t &key)
+{
+	if (k <= 32) {
+		const int t = 2 * k - l_pre;
+		const uint64_t z = y0 << k | y1;
+		key = z & ((1ULL << t) - 1);
+		sub = (uint32_t)(z >> t);
+	} else {
+		const int t = k - l_pre;
+		const int shift = t + k < BFC_CH_KEYBITS ? k : BFC_CH_KEYBITS - t;
+		key = (((y0 & ((1ULL << t) - 1)) << shift) ^ y1) & ((1ULL << BFC_CH_KEYBITS) - 1);
+		sub = (uint32_t)(y0 >> t);
+	}
+}
+
+__device__ __forceinline__ uint64_t tab_mix(uint64_t key)
+{
+	key ^= key >> 29;
+	key *= 0xBF58476D1CE4E5B9ULL;
+	key ^= key >> 32;
+	key *= 0x94D049BB133111EBULL;
+	key ^= key >> 29;
+	return key;
+}
+
+// Slot = key50 << 14 | high6 << 8 | cnt8; 0 = empty (cnt8 >= 1 for every stored key).
+// Probing: 4-slot (32-byte, one DRAM sector) buckets, linear over buckets inside the
+// key's region.  Returns 1 = new key stored, 0 = existing key updated, -1 = region
+// full (insert parked in the deferred list and re-applied after the table has grown).
+__device__ __forceinline__ int tab_upsert(const TabView &t, uint64_t y0, uint64_t y1, int is_high)
+{
+	uint32_t sub; uint64_t key;
+	tab_subkey(t.k, t.l_pre, y0, y1, sub, key);
+	const uint64_t R = 1ULL << t.rbits;
+	unsigned long long *reg = t.slots + ((uint64_t)sub << t.rbits);
+	uint64_t h = tab_mix(key) & (R - 1) & ~3ULL;
+	const unsigned long long fresh = key << 14 | (unsigned long long)(is_high ? 1 : 0) << 8 | 1ULL;
+	for (uint64_t n = 0; n < R; n += 4, h = (h + 4) & (R - 1)) {
+		unsigned long long *b = reg + h;
+		const ulonglong2 v01 = __ldcg((const ulonglong2*)b);
+		const ulonglong2 v23 = __ldcg((const ulonglong2*)b + 1);
+		unsigned long long v[4] = { v01.x, v01.y, v23.x, v23.y };
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			unsigned long long s = v[j];
+			if (s == 0) {
+				const unsigned long long prev = atomicCAS(b + j, 0ULL, fresh);
+				if (prev == 0) return 1;
+				s = prev;
+			}
+			if ((s >> 14) == key) {
+				for (;;) { // saturating increments (reference htab.c:76-79)
+					unsigned long long ns = s;
+					if ((s & 0xff) != 0xff) ++ns;
+					if (is_high && ((s >> 8) & 0x3f) != 0x3f) ns += 1 << 8;
+					if (ns == s) return 0;
+					const unsigned long long prev = atomicCAS(b + j, s, ns);
+					if (prev == s) return 0;
+					s = prev;
+				}
+			}
+		}
+	}
+	const unsigned long long idx = atomicAdd(t.counters + 1, 1ULL);
+	if (idx < t.def_cap) {
+		t.deferred[2 * idx] = y0 | (unsigned long long)(is_high ? 1 : 0) << 63;
+		t.deferred[2 * idx + 1] = y1;
+	}
+	return -1;
+}
+
+// store a ready-made slot value (restore / rehash); the key must not be present yet
+__device__ __forceinline__ bool tab_put_raw(const TabView &t, uint32_t sub, unsigned long long slot)
+{
+	const uint64_t R = 1ULL << t.rbits;
+	unsigned long long *reg = t.slots + ((uint64_t)sub << t.rbits);
+	uint64_t h = tab_mix(slot >> 14) & (R - 1) & ~3ULL;
+	for (uint64_t n = 0; n < R; ++n) {
+		const uint64_t i = (h + n) & (R - 1);
+		if (__ldcg(reg + i) == 0 && atomicCAS(reg + i, 0ULL, slot) == 0) return true;
+	}
+	return false;
+}
+
+// reference htab.c:84-92: -1 = absent, else the low 14 bits.  Read-only phase.
+__device__ __forceinline__ int tab_get(const TabView &t, uint64_t y0, uint64_t y1)
+{
+	uint32_t sub; uint64_t key;
+	tab_subkey(t.k, t.l_pre, y0, y1, sub, key);
+	const uint64_t R = 1ULL << t.rbits;
+	const unsigned long long *reg = t.slots + ((uint64_t)sub << t.rbits);
+	uint64_t h = tab_mix(key) & (R - 1) & ~3ULL;
+	for (uint64_t n = 0; n < R; n += 4, h = (h + 4) & (R - 1)) {
+		const ulonglong2 v01 = __ldg((const ulonglong2*)(reg + h));
+		const ulonglong2 v23 = __ldg((const ulonglong2*)(reg + h) + 1);
+		const unsigned long long v[4] = { v01.x, v01.y, v23.x, v23.y };
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			if (v[j] == 0) return -1;
+			if ((v[j] >> 14) == key) return (int)(v[j] & 0x3fff);
+		}
+	}
+	return -1;
+}
+
+// reference htab.c:94-99
+__device__ __forceinline__ int tab_kmer_occ(const TabView &t, const uint64_t x[4])
+{
+	uint64_t y[2];
+	bfc_kmer_hash(t.k, x, y);
+	return tab_get(t, y[0], y[1]);
+}
+
+// block-wide sum of a per-thread counter, one atomic per CTA
+__device__ __forceinline__ void block_add(unsigned long long *dst, unsigned long long v)
+{
+	__shared__ unsigned long long s_acc;
+	if (threadIdx.x == 0) s_acc = 0;
+	__syncthreads();
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+	if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_acc, v);
+	__syncthreads();
+	if (threadIdx.x == 0 && s_acc) atomicAdd(dst, s_acc);
+}
+
+#endif // __CUDACC__

@@ -1,0 +1,312 @@
+// count.cu -- the count phase: what the reference runs inside
+// kt_for(..., worker_count, ...) (count.c:106, :72-89) with the Bloom -> table cascade
+// of bfc_kmer_insert (count.c:54-70), reproduced with the SEQUENTIAL (-t1) semantics.
+//
+// Order dependence (count.c:9-18): occurrence t of a k-mer "passes" iff all n_hashes
+// Bloom bits were set by occurrences < t.  All ordering constraints are local to one
+// 64-byte Bloom block, so a sub-batch is processed as
+//
+//   K1 k_count_probe    every occurrence tests its bits against the filter as it was
+//                       BEFORE the sub-batch (no data bit is written in K1).  All bits
+//                       set -> it passes regardless of order: table upsert (or bf_high
+//                       insert in trim mode) right away.  Otherwise it is "pending": it
+//                       is appended to a list and marks its Bloom block in the two
+//                       spare bits of the block's lock byte (bit 0: one pending
+//                       occurrence, bit 1: more than one).
+//   K2 k_count_resolve  a pending occurrence alone in its block sets a bit nobody else
+//                       touches in this sub-batch: it cannot pass; its bits are OR-ed in.
+//                       Pending occurrences that share a block go to the conflict list.
+//   K3 radix sort       conflict list by (block, stream position)
+//   K4 k_count_replay   one thread per conflicting block replays its occurrences in
+//                       stream order with the reference's test-then-set, exactly.
+//
+// The lock byte is 0 again when the sub-batch ends, as in the reference (bbf.c:43).
+#include "common.cuh"
+#include <cub/device/device_radix_sort.cuh>
+#include <algorithm>
+
+#define CNT_THREADS 256
+#define CNT_CHUNK   36     // positions per thread; CHUNK/4 odd => conflict-free shared-memory reads
+#define CNT_SEG     (CNT_THREADS * CNT_CHUNK)
+#define CNT_HALO_MAX 64
+
+struct CountParams {
+	const uint8_t *seq, *qual;   // loaded stream window (device)
+	uint64_t len;                // bytes in the window
+	uint64_t emit_from;          // window positions < emit_from only warm the rolling k-mer up
+	int k, q;
+	BloomView bf, bf_high;       // bf_high.w == 0 in normal mode
+	TabView tab;                 // tab.slots == 0 in trim mode
+	unsigned long long *pend_y0, *pend_y1;
+	uint32_t *pend_t;
+	unsigned long long *ctr;     // [0] n_pending [1] n_kmers [2] n_pass [3] n_conflict
+	unsigned long long *conf_key;
+	uint32_t *conf_val;
+};
+
+__device__ __forceinline__ uint64_t hash_from_y(int k, uint64_t y0, uint64_t y1)
+{
+	// inverse of the last two lines of bfc_kmer_hash (kmer.h:85-86): h1 = y1, h0 = y0 - y1
+	const uint64_t m = (1ULL << k) - 1, h0 = (y0 - y1) & m;
+	return ((h0 ^ y1) << k) | y0;
+}
+
+__global__ void __launch_bounds__(CNT_THREADS) k_count_probe(CountParams p)
+{
+	__shared__ uint8_t s_code[CNT_SEG + CNT_HALO_MAX];
+	const int halo = p.k - 1;
+	const int64_t seg0 = (int64_t)p.emit_from + (int64_t)blockIdx.x * CNT_SEG;
+
+	// stage the CTA's window as codes: bits 0-2 base (4 = not ACGT / outside), bit 3 Q >= q
+	for (int i = threadIdx.x; i < CNT_SEG + halo; i += CNT_THREADS) {
+		const int64_t pos = seg0 - halo + i;
+		uint32_t c = 4;
+		if (pos >= 0 && (uint64_t)pos < p.len) {
+			c = base_code(p.seq[pos]);
+			if (c < 4 && (p.qual == 0 || (int)p.qual[pos] - 33 >= p.q)) c |= 8;
+		}
+		s_code[i] = (uint8_t)c;
+	}
+	__syncthreads();
+
+	const int base = threadIdx.x * CNT_CHUNK;
+	const int k = p.k;
+	const uint64_t mask = (1ULL << k) - 1;
+	uint64_t x[4] = {0, 0, 0, 0}, qmer = 0;
+	int l = 0;
+	unsigned long long n_kmers = 0, n_pass = 0, n_new = 0;
+	const unsigned lane = threadIdx.x & 31;
+
+	for (int j = 0; j < CNT_CHUNK + halo; ++j) {
+		const uint32_t c = s_code[base + j];
+		bool pend = false, pass = false;
+		uint64_t y[2] = {0, 0};
+		BloomProbe pr;
+		pr.blk = 0, pr.h1 = pr.h2 = 0;
+		if ((c & 7) < 4) {
+			bfc_kmer_append(k, x, c & 3);
+			qmer = (qmer << 1 | (c >> 3)) & mask;
+			if (++l >= k && j >= halo) {
+				const uint64_t hash = bfc_kmer_hash(k, x, y);
+				pr = bloom_locate(hash, p.bf.n_shift);
+				const int cnt = bloom_count_set<false>(p.bf.w + (pr.blk << 4), pr, p.bf.n_hashes);
+				pass = cnt == p.bf.n_hashes;
+				pend = !pass;
+				++n_kmers;
+			}
+		} else l = 0, qmer = 0, x[0] = x[1] = x[2] = x[3] = 0;
+
+		// warp-aggregated append of the pending occurrences (the loop is uniform: all lanes are here)
+		const unsigned pm = __ballot_sync(0xffffffffu, pend);
+		if (pm) {
+			unsigned long long at = 0;
+			if (lane == (unsigned)(__ffs(pm) - 1)) at = atomicAdd(p.ctr, (unsigned long long)__popc(pm));
+			at = __shfl_sync(0xffffffffu, at, __ffs(pm) - 1);
+			if (pend) {
+				at += __popc(pm & ((1u << lane) - 1));
+				p.pend_y0[at] = y[0] | (unsigned long long)(qmer == mask) << 63;
+				p.pend_y1[at] = y[1];
+				p.pend_t[at] = (uint32_t)(seg0 + base + j - halo);
+				uint32_t *w0 = p.bf.w + (pr.blk << 4);
+				if (atomicOr(w0, 1u) & 1u) atomicOr(w0, 2u);
+			}
+		}
+		if (pass) {
+			++n_pass;
+			if (p.tab.slots) n_new += tab_upsert(p.tab, y[0], y[1], qmer == mask) == 1;
+			else {
+				const BloomProbe ph = bloom_locate(hash_from_y(k, y[0], y[1]), p.bf_high.n_shift);
+				bloom_set_atomic(p.bf_high.w + (ph.blk << 4), ph, p.bf_high.n_hashes);
+			}
+		}
+	}
+	block_add(p.ctr + 1, n_kmers);
+	block_add(p.ctr + 2, n_pass);
+	if (p.tab.slots) block_add(p.tab.counters, n_new);
+}
+
+__global__ void __launch_bounds__(256) k_count_resolve(CountParams p, uint64_t n_pending)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned lane = threadIdx.x & 31;
+	bool conflict = false;
+	uint64_t blk = 0;
+	if (i < n_pending) {
+		const uint64_t y0 = p.pend_y0[i] & ~(1ULL << 63), y1 = p.pend_y1[i];
+		const BloomProbe pr = bloom_locate(hash_from_y(p.k, y0, y1), p.bf.n_shift);
+		uint32_t *w = p.bf.w + (pr.blk << 4);
+		blk = pr.blk;
+		if (__ldcg(w) & 2u) conflict = true;
+		else { // the only pending occurrence of this block: sets at least one new bit => does not pass
+			bloom_set_atomic(w, pr, p.bf.n_hashes);
+			atomicAnd(w, ~1u);
+		}
+	}
+	const unsigned cm = __ballot_sync(0xffffffffu, conflict);
+	if (cm) {
+		unsigned long long at = 0;
+		if (lane == (unsigned)(__ffs(cm) - 1)) at = atomicAdd(p.ctr + 3, (unsigned long long)__popc(cm));
+		at = __shfl_sync(0xffffffffu, at, __ffs(cm) - 1);
+		if (conflict) {
+			at += __popc(cm & ((1u << lane) - 1));
+			p.conf_key[at] = blk << 32 | p.pend_t[i];
+			p.conf_val[at] = (uint32_t)i;
+		}
+	}
+}
+
+__global__ void __launch_bounds__(256) k_count_replay(CountParams p, const unsigned long long *key, const uint32_t *val, uint64_t n)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned long long n_pass = 0, n_new = 0;
+	if (i < n) {
+		const uint64_t blk = key[i] >> 32;
+		if (i == 0 || (key[i - 1] >> 32) != blk) { // head of the block's run: replay it in stream order
+			volatile uint32_t *w = p.bf.w + (blk << 4);
+			const int H = p.bf.n_hashes;
+			for (uint64_t j = i; j < n && (key[j] >> 32) == blk; ++j) {
+				const uint32_t r = val[j];
+				const uint64_t y0f = p.pend_y0[r], y0 = y0f & ~(1ULL << 63), y1 = p.pend_y1[r];
+				const int is_high = (int)(y0f >> 63);
+				const uint64_t hash = hash_from_y(p.k, y0, y1);
+				const BloomProbe pr = bloom_locate(hash, p.bf.n_shift);
+				// reference bbf.c:35-42: test-then-set each probe
+				int z = pr.h1, done = 0, cnt = 0;
+				while (done < H) {
+					if (z >= 8) {
+						const uint32_t bit = 1u << (z & 31), v = w[z >> 5];
+						cnt += (v & bit) != 0;
+						w[z >> 5] = v | bit;
+						++done;
+					}
+					z = (z + pr.h2) & BFC_BLK_MASK;
+				}
+				if (cnt == H) { // reference count.c:60
+					++n_pass;
+					if (p.tab.slots) n_new += tab_upsert(p.tab, y0, y1, is_high) == 1;
+					else {
+						const BloomProbe ph = bloom_locate(hash, p.bf_high.n_shift);
+						bloom_set_atomic(p.bf_high.w + (ph.blk << 4), ph, p.bf_high.n_hashes);
+					}
+				}
+			}
+			w[0] = w[0] & ~3u; // release the block's marker bits
+		}
+	}
+	block_add(p.ctr + 2, n_pass);
+	if (p.tab.slots) block_add(p.tab.counters, n_new);
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static uint64_t sub_batch_positions(const bfc_opt_t *opt)
+{
+	const char *e = getenv("BFC_B200_SUBBATCH");
+	if (e && atoll(e) >= 1024) return (uint64_t)atoll(e);
+	// conflicts cost a sort: keep the expected number of pending occurrences per Bloom
+	// block well below 1 (2^(b-9) blocks), within [2^20, 2^26] positions per sub-batch
+	int lg = opt->bf_shift - BFC_BLK_SHIFT - 2;
+	if (lg < 20) lg = 20;
+	if (lg > 26) lg = 26;
+	return 1ULL << lg;
+}
+
+extern "C" int bfcg_count_batch(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, bfc_ch_t *ch,
+                                const bfcg_batch_t *batch, bfcg_stats_t *stats)
+{
+	int r;
+	if ((r = bfcg_rt_init()) != BFCG_OK) return r;
+	BfcgRuntime &rt = bfcg_rt();
+	if (!opt || !bf || !batch || (ch == 0) == (bf_high == 0) || opt->k < 1 || opt->k > BFC_MAX_KMER ||
+		(ch && bfc_ch_get_k(ch) != opt->k) || bf->n_hashes < 1 || (bf_high && (bf_high->n_shift != bf->n_shift || bf_high->n_hashes != bf->n_hashes)))
+		return bfcg_fail(__func__, "invalid arguments", cudaSuccess), BFCG_ERR_ARG;
+	if (batch->n_bytes == 0) return BFCG_OK;
+
+	const uint64_t sub = sub_batch_positions(opt);
+	const uint64_t halo = opt->k - 1;
+	const uint64_t win_max = std::min<uint64_t>(sub, batch->n_bytes) + halo;
+	const bool host = batch->where == BFCG_HOST;
+
+	// carve the arena for the worst case (every occurrence pending and conflicting)
+	size_t temp_bytes = 0;
+	cub::DeviceRadixSort::SortPairs((void*)0, temp_bytes, (const unsigned long long*)0, (unsigned long long*)0,
+	                                (const uint32_t*)0, (uint32_t*)0, (size_t)win_max, 0, 64, rt.stream);
+	size_t o_seq = 0, o_qual = 0, o_y0, o_y1, o_t, o_ck0, o_ck1, o_cv0, o_cv1, o_tmp, o_ctr, tot = 0;
+	if (host) { o_seq = tot; tot = align_up(tot + win_max, 256); o_qual = tot; tot = align_up(tot + win_max, 256); }
+	o_y0 = tot; tot = align_up(tot + win_max * 8, 256);
+	o_y1 = tot; tot = align_up(tot + win_max * 8, 256);
+	o_t = tot; tot = align_up(tot + win_max * 4, 256);
+	o_ck0 = tot; tot = align_up(tot + win_max * 8, 256);
+	o_ck1 = tot; tot = align_up(tot + win_max * 8, 256);
+	o_cv0 = tot; tot = align_up(tot + win_max * 4, 256);
+	o_cv1 = tot; tot = align_up(tot + win_max * 4, 256);
+	o_tmp = tot; tot = align_up(tot + temp_bytes, 256);
+	o_ctr = tot; tot += 256;
+	uint8_t *a = (uint8_t*)bfcg_arena(tot);
+	if (!a) return BFCG_ERR_NOMEM;
+
+	CountParams p;
+	memset(&p, 0, sizeof(p));
+	p.k = opt->k, p.q = opt->q;
+	p.bf = bloom_view(bf);
+	if (bf_high) p.bf_high = bloom_view(bf_high);
+	p.pend_y0 = (unsigned long long*)(a + o_y0), p.pend_y1 = (unsigned long long*)(a + o_y1), p.pend_t = (uint32_t*)(a + o_t);
+	p.ctr = (unsigned long long*)(a + o_ctr);
+	p.conf_key = (unsigned long long*)(a + o_ck0), p.conf_val = (uint32_t*)(a + o_cv0);
+	unsigned long long *ck1 = (unsigned long long*)(a + o_ck1);
+	uint32_t *cv1 = (uint32_t*)(a + o_cv1);
+
+	BfcgTimer timer(stats);
+	for (uint64_t s = 0; s < batch->n_bytes; s += sub) {
+		const uint64_t e = std::min(batch->n_bytes, s + sub);
+		const uint64_t w0 = s >= halo ? s - halo : 0; // window start: k-1 bases of warm-up before s
+		const uint64_t len = e - w0;
+		if (host) {
+			BFCG_CUDA(cudaMemcpyAsync(a + o_seq, batch->seq + w0, len, cudaMemcpyHostToDevice, rt.stream));
+			if (batch->qual) BFCG_CUDA(cudaMemcpyAsync(a + o_qual, batch->qual + w0, len, cudaMemcpyHostToDevice, rt.stream));
+			p.seq = a + o_seq, p.qual = batch->qual ? a + o_qual : 0;
+		} else p.seq = batch->seq + w0, p.qual = batch->qual ? batch->qual + w0 : 0;
+		p.len = len, p.emit_from = s - w0;
+		if (ch) {
+			if ((r = bfcg_tab_reserve(ch, e - s)) != BFCG_OK) return r;
+			p.tab = tab_view(ch);
+		}
+		BFCG_CUDA(cudaMemsetAsync(p.ctr, 0, 64, rt.stream));
+		const unsigned grid = (unsigned)((e - s + CNT_SEG - 1) / CNT_SEG);
+		k_count_probe<<<grid, CNT_THREADS, 0, rt.stream>>>(p);
+		BFCG_LAUNCH_CHECK();
+		unsigned long long c[4];
+		BFCG_CUDA(cudaMemcpyAsync(c, p.ctr, sizeof(c), cudaMemcpyDeviceToHost, rt.stream));
+		BFCG_CUDA(cudaStreamSynchronize(rt.stream));
+		const uint64_t n_pending = c[0];
+		uint64_t n_conflict = 0;
+		if (n_pending) {
+			k_count_resolve<<<(unsigned)((n_pending + 255) / 256), 256, 0, rt.stream>>>(p, n_pending);
+			BFCG_LAUNCH_CHECK();
+			BFCG_CUDA(cudaMemcpyAsync(c, p.ctr, sizeof(c), cudaMemcpyDeviceToHost, rt.stream));
+			BFCG_CUDA(cudaStreamSynchronize(rt.stream));
+			n_conflict = c[3];
+		}
+		if (n_conflict) {
+			int pos_bits = 1;
+			while ((1ULL << pos_bits) < len) ++pos_bits;
+			size_t tb = temp_bytes;
+			BFCG_CUDA(cub::DeviceRadixSort::SortPairs(a + o_tmp, tb, (const unsigned long long*)p.conf_key, ck1,
+			                                          (const uint32_t*)p.conf_val, cv1, (size_t)n_conflict, 0,
+			                                          32 + (bf->n_shift - BFC_BLK_SHIFT), rt.stream));
+			rt.n_launches += 1 + (32 + bf->n_shift - BFC_BLK_SHIFT + 7) / 8; // histogram + one onesweep pass per 8 bits
+			k_count_replay<<<(unsigned)((n_conflict + 255) / 256), 256, 0, rt.stream>>>(p, ck1, cv1, n_conflict);
+			BFCG_LAUNCH_CHECK();
+			BFCG_CUDA(cudaMemcpyAsync(c, p.ctr, sizeof(c), cudaMemcpyDeviceToHost, rt.stream));
+			BFCG_CUDA(cudaStreamSynchronize(rt.stream));
+		}
+		if (ch && (r = bfcg_tab_drain_deferred(ch)) != BFCG_OK) return r;
+		if (stats) {
+			stats->n_kmers += c[1], stats->n_pass += c[2];
+			stats->n_pending += n_pending, stats->n_conflict += n_conflict;
+		}
+	}
+	timer.stop();
+	BFCG_CUDA(cudaStreamSynchronize(rt.stream));
+	return BFCG_OK;
+}

@@ -1,0 +1,108 @@
+/* bfc_b200.h -- batch-level C ABI of the B200 count / correct / trim engine.
+ *
+ * This is the boundary a host program (the `bfc` CLI in csrc/, the Python mirror
+ * in bfc_b200/, or a maintainer's patch to the reference) binds:
+ * plain pointers and sizes, no C++ or torch types.  It replaces what runs INSIDE the
+ * reference's two parallel loops:
+ *
+ *   bfcg_count_batch    <- kt_for(..., worker_count, ...)   reference count.c:106 (+ :54-89, :116-117)
+ *   bfcg_correct_batch  <- kt_for(..., worker_ec, ...)      reference correct.c:587 (+ :388-472, :533-553)
+ *   bfcg_trim_batch     <- worker_ec, filter_mode branch    reference correct.c:554-569 (+ :478-497)
+ *
+ * Results are those of the reference run with `-t1` (strict read order), bit for bit.
+ * There is no CPU fallback: every entry point returns BFCG_ERR_CUDA (and prints a
+ * `[E::...]` line) when no CUDA device / kernel image is usable.
+ *
+ * Host batch layout ("reads back to back"):
+ *   read i occupies seq[off[i] .. off[i+1]-2]; seq[off[i+1]-1] is a 0 terminator.
+ *   qual uses the same offsets; qual == NULL means no read has qualities; a read
+ *   without quality inside a batch that has a qual array carries 0xFF in all of
+ *   its qual bytes.  off[] has n_reads+1 entries; off[n_reads] = total bytes.
+ */
+#ifndef BFC_B200_ABI_H
+#define BFC_B200_ABI_H
+
+#include <stdint.h>
+#include "bfc.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { BFCG_OK = 0, BFCG_ERR_CUDA = -1, BFCG_ERR_ARG = -2, BFCG_ERR_NOMEM = -3, BFCG_ERR_OVERFLOW = -4 };
+
+enum { BFCG_HOST = 0, BFCG_DEVICE = 1 };
+
+typedef struct {
+	int64_t n_reads;
+	uint64_t n_bytes;        /* = off[n_reads]: total bytes of seq (and of qual) */
+	int where;               /* BFCG_HOST: pointers are host memory; BFCG_DEVICE: device memory */
+	const uint64_t *off;     /* n_reads + 1 (not needed by bfcg_count_batch) */
+	uint8_t *seq;            /* n_bytes bytes; edited in place by bfcg_correct_batch */
+	uint8_t *qual;           /* same, or NULL */
+} bfcg_batch_t;
+
+/* counters filled by the batch calls (all cumulative adds) */
+typedef struct {
+	uint64_t n_kmers;        /* k-mer occurrences enumerated                               */
+	uint64_t n_pass;         /* occurrences whose Bloom bits were all set (count.c:60)      */
+	uint64_t n_pending;      /* occurrences that set at least one new bit                   */
+	uint64_t n_conflict;     /* of those, resolved by the ordered replay                    */
+	uint64_t n_lookups;      /* bfc_ch_kmer_occ / bfc_bf_get calls made by correct / trim   */
+	uint64_t n_redo;         /* reads re-run with a larger search scratch                   */
+	uint64_t n_launches;     /* kernels launched                                            */
+	double   kernel_ms;      /* device time of those kernels (CUDA events), when timing on  */
+} bfcg_stats_t;
+
+/* device selection / info ------------------------------------------------------- */
+int  bfcg_device_count(void);
+int  bfcg_set_device(int dev);                 /* default 0 (or LOCAL_RANK when set) */
+int  bfcg_sync(void);
+void bfcg_set_timing(int on);                  /* time kernels with CUDA events into stats.kernel_ms */
+const char *bfcg_last_error(void);
+
+/* count: insert every k-mer of the batch, in read order, as count.c:54-89 does.
+ * bf: first Bloom filter; exactly one of ch / bf_high is non-NULL
+ * (normal mode / opt->filter_mode). */
+int bfcg_count_batch(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, bfc_ch_t *ch,
+                     const bfcg_batch_t *batch, bfcg_stats_t *stats);
+
+/* correct: bfc_ec1 on every read (correct.c:388-472).  seq/qual are rewritten in
+ * place exactly as there (untouched on failure); aux[2*i] = s->aux, aux[2*i+1] =
+ * s->aux2 as packed by worker_ec (correct.c:552-553).  `mode` is the return value
+ * of bfc_ch_hist.  aux lives where the batch lives (host or device). */
+int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int mode,
+                       bfcg_batch_t *batch, uint32_t *aux, bfcg_stats_t *stats);
+
+/* trim: max_streak + the keep rule (correct.c:478-497, 555-569).  keep[i] = 1 and
+ * the kept bases are [tstart[i], tend[i]), or keep[i] = 0.  The caller moves the
+ * bytes (as worker_ec's memmove does). */
+int bfcg_trim_batch(const bfc_opt_t *opt, const bfc_bf_t *bf_high, const bfcg_batch_t *batch,
+                    uint8_t *keep, int32_t *tstart, int32_t *tend, bfcg_stats_t *stats);
+
+/* device memory helpers for callers that keep batches resident in HBM -------------- */
+void *bfcg_dev_alloc(uint64_t bytes);
+void  bfcg_dev_free(void *p);
+int   bfcg_h2d(void *dst, const void *src, uint64_t bytes);
+int   bfcg_d2h(void *dst, const void *src, uint64_t bytes);
+void *bfcg_host_alloc_pinned(uint64_t bytes);
+void  bfcg_host_free_pinned(void *p);
+
+/* inspection (tests, dumps) --------------------------------------------------------- */
+int      bfcg_bf_download(const bfc_bf_t *bf, uint8_t *dst);          /* 2^(n_shift-3) bytes */
+int      bfcg_bf_upload(bfc_bf_t *bf, const uint8_t *src);
+int      bfcg_bf_clear(bfc_bf_t *bf);
+/* all entries as (sub-table index, key50<<14 | val14), sorted by (sub, key); pass NULLs to get n */
+uint64_t bfcg_ch_export(const bfc_ch_t *ch, uint32_t *sub, uint64_t *key);
+int      bfcg_ch_l_pre(const bfc_ch_t *ch);
+int      bfcg_ch_capacity_log2(const bfc_ch_t *ch);
+int      bfcg_ch_clear(bfc_ch_t *ch);
+int      bfcg_ch_reserve(bfc_ch_t *ch, uint64_t n_keys);              /* pre-size for n_keys distinct keys */
+/* batched lookups: y = n pairs of k-bit words (bfc_kmer_hash output); out[i] = bfc_ch_get */
+int      bfcg_ch_get_batch(const bfc_ch_t *ch, int where, uint64_t n, const uint64_t *y, int32_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

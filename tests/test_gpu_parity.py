@@ -1,0 +1,199 @@
+"""GPU (B200): the CUDA path, called through the C ABI (include/bfc_b200.h), against
+ (a) the golden fixtures produced by the unmodified reference, and
+ (b) the CPU oracle on seeded random inputs,
+bit-exact: identical Bloom bytes, identical table entries (identity, cnt8, high6),
+byte-identical corrected / trimmed FASTQ including the ec:Z: tag."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import orc
+from golden_util import CASES, Case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def bfc():
+    import bfc_b200
+    L = bfc_b200.lib()
+    assert L.bfcg_device_count() > 0, "no CUDA device: the product has no CPU fallback"
+    return bfc_b200
+
+
+def as_bfc_opt(bfc, o):
+    return bfc.make_opt(**{n: getattr(o, n) for n, _ in orc.Opt._fields_})
+
+
+def mark_noqual(recs, qual, off):
+    """Reads without quality carry 0xFF bytes in the flat layout."""
+    if qual is None:
+        return None
+    q = qual.copy()
+    for i, r in enumerate(recs):
+        if r[3] is None:
+            q[int(off[i]):int(off[i + 1]) - 1] = 0xFF
+    return q
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_count_correct(bfc, name):
+    c = Case(name)
+    qual = mark_noqual(c.recs, c.qual, c.off)
+    e = bfc.Engine(as_bfc_opt(bfc, c.opt()))
+    try:
+        e.count(c.seq, qual, c.off)
+        assert hashlib.sha256(e.bloom_bytes().tobytes()).hexdigest() == c.meta["bloom_sha256"]
+        sub, key = e.table()
+        assert len(key) == c.meta["table_n"] == e.n_distinct()
+        assert np.array_equal(sub, c.sub) and np.array_equal(key, c.key)
+        s, q, aux = e.correct(c.seq, qual, c.off)
+        assert orc.format_corrected(c.recs, s, q, c.off, aux) == c.corrected
+    finally:
+        e.close()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_trim(bfc, name):
+    c = Case(name)
+    qual = mark_noqual(c.recs, c.qual, c.off)
+    e = bfc.Engine(as_bfc_opt(bfc, c.opt(filter_mode=1)))
+    try:
+        e.count(c.seq, qual, c.off)
+        assert hashlib.sha256(e.bloom_bytes().tobytes()).hexdigest() == c.meta["bloom_sha256"]
+        assert hashlib.sha256(e.bloom_bytes(high=True).tobytes()).hexdigest() == c.meta["bf_high_sha256"]
+        keep, ts, te = e.trim(c.seq, c.off)
+        assert orc.format_trimmed(c.recs, c.seq, c.qual, c.off, keep, ts, te) == c.trimmed
+    finally:
+        e.close()
+
+
+def synth_batch(G, N, L, seed, err=0.01, repeat=0.0):
+    from bfc_b200 import synth
+    genome = synth.make_genome(G, seed, repeat)
+    seq, qual = synth.make_reads(genome, N, L, seed, err)
+    return synth.concat_batch(seq, qual)
+
+
+@pytest.mark.parametrize("k,b,G,N,L,repeat,sub", [
+    (21, 20, 30000, 20000, 100, 0.0, None),     # tiny filter: almost every occurrence conflicts
+    (31, 26, 200000, 60000, 100, 0.2, None),
+    (33, 30, 300000, 60000, 150, 0.3, 1 << 18),  # several sub-batches, few conflicts
+    (55, 24, 100000, 30000, 150, 0.3, 1 << 17),
+    (63, 22, 50000, 12000, 151, 0.1, 50000),
+])
+def test_oracle_random(bfc, monkeypatch, k, b, G, N, L, repeat, sub):
+    if sub:
+        monkeypatch.setenv("BFC_B200_SUBBATCH", str(sub))
+    seq, qual, off = synth_batch(G, N, L, seed=k * 1000 + b, repeat=repeat)
+    o = orc.OracleRun(orc.make_opt(k=k, bf_shift=b))
+    e = bfc.Engine(bfc.make_opt(k=k, bf_shift=b))
+    try:
+        # two count batches: state carries over exactly
+        h = N // 2
+        cut = int(off[h])
+        o.count(seq[:cut], qual[:cut], off[:h + 1])
+        o.count(seq[cut:], qual[cut:], off[h:] - off[h])
+        e.count(seq[:cut], qual[:cut], off[:h + 1])
+        e.count(seq[cut:], qual[cut:], off[h:] - off[h])
+        assert np.array_equal(e.bloom_bytes(), o.bloom_bytes())
+        assert int(e.stats.n_kmers) == int(o.stats[0]) and int(e.stats.n_pass) == int(o.stats[1])
+        sub_o, key_o = o.table()
+        sub_e, key_e = e.table()
+        assert np.array_equal(sub_e, sub_o) and np.array_equal(key_e, key_o)
+        mo, co, ho = o.hist()
+        me, ce, he = e.hist()
+        assert mo == me and np.array_equal(co, ce) and np.array_equal(ho, he)
+        so, qo, ao, ctr = o.correct(seq, qual, off)
+        se, qe, ae = e.correct(seq, qual, off)
+        assert np.array_equal(ae, ao)
+        assert np.array_equal(se, so) and np.array_equal(qe, qo)
+        assert int(e.stats.n_lookups) == int(ctr[0])
+    finally:
+        e.close()
+        o.close()
+
+
+@pytest.mark.parametrize("k,b,H", [(31, 24, 4), (51, 25, 4), (27, 22, 9)])
+def test_oracle_random_trim(bfc, k, b, H):
+    seq, qual, off = synth_batch(100000, 30000, 120, seed=k + b)
+    o = orc.OracleRun(orc.make_opt(k=k, bf_shift=b, n_hashes=H, filter_mode=1))
+    e = bfc.Engine(bfc.make_opt(k=k, bf_shift=b, n_hashes=H, filter_mode=1))
+    try:
+        o.count(seq, qual, off)
+        e.count(seq, qual, off)
+        assert np.array_equal(e.bloom_bytes(), o.bloom_bytes())
+        assert np.array_equal(e.bloom_bytes(high=True), o.bloom_bytes(high=True))
+        ko, so, eo = o.trim(seq, off)
+        ke, se, ee = e.trim(seq, off)
+        assert np.array_equal(ke, ko) and np.array_equal(se, so) and np.array_equal(ee, eo)
+    finally:
+        e.close()
+        o.close()
+
+
+def test_small_search_stack_is_redone_on_gpu(bfc, monkeypatch):
+    """Reads whose search outgrows the per-thread stack are re-run by the same kernel with a
+    larger stack; results stay identical to the oracle."""
+    seq, qual, off = synth_batch(20000, 8000, 150, seed=99, err=0.03, repeat=0.5)
+    o = orc.OracleRun(orc.make_opt(k=21, bf_shift=22))
+    e = bfc.Engine(bfc.make_opt(k=21, bf_shift=22))
+    try:
+        o.count(seq, qual, off)
+        e.count(seq, qual, off)
+        so, qo, ao, ctr = o.correct(seq, qual, off)
+        se, qe, ae = e.correct(seq, qual, off)
+        assert np.array_equal(ae, ao) and np.array_equal(se, so) and np.array_equal(qe, qo)
+        if int(ctr[2]) > 512:
+            assert int(e.stats.n_redo) > 0
+    finally:
+        e.close()
+        o.close()
+
+
+def test_reference_api_single_item(bfc):
+    """bfc_bf_insert/get, bfc_ch_insert/get/kmer_occ through one-element kernels (KATs from the reference)."""
+    import ctypes as C
+    from golden_util import kat
+    L = bfc.lib()
+    K = kat()
+    for v in K["bloom"][:2]:
+        bf = L.bfc_bf_init(v["n_shift"], v["n_hashes"])
+        rets = [int(L.bfc_bf_insert(bf, h)) for h in v["hashes"][:120]]
+        assert rets == v["insert_ret"][:120]
+        L.bfc_bf_destroy(bf)
+    assert not L.bfc_bf_init(8, 4)
+    for v in K["table"][:4]:
+        ch = L.bfc_ch_init(v["k"], v["l_pre"])
+        for i, op in enumerate(v["ops"][:12]):
+            y = (C.c_uint64 * 2)(*op["y"])
+            assert L.bfc_ch_get(ch, y) == op["get_before"]
+            for j in range(op["n_insert"]):
+                assert L.bfc_ch_insert(ch, y, (i + j) & 1 if i != 7 else 1, 1) == 0
+            assert L.bfc_ch_get(ch, y) == op["get_after"]
+        L.bfc_ch_destroy(ch)
+
+
+def test_cli_matches_reference_golden(bfc, tmp_path):
+    """The drop-in `bfc` binary end to end (FASTQ file -> stdout) against the reference's stdout."""
+    import gzip, subprocess
+    exe = os.path.join(os.path.dirname(bfc.lib_path()), "bfc")
+    for name in ("k31_edge", "k33_rep"):
+        c = Case(name)
+        fq = tmp_path / (name + ".fq")
+        fq.write_bytes(c.fastq)
+        args = ["-k", str(c.meta["k"]), "-b", str(c.meta["b"])] + c.meta["extra_args"]
+        out = subprocess.run([exe] + args + ["-t", "4", str(fq)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True).stdout
+        assert out == c.corrected
+        out = subprocess.run([exe] + args + ["-1", str(fq)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True).stdout
+        assert out == c.trimmed
+        # dump -> restore -> correct gives the same output; the dump holds the reference's keys
+        dump = tmp_path / (name + ".dump")
+        subprocess.run([exe] + args + ["-E", "-d", str(dump), str(fq)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True)
+        k, l_pre, sub, key = orc.parse_ref_dump(str(dump))
+        assert k == c.meta["table_k"] and l_pre == c.meta["table_l_pre"]
+        assert np.array_equal(sub, c.sub) and np.array_equal(key, c.key)
+        out = subprocess.run([exe] + args + ["-r", str(dump), str(fq)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True).stdout
+        assert out == c.corrected
