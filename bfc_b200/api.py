@@ -133,8 +133,27 @@ def lib():
     L.bfcg_ch_clear.argtypes = [C.c_void_p]
     L.bfcg_ch_reserve.argtypes = [C.c_void_p, C.c_uint64]
     L.bfcg_ch_get_batch.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
+    L.bfcg_kernel_times.argtypes = [C.POINTER(C.c_double), u64p, C.c_int]
+    L.bfcg_event_record.argtypes = [C.c_int]
+    L.bfcg_event_elapsed_ms.restype = C.c_double
+    L.bfcg_event_elapsed_ms.argtypes = [C.c_int, C.c_int]
+    L.bfcg_synth_genome.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
+    L.bfcg_synth_reads.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int64, C.c_int, C.c_double,
+                                   C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = L
     return L
+
+
+KERNEL_NAMES = ["count_probe", "count_resolve", "conflict_sort", "count_replay", "correct", "correct_redo", "trim",
+                "tab_rehash", "tab_hist", "tab_apply"]
+
+
+def kernel_times():
+    """{kernel: (ms, launches)} of device time accumulated since the last call (timing must be on)."""
+    ms = (C.c_double * 16)()
+    n = (C.c_uint64 * 16)()
+    k = lib().bfcg_kernel_times(ms, n, 16)
+    return {KERNEL_NAMES[i]: (ms[i], int(n[i])) for i in range(min(k, len(KERNEL_NAMES)))}
 
 
 def make_opt(**kw) -> Opt:

@@ -7,6 +7,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <vector>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -31,6 +32,24 @@ struct BfcgRuntime {
 	uint8_t *pin[2];
 	size_t pin_bytes[2];
 	int sm_count;
+	// per-kernel device timing (only when `timing`): event pairs resolved lazily
+	struct Span { int id; cudaEvent_t a, b; };
+	std::vector<Span> spans;
+	std::vector<cudaEvent_t> ev_pool;
+	double kt_ms[16];
+	uint64_t kt_n[16];
+	cudaEvent_t user_ev[8];
+};
+
+enum { KT_COUNT_PROBE = 0, KT_COUNT_RESOLVE, KT_COUNT_SORT, KT_COUNT_REPLAY, KT_CORRECT, KT_CORRECT_REDO,
+       KT_TRIM, KT_TAB_REHASH, KT_TAB_HIST, KT_TAB_APPLY, KT_N };
+
+int  bfcg_kt_begin(int id);   // records a start event on the stream when timing is on; returns a span index or -1
+void bfcg_kt_end(int idx);
+struct KTime { // RAII: time the launches enqueued while it is alive
+	int idx;
+	explicit KTime(int id) : idx(bfcg_kt_begin(id)) {}
+	~KTime() { bfcg_kt_end(idx); }
 };
 
 BfcgRuntime &bfcg_rt();

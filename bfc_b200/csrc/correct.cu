@@ -541,7 +541,7 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 		P.heap_cap = heap_cap, P.stack_cap = stack_cap0;
 		P.overflow = (uint32_t*)(a + o_ovf), P.ctr = (unsigned long long*)(a + o_ctr);
 		BFCG_CUDA(cudaMemsetAsync(P.ctr, 0, 64, rt.stream));
-		k_correct<<<(unsigned)(slots / threads), threads, 0, rt.stream>>>(P);
+		{ KTime kt(KT_CORRECT); k_correct<<<(unsigned)(slots / threads), threads, 0, rt.stream>>>(P); }
 		BFCG_LAUNCH_CHECK();
 		unsigned long long c[2];
 		BFCG_CUDA(cudaMemcpyAsync(c, P.ctr, sizeof(c), cudaMemcpyDeviceToHost, rt.stream));
@@ -562,7 +562,7 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 			BFCG_CUDA(cudaMemsetAsync(P.ctr, 0, 8, rt.stream));
 			EcParams Q = P;
 			Q.redo = redo, Q.n_reads = (int64_t)n_redo, Q.stack = big, Q.stack_cap = cap;
-			k_correct<<<(unsigned)(rs / 32), 32, 0, rt.stream>>>(Q);
+			{ KTime kt(KT_CORRECT_REDO); k_correct<<<(unsigned)(rs / 32), 32, 0, rt.stream>>>(Q); }
 			BFCG_LAUNCH_CHECK();
 			BFCG_CUDA(cudaMemcpyAsync(c, P.ctr, sizeof(c), cudaMemcpyDeviceToHost, rt.stream));
 			BFCG_CUDA(cudaStreamSynchronize(rt.stream));
@@ -603,7 +603,7 @@ extern "C" int bfcg_trim_batch(const bfc_opt_t *opt, const bfc_bf_t *bf_high, co
 		P.off = batch->off, P.seq = batch->seq, P.n_reads = n, P.bf = bloom_view(bf_high), P.k = opt->k, P.min_frac = opt->min_frac;
 		P.keep = keep, P.tstart = tstart, P.tend = tend, P.ctr = ctr;
 		BFCG_CUDA(cudaMemsetAsync(ctr, 0, 64, rt.stream));
-		k_trim<<<(unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)rt.sm_count * 8), 256, 0, rt.stream>>>(P);
+		{ KTime kt(KT_TRIM); k_trim<<<(unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)rt.sm_count * 8), 256, 0, rt.stream>>>(P); }
 		BFCG_LAUNCH_CHECK();
 		BFCG_CUDA(cudaMemcpyAsync(c, ctr, sizeof(c), cudaMemcpyDeviceToHost, rt.stream));
 		timer.stop();
@@ -633,7 +633,7 @@ extern "C" int bfcg_trim_batch(const bfc_opt_t *opt, const bfc_bf_t *bf_high, co
 		P.off = (const uint64_t*)(a + o_off), P.seq = a + o_seq, P.n_reads = nr, P.bf = bloom_view(bf_high), P.k = opt->k, P.min_frac = opt->min_frac;
 		P.keep = a + o_keep, P.tstart = (int32_t*)(a + o_ts), P.tend = (int32_t*)(a + o_te), P.ctr = (unsigned long long*)(a + o_ctr);
 		BFCG_CUDA(cudaMemsetAsync(P.ctr, 0, 64, rt.stream));
-		k_trim<<<(unsigned)std::min<int64_t>((nr + 255) / 256, (int64_t)rt.sm_count * 8), 256, 0, rt.stream>>>(P);
+		{ KTime kt(KT_TRIM); k_trim<<<(unsigned)std::min<int64_t>((nr + 255) / 256, (int64_t)rt.sm_count * 8), 256, 0, rt.stream>>>(P); }
 		BFCG_LAUNCH_CHECK();
 		unsigned long long c[2];
 		BFCG_CUDA(cudaMemcpyAsync(c, P.ctr, sizeof(c), cudaMemcpyDeviceToHost, rt.stream));

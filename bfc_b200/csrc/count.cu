@@ -273,7 +273,7 @@ extern "C" int bfcg_count_batch(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf
 		}
 		BFCG_CUDA(cudaMemsetAsync(p.ctr, 0, 64, rt.stream));
 		const unsigned grid = (unsigned)((e - s + CNT_SEG - 1) / CNT_SEG);
-		k_count_probe<<<grid, CNT_THREADS, 0, rt.stream>>>(p);
+		{ KTime kt(KT_COUNT_PROBE); k_count_probe<<<grid, CNT_THREADS, 0, rt.stream>>>(p); }
 		BFCG_LAUNCH_CHECK();
 		unsigned long long c[4];
 		BFCG_CUDA(cudaMemcpyAsync(c, p.ctr, sizeof(c), cudaMemcpyDeviceToHost, rt.stream));
@@ -281,7 +281,7 @@ extern "C" int bfcg_count_batch(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf
 		const uint64_t n_pending = c[0];
 		uint64_t n_conflict = 0;
 		if (n_pending) {
-			k_count_resolve<<<(unsigned)((n_pending + 255) / 256), 256, 0, rt.stream>>>(p, n_pending);
+			{ KTime kt(KT_COUNT_RESOLVE); k_count_resolve<<<(unsigned)((n_pending + 255) / 256), 256, 0, rt.stream>>>(p, n_pending); }
 			BFCG_LAUNCH_CHECK();
 			BFCG_CUDA(cudaMemcpyAsync(c, p.ctr, sizeof(c), cudaMemcpyDeviceToHost, rt.stream));
 			BFCG_CUDA(cudaStreamSynchronize(rt.stream));
@@ -291,11 +291,13 @@ extern "C" int bfcg_count_batch(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf
 			int pos_bits = 1;
 			while ((1ULL << pos_bits) < len) ++pos_bits;
 			size_t tb = temp_bytes;
+			KTime *kts = new KTime(KT_COUNT_SORT);
 			BFCG_CUDA(cub::DeviceRadixSort::SortPairs(a + o_tmp, tb, (const unsigned long long*)p.conf_key, ck1,
 			                                          (const uint32_t*)p.conf_val, cv1, (size_t)n_conflict, 0,
 			                                          32 + (bf->n_shift - BFC_BLK_SHIFT), rt.stream));
+			delete kts;
 			rt.n_launches += 1 + (32 + bf->n_shift - BFC_BLK_SHIFT + 7) / 8; // histogram + one onesweep pass per 8 bits
-			k_count_replay<<<(unsigned)((n_conflict + 255) / 256), 256, 0, rt.stream>>>(p, ck1, cv1, n_conflict);
+			{ KTime kt(KT_COUNT_REPLAY); k_count_replay<<<(unsigned)((n_conflict + 255) / 256), 256, 0, rt.stream>>>(p, ck1, cv1, n_conflict); }
 			BFCG_LAUNCH_CHECK();
 			BFCG_CUDA(cudaMemcpyAsync(c, p.ctr, sizeof(c), cudaMemcpyDeviceToHost, rt.stream));
 			BFCG_CUDA(cudaStreamSynchronize(rt.stream));

@@ -110,7 +110,7 @@ static int tab_resize(bfc_ch_s *ch, int new_rbits)
 	BFCG_CUDA(cudaMemsetAsync(fail, 0, 8, rt.stream));
 	TabView nt = tab_view(ch);
 	nt.slots = ns, nt.rbits = new_rbits;
-	k_tab_rehash<<<rt.sm_count * 8, 256, 0, rt.stream>>>(ch->slots, ch->rbits, tab_capacity(ch), nt, fail);
+	{ KTime kt(KT_TAB_REHASH); k_tab_rehash<<<rt.sm_count * 8, 256, 0, rt.stream>>>(ch->slots, ch->rbits, tab_capacity(ch), nt, fail); }
 	BFCG_LAUNCH_CHECK();
 	BFCG_CUDA(cudaMemcpyAsync(&h_fail, fail, 8, cudaMemcpyDeviceToHost, rt.stream));
 	BFCG_CUDA(cudaStreamSynchronize(rt.stream));
@@ -275,7 +275,7 @@ int bfc_ch_hist(const bfc_ch_t *ch, uint64_t cnt[256], uint64_t high[64])
 	unsigned long long *d = (unsigned long long*)bfcg_arena(320 * 8), h[320];
 	if (!d) return -1;
 	cudaMemsetAsync(d, 0, 320 * 8, rt.stream);
-	k_tab_hist<<<rt.sm_count * 8, 256, 0, rt.stream>>>(ch->slots, tab_capacity(ch), d);
+	{ KTime kt(KT_TAB_HIST); k_tab_hist<<<rt.sm_count * 8, 256, 0, rt.stream>>>(ch->slots, tab_capacity(ch), d); }
 	++rt.n_launches;
 	cudaMemcpyAsync(h, d, 320 * 8, cudaMemcpyDeviceToHost, rt.stream);
 	if (cudaStreamSynchronize(rt.stream) != cudaSuccess) { bfcg_fail(__func__, "kernel", cudaGetLastError()); return -1; }

@@ -43,6 +43,42 @@ int bfcg_rt_init()
 	return BFCG_OK;
 }
 
+static cudaEvent_t ev_get()
+{
+	cudaEvent_t e;
+	if (!g_rt.ev_pool.empty()) { e = g_rt.ev_pool.back(); g_rt.ev_pool.pop_back(); return e; }
+	cudaEventCreate(&e);
+	return e;
+}
+
+int bfcg_kt_begin(int id)
+{
+	if (!g_rt.timing) return -1;
+	BfcgRuntime::Span s;
+	s.id = id, s.a = ev_get(), s.b = ev_get();
+	cudaEventRecord(s.a, g_rt.stream);
+	g_rt.spans.push_back(s);
+	return (int)g_rt.spans.size() - 1;
+}
+
+void bfcg_kt_end(int idx)
+{
+	if (idx >= 0) cudaEventRecord(g_rt.spans[idx].b, g_rt.stream);
+}
+
+static void kt_collect()
+{
+	if (g_rt.spans.empty()) return;
+	cudaStreamSynchronize(g_rt.stream);
+	for (size_t i = 0; i < g_rt.spans.size(); ++i) {
+		float ms = 0;
+		const BfcgRuntime::Span &s = g_rt.spans[i];
+		if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) g_rt.kt_ms[s.id] += ms, ++g_rt.kt_n[s.id];
+		g_rt.ev_pool.push_back(s.a), g_rt.ev_pool.push_back(s.b);
+	}
+	g_rt.spans.clear();
+}
+
 void *bfcg_arena(size_t bytes)
 {
 	if (bytes <= g_rt.arena_bytes) return g_rt.arena;
@@ -99,6 +135,34 @@ int bfcg_sync(void)
 }
 
 void bfcg_set_timing(int on) { g_rt.timing = on != 0; }
+
+// per-kernel device time since the last call (indices: KT_* in common.cuh); resets the accumulators
+int bfcg_kernel_times(double *ms, uint64_t *launches, int n)
+{
+	kt_collect();
+	for (int i = 0; i < n && i < 16; ++i) ms[i] = g_rt.kt_ms[i], launches[i] = g_rt.kt_n[i];
+	memset(g_rt.kt_ms, 0, sizeof(g_rt.kt_ms));
+	memset(g_rt.kt_n, 0, sizeof(g_rt.kt_n));
+	return KT_N;
+}
+
+// step timing on the engine's own stream (torch.cuda.Event only sees torch's stream)
+int bfcg_event_record(int slot)
+{
+	if (bfcg_rt_init() != BFCG_OK || slot < 0 || slot >= 8) return BFCG_ERR_ARG;
+	if (!g_rt.user_ev[slot]) BFCG_CUDA(cudaEventCreate(&g_rt.user_ev[slot]));
+	BFCG_CUDA(cudaEventRecord(g_rt.user_ev[slot], g_rt.stream));
+	return BFCG_OK;
+}
+
+double bfcg_event_elapsed_ms(int a, int b)
+{
+	float ms = -1;
+	if (a < 0 || b < 0 || a >= 8 || b >= 8 || !g_rt.user_ev[a] || !g_rt.user_ev[b]) return -1;
+	if (cudaEventSynchronize(g_rt.user_ev[b]) != cudaSuccess) return -1;
+	if (cudaEventElapsedTime(&ms, g_rt.user_ev[a], g_rt.user_ev[b]) != cudaSuccess) return -1;
+	return ms;
+}
 
 const char *bfcg_last_error(void) { return g_rt.err; }
 

@@ -103,3 +103,46 @@ def concat_batch(seq: np.ndarray, qual: np.ndarray | None):
         q = q.reshape(-1)
     offsets = (np.arange(N + 1, dtype=np.uint64) * np.uint64(L + 1))
     return s.reshape(-1), q, offsets
+
+
+# ----------------------------------------------------------------------------- counter-based twin of csrc/synth.cu
+
+def _splitmix64(x: np.ndarray) -> np.ndarray:
+    with np.errstate(over="ignore"):
+        x = x + np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return x ^ (x >> np.uint64(31))
+
+
+def cb_genome(G: int, seed: int, lo: int = 0, hi: int | None = None) -> np.ndarray:
+    """genome[lo:hi] as codes 0..3 -- same values as bfcg_synth_genome."""
+    hi = G if hi is None else hi
+    with np.errstate(over="ignore"):
+        i = np.arange(lo, hi, dtype=np.uint64) + np.uint64(seed) * np.uint64(0x632BE59BD9B4E019)
+    return (_splitmix64(i) >> np.uint64(62)).astype(np.uint8)
+
+
+def cb_reads(G: int, seed: int, first_read: int, n_reads: int, L: int, err: float = 0.01, n_rate: float = 2e-4,
+             genome_seed: int | None = None):
+    """(seq, qual) ASCII arrays of shape (n_reads, L) -- same values as bfcg_synth_reads.
+    The genome is evaluated lazily at the positions the reads cover, so a 3 Gb genome needs no memory."""
+    gseed = seed if genome_seed is None else genome_seed
+    with np.errstate(over="ignore"):
+        r = (np.arange(n_reads, dtype=np.uint64) + np.uint64(first_read)) * np.uint64(0xD6E8FEB86659FD93)
+        h = _splitmix64(np.uint64(seed) ^ r)
+        start = h % np.uint64(G - L + 1)
+        strand = (_splitmix64(h) & np.uint64(1)).astype(bool)
+        j = np.arange(L, dtype=np.uint64)
+        pos = np.where(strand[:, None], start[:, None] + np.uint64(L - 1) - j[None, :], start[:, None] + j[None, :])
+        g = (_splitmix64(pos + np.uint64(gseed) * np.uint64(0x632BE59BD9B4E019)) >> np.uint64(62)).astype(np.int64)
+        c = np.where(strand[:, None], 3 - g, g)
+        u = _splitmix64(h[:, None] ^ ((j[None, :] + np.uint64(1)) * np.uint64(0xA24BAED4963EE407)))
+    is_err = (u & np.uint64(0xFFFF)).astype(np.int64) < int(err * 65536.0 + 0.5)
+    c = np.where(is_err, (c + 1 + ((u >> np.uint64(16)) & np.uint64(0xFF)).astype(np.int64) % 3) & 3, c)
+    q = np.where(is_err, 2 + ((u >> np.uint64(28)) & np.uint64(0xFF)).astype(np.int64) % 18,
+                 25 + ((u >> np.uint64(24)) & np.uint64(15)).astype(np.int64))
+    is_n = ((u >> np.uint64(40)) & np.uint64(0xFFFFF)).astype(np.int64) < int(n_rate * 1048576.0 + 0.5)
+    seq = np.where(is_n, np.uint8(ord("N")), _ACGT[c]).astype(np.uint8)
+    qual = (q + 33).astype(np.uint8)
+    return seq, qual

@@ -60,6 +60,13 @@ int  bfcg_set_device(int dev);                 /* default 0 (or LOCAL_RANK when 
 int  bfcg_sync(void);
 void bfcg_set_timing(int on);                  /* time kernels with CUDA events into stats.kernel_ms */
 const char *bfcg_last_error(void);
+/* per-kernel device time accumulated since the last call (needs bfcg_set_timing(1)); indices:
+ * 0 count_probe 1 count_resolve 2 conflict sort 3 count_replay 4 correct 5 correct redo 6 trim
+ * 7 table rehash 8 table hist 9 table deferred-apply.  Returns the number of valid entries. */
+int  bfcg_kernel_times(double *ms, uint64_t *launches, int n);
+/* CUDA events on the engine's stream: record into slot 0..7, elapsed ms between two slots */
+int  bfcg_event_record(int slot);
+double bfcg_event_elapsed_ms(int a, int b);
 
 /* count: insert every k-mer of the batch, in read order, as count.c:54-89 does.
  * bf: first Bloom filter; exactly one of ch / bf_high is non-NULL
@@ -100,6 +107,11 @@ int      bfcg_ch_clear(bfc_ch_t *ch);
 int      bfcg_ch_reserve(bfc_ch_t *ch, uint64_t n_keys);              /* pre-size for n_keys distinct keys */
 /* batched lookups: y = n pairs of k-bit words (bfc_kmer_hash output); out[i] = bfc_ch_get */
 int      bfcg_ch_get_batch(const bfc_ch_t *ch, int where, uint64_t n, const uint64_t *y, int32_t *out);
+
+/* synthetic input for HBM-resident benchmarks (csrc/synth.cu; numpy twin in bfc_b200/synth.py) */
+int bfcg_synth_genome(uint8_t *d_genome, uint64_t G, uint64_t seed);
+int bfcg_synth_reads(const uint8_t *d_genome, uint64_t G, uint64_t seed, uint64_t first_read, int64_t n_reads, int L,
+                     double err, double n_rate, uint8_t *d_seq, uint8_t *d_qual, uint64_t *d_off);
 
 #ifdef __cplusplus
 }
