@@ -145,7 +145,7 @@ def lib():
 
 
 KERNEL_NAMES = ["count_probe", "count_resolve", "conflict_sort", "count_replay", "correct", "correct_redo", "trim",
-                "tab_rehash", "tab_hist", "tab_apply"]
+                "tab_rehash", "tab_hist", "tab_apply", "enum", "ec_lookup"]
 
 
 def kernel_times():

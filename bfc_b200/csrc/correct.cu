@@ -1,28 +1,43 @@
 // correct.cu -- the correction phase: what the reference runs inside
 // kt_for(..., worker_ec, ...) (correct.c:587): bfc_ec1 per read (correct.c:388-472)
-// with its two bfc_ec1dir heap searches (correct.c:249-386), and the `-1` trim
-// lookup (max_streak, correct.c:478-497, keep rule :555-569).
+// with its two bfc_ec1dir heap searches (correct.c:249-386).
 //
-// One read per thread: the search is a chain of dependent table lookups, so
-// throughput comes from reads in flight, not from per-read speed.  Each thread owns a
-// fixed heap (max_heap + 4 entries are enough: the reference stops growing it at
-// max_heap, correct.c:349) and a fixed stack; a read whose stack overflows is re-run
-// by the same kernel with a larger stack (never on the CPU).
+// Three kernels per batch:
+//   K0 k_enum         (enum.cuh) canonical k-mer hash of every stream position
+//   K5 k_ec_lookup    bfc_ec_kcov's one-lookup-per-k-mer (correct.c:106) for the whole
+//                     batch at once: a thread does 36 independent table probes, results
+//                     go to occ16[position] through shared memory (coalesced both ways)
+//   K6 k_ec_read      one read per thread: per-base coverage flags, longest solid
+//                     island, rescue, the two heap searches, merge, rewrite.
 //
-// Pop/push order, klib heap tie-breaking (ksort.h:125-146) and every threshold follow
-// the reference exactly: the `ec:Z:` tag exposes max_heap / n_absent, so the search
-// internals are part of the byte-parity contract.
+// The search is a chain of dependent table lookups, so throughput comes from reads in
+// flight.  Two things keep a search step cheap without changing its result:
+//   * the heap lives in global memory, but while it holds a single state (the common,
+//     unbranched walk) that state stays in registers -- states enter the memory heap
+//     in exactly the reference's push order, so ties pop identically (ksort.h:125-146);
+//   * the lookup of the READ's own k-mer at a position (`os`, correct.c:299) is the
+//     value K5 already fetched whenever the path has matched the original read for the
+//     last k-1 bases; only k-mers that contain an edit are hashed and probed again.
+// Each thread owns a fixed heap (max_heap + 4 states suffice: growth stops at
+// max_heap, correct.c:349) and a fixed stack; a read whose stack overflows is re-run by
+// the same kernel with a larger stack (never on the CPU).
+//
+// Pop/push order and every threshold follow the reference exactly: the `ec:Z:` tag
+// exposes max_heap / n_absent, so the search internals are part of byte parity.
 #include "common.cuh"
+#include "enum.cuh"
 #include <algorithm>
 #include <climits>
 #include <vector>
 
 #define EC_OVERFLOW (-100)
+#define OCC_NONE 0xFFFFu
 
-struct HeapEnt {                 // reference correct.c:153-160 (echeap1_t)
+struct HeapEnt {                 // reference correct.c:153-160 (echeap1_t) + `clean`
 	int tot_pen, i, k;
 	int ecpos_high[BFC_EC_HIST_HIGH];
 	int ecpos[BFC_EC_HIST];
+	int clean;                   // trailing path bases equal to the original read (memoised lookups)
 	uint64_t x[4];
 };
 
@@ -37,8 +52,10 @@ struct EcParams {
 	const uint64_t *off;
 	uint8_t *seq, *qual;
 	int64_t n_reads;
+	uint64_t base0;              // stream offset of the window: occ16 / scratch index = off - base0
 	uint32_t *aux;
-	uint8_t *fb, *p0, *p1;       // per-base scratch, same offsets as seq
+	const uint16_t *occ16;       // per window position: bfc_ch_kmer_occ of the k-mer ending there, OCC_NONE = absent / no k-mer
+	uint8_t *fb, *p0, *p1;       // per-base scratch (window-relative)
 	TabView tab;
 	int k, q, min_cov, win_multi_ec, max_end_ext;
 	int w_ec, w_ec_high, w_absent, w_absent_high, max_path_diff, max_heap, mode;
@@ -60,12 +77,50 @@ struct EcParams {
 
 __device__ __forceinline__ int comp_b(int b) { return b < 4 ? 3 - b : 4; }
 
+// ------------------------------------------------------------------ K5: batched k-mer lookups
+
+__global__ void __launch_bounds__(ENUM_THREADS) k_ec_lookup(TabView tab, const unsigned long long *rec_y0, const unsigned long long *rec_y1,
+                                                              uint16_t *occ16, uint64_t n_pos, unsigned long long *ctr)
+{
+	__shared__ uint16_t s_occ[ENUM_SEG];
+	const uint64_t seg = blockIdx.x;
+	unsigned long long n_lookups = 0;
+	for (int j = 0; j < ENUM_CHUNK; ++j) {
+		const uint64_t i = seg * ENUM_SEG + (uint64_t)j * ENUM_THREADS + threadIdx.x;
+		const unsigned long long y1 = __ldg(rec_y1 + i);
+		uint32_t v = OCC_NONE;
+		if (y1 != ~0ULL) {
+			const int r = tab_get(tab, __ldg(rec_y0 + i) & ~(1ULL << 63), y1);
+			if (r >= 0) v = (uint32_t)r;
+			++n_lookups;
+		}
+		s_occ[threadIdx.x * ENUM_CHUNK + j] = (uint16_t)v;
+	}
+	__syncthreads();
+	for (int idx = threadIdx.x; idx < ENUM_SEG; idx += ENUM_THREADS) {
+		const uint64_t pos = seg * ENUM_SEG + idx;
+		if (pos < n_pos) occ16[pos] = s_occ[idx];
+	}
+	block_add(ctr + 1, n_lookups);
+}
+
+// ------------------------------------------------------------------ K6: per-read search
+
 // view of the read in search coordinates (dir 1 = reverse complement, correct.c:39-57)
 struct RView {
-	const uint8_t *fb;
-	int n, dir;
+	const uint8_t *fb, *seq;
+	const uint16_t *occ;
+	int n, dir, k;
 	__device__ __forceinline__ uint8_t raw(int i) const { return fb[dir ? n - 1 - i : i]; }
 	__device__ __forceinline__ int b(int i) const { const int v = FB_B(raw(i)); return dir ? comp_b(v) : v; }
+	// the ORIGINAL read base (what K5's k-mers were made of)
+	__device__ __forceinline__ int ob(int i) const { const int v = base_code(seq[dir ? n - 1 - i : i]); return dir ? comp_b(v) : v; }
+	// K5's value for the read k-mer that ends at search position i
+	__device__ __forceinline__ int occ_end(int i) const
+	{
+		const uint32_t v = occ[dir ? n - 1 - i + k - 1 : i];
+		return v == OCC_NONE ? -1 : (int)v;
+	}
 };
 
 // klib heap with "less" = larger tot_pen: root = smallest penalty (correct.c:179, ksort.h:125-146)
@@ -98,19 +153,30 @@ __device__ __forceinline__ int pen_weight(const EcParams &P, const Pen &p)
 	return P.w_ec * p.ec + P.w_ec_high * p.ec_high + P.w_absent * p.absent + P.w_absent_high * p.absent_high;
 }
 
+// Logical heap = memory heap[0..heap_n) plus, when `top_valid`, one state held in
+// registers (`top`).  Invariant: top_valid implies heap_n == 0, so the logical heap is
+// either {top} or the memory heap; states reach the memory heap in push order.
+struct SearchState {
+	HeapEnt *heap;
+	StackEnt *stack;
+	int heap_n, stack_n, stack_cap, heap_cap;
+	bool top_valid;
+	HeapEnt top;
+	__device__ __forceinline__ int size() const { return heap_n + (top_valid ? 1 : 0); }
+};
+
 // reference correct.c:198-230 (buf_update); false when the stack is full
-__device__ __forceinline__ bool push_state(const EcParams &P, HeapEnt *heap, int &heap_n, StackEnt *stack, int &stack_n,
-                                           int stack_cap, const HeapEnt &prev, const Pen &pen)
+__device__ __forceinline__ bool push_state(const EcParams &P, SearchState &S, const HeapEnt &prev, const Pen &pen, int ob_prev)
 {
-	if (stack_n >= stack_cap || heap_n >= P.heap_cap) return false;
+	if (S.stack_n >= S.stack_cap || S.heap_n + 2 > S.heap_cap) return false;
 	StackEnt q;
 	q.parent = prev.k, q.i = prev.i;
 	q.info = (uint32_t)pen.b | pen.ec << 4 | pen.ec_high << 5 | pen.absent << 6 | pen.absent_high << 7;
 	q.tot_pen = prev.tot_pen + pen_weight(P, pen);
-	stack[stack_n++] = q;
+	S.stack[S.stack_n++] = q;
 	HeapEnt r;
 	r.i = prev.i + 1;
-	r.k = stack_n - 1;
+	r.k = S.stack_n - 1;
 	r.x[0] = prev.x[0], r.x[1] = prev.x[1], r.x[2] = prev.x[2], r.x[3] = prev.x[3];
 	if (pen.ec_high) r.ecpos_high[0] = prev.i, r.ecpos_high[1] = prev.ecpos_high[0];
 	else r.ecpos_high[0] = prev.ecpos_high[0], r.ecpos_high[1] = prev.ecpos_high[1];
@@ -123,45 +189,60 @@ __device__ __forceinline__ bool push_state(const EcParams &P, HeapEnt *heap, int
 		for (int t = 0; t < BFC_EC_HIST; ++t) r.ecpos[t] = prev.ecpos[t];
 	}
 	r.tot_pen = q.tot_pen;
+	r.clean = pen.b == ob_prev ? prev.clean + 1 : 0;
 	bfc_kmer_append(P.k, r.x, pen.b);
-	heap[heap_n++] = r;
-	heap_up(heap, heap_n);
+	if (S.heap_n == 0 && !S.top_valid) { S.top = r; S.top_valid = true; return true; }
+	if (S.top_valid) { // a second state arrives: the register state goes to memory first (same order as the reference)
+		S.heap[S.heap_n++] = S.top;
+		heap_up(S.heap, S.heap_n);
+		S.top_valid = false;
+	}
+	S.heap[S.heap_n++] = r;
+	heap_up(S.heap, S.heap_n);
 	return true;
 }
 
 // reference correct.c:249-386 (bfc_ec1dir).  `path` receives ec[].b in FORWARD read
 // coordinates (for dir 1 that is the result after the reference's final revcomp).
-__device__ int ec_search(const EcParams &P, const RView &rv, int start, int end, HeapEnt *heap, StackEnt *stack,
-                         int stack_cap, uint8_t *path, int &max_heap, unsigned long long &n_lookups)
+__device__ int ec_search(const EcParams &P, const RView &rv, int start, int end, SearchState &S, uint8_t *path,
+                         int &max_heap, bool memo, unsigned long long &n_lookups)
 {
 	const int k = P.k, n = rv.n;
 	HeapEnt z;
-	int heap_n = 0, stack_n = 0, rvl = -1, n_paths = 0, best = -1, best_pen = INT_MAX, n_fail = 0, run = 0;
+	int rvl = -1, n_paths = 0, best = -1, best_pen = INT_MAX, n_fail = 0, run = 0;
 	int paths[BFC_MAX_PATHS];
+	S.heap_n = S.stack_n = 0, S.top_valid = false;
 	max_heap = 0;
-	z.tot_pen = 0, z.k = -1;
+	z.tot_pen = 0, z.k = -1, z.clean = 0;
 	z.x[0] = z.x[1] = z.x[2] = z.x[3] = 0;
 	for (z.i = start; z.i < end; ++z.i) { // seed: k-1 bases (correct.c:260-267)
 		const int c = rv.b(z.i);
 		if (c < 4) {
 			if (++run == k) break;
 			bfc_kmer_append(k, z.x, c);
-		} else run = 0, z.x[0] = z.x[1] = z.x[2] = z.x[3] = 0;
+			z.clean = c == rv.ob(z.i) ? z.clean + 1 : 0;
+		} else run = 0, z.clean = 0, z.x[0] = z.x[1] = z.x[2] = z.x[3] = 0;
 	}
 	if (z.i >= end) return -1; // the reference asserts; cannot happen after an island / rescue was found
 #pragma unroll
 	for (int t = 0; t < BFC_EC_HIST; ++t) z.ecpos[t] = -1;
 #pragma unroll
 	for (int t = 0; t < BFC_EC_HIST_HIGH; ++t) z.ecpos_high[t] = -1;
-	heap[heap_n++] = z;
+	S.top = z, S.top_valid = true;
 
 	for (;;) {
 		bool stop = false;
-		max_heap = max_heap > 255 ? 255 : max_heap > heap_n ? max_heap : heap_n;
-		if (heap_n == 0) { rvl = -2; break; }
-		z = heap[0];
-		heap[0] = heap[--heap_n];
-		heap_down(heap, heap_n);
+		{
+			const int hs = S.size();
+			max_heap = max_heap > 255 ? 255 : max_heap > hs ? max_heap : hs;
+			if (hs == 0) { rvl = -2; break; }
+		}
+		if (S.top_valid) { z = S.top; S.top_valid = false; }
+		else {
+			z = S.heap[0];
+			S.heap[0] = S.heap[--S.heap_n];
+			heap_down(S.heap, S.heap_n);
+		}
 		if (best >= 0 && z.tot_pen > best_pen + P.max_path_diff) break;
 		if (z.i - end > P.max_end_ext) stop = true;
 		if (!stop) {
@@ -169,14 +250,18 @@ __device__ int ec_search(const EcParams &P, const RView &rv, int start, int end,
 			const uint8_t craw = has_c ? rv.raw(z.i) : 0;
 			const int cb = has_c ? (rv.dir ? comp_b(FB_B(craw)) : FB_B(craw)) : -1;
 			const int cq = (craw & FB_Q) != 0;
+			const int cob = has_c ? rv.ob(z.i) : -1;
 			int os = -1, other_ext = 0, n_added = 0;
 			bool fixed = z.i > end;
 			Pen added[4];
 			if (has_c && cb < 4) {
-				uint64_t x[4] = { z.x[0], z.x[1], z.x[2], z.x[3] };
-				bfc_kmer_append(k, x, cb);
-				os = tab_kmer_occ(P.tab, x);
-				++n_lookups;
+				if (memo && z.clean >= k - 1 && cb == cob) os = rv.occ_end(z.i); // the read's own k-mer: fetched by K5
+				else {
+					uint64_t x[4] = { z.x[0], z.x[1], z.x[2], z.x[3] };
+					bfc_kmer_append(k, x, cb);
+					os = tab_kmer_occ(P.tab, x);
+					++n_lookups;
+				}
 				if (cq && (os & 0xff) >= P.min_cov + 1 && (craw & FB_LCOV)) fixed = true;
 				else if (craw & FB_HCOV) fixed = true;
 			}
@@ -211,24 +296,24 @@ __device__ int ec_search(const EcParams &P, const RView &rv, int start, int end,
 			if (!fixed && other_ext == 0) ++n_fail;
 			if (n_fail > n * 2) { rvl = -3; break; }
 			if (has_c || n_added == 1) {
-				if (n_added > 1 && heap_n > P.max_heap) { // keep only the cheapest extension (first on ties)
+				if (n_added > 1 && S.size() > P.max_heap) { // keep only the cheapest extension (first on ties)
 					int min_b = -1, min = INT_MAX;
 					for (int b = 0; b < n_added; ++b) {
 						const int t = pen_weight(P, added[b]);
 						if (min > t) min = t, min_b = b;
 					}
-					if (!push_state(P, heap, heap_n, stack, stack_n, stack_cap, z, added[min_b])) return EC_OVERFLOW;
+					if (!push_state(P, S, z, added[min_b], cob)) return EC_OVERFLOW;
 				} else {
 					for (int b = 0; b < n_added; ++b)
-						if (!push_state(P, heap, heap_n, stack, stack_n, stack_cap, z, added[b])) return EC_OVERFLOW;
+						if (!push_state(P, S, z, added[b], cob)) return EC_OVERFLOW;
 				}
 			} else {
-				if (n_added == 0) stack[z.k].tot_pen += P.w_absent * (P.max_end_ext - (z.i - end));
+				if (n_added == 0) S.stack[z.k].tot_pen += P.w_absent * (P.max_end_ext - (z.i - end));
 				stop = true;
 			}
 		}
 		if (stop) {
-			if (stack[z.k].tot_pen < best_pen) best_pen = stack[z.k].tot_pen, best = n_paths;
+			if (S.stack[z.k].tot_pen < best_pen) best_pen = S.stack[z.k].tot_pen, best = n_paths;
 			paths[n_paths++] = z.k;
 			if (n_paths == BFC_MAX_PATHS) break;
 		}
@@ -237,12 +322,12 @@ __device__ int ec_search(const EcParams &P, const RView &rv, int start, int end,
 	// ec[].b := read bases, then the best path (buf_backtrack, correct.c:232-247), then the mask (correct.c:378-379)
 	for (int j = 0; j < n; ++j) path[j] = FB_B(rv.fb[j]);
 	int n_absent = 0;
-	for (int e = paths[best]; e >= 0; e = stack[e].parent) {
-		const int i = stack[e].i;
+	for (int e = paths[best]; e >= 0; e = S.stack[e].parent) {
+		const int i = S.stack[e].i;
 		if (i < n) {
-			const int b = stack[e].info & 15;
+			const int b = S.stack[e].info & 15;
 			path[rv.dir ? n - 1 - i : i] = (uint8_t)(rv.dir ? comp_b(b) : b);
-			n_absent += stack[e].info >> 6 & 1;
+			n_absent += S.stack[e].info >> 6 & 1;
 		}
 	}
 	for (int i = 0; i < n; ++i)
@@ -287,40 +372,32 @@ __device__ int ec_first_kmer(int k, const uint8_t *fb, int n, int start, uint64_
 }
 
 // reference correct.c:388-472 (bfc_ec1) + the packing of worker_ec (correct.c:552-553)
-__device__ int ec_read(const EcParams &P, int64_t r, HeapEnt *heap, StackEnt *stack, unsigned long long &n_lookups)
+__device__ int ec_read(const EcParams &P, int64_t r, SearchState &S, unsigned long long &n_lookups)
 {
-	const uint64_t o = P.off[r];
+	const uint64_t o = P.off[r], ow = o - P.base0;
 	const int n = (int)(P.off[r + 1] - o - 1), k = P.k;
-	uint8_t *seq = P.seq + o, *fb = P.fb + o;
+	uint8_t *seq = P.seq + o, *fb = P.fb + ow;
 	uint8_t *qual = P.qual && n > 0 && P.qual[o] != 0xFF ? P.qual + o : 0;
+	const uint16_t *occ = P.occ16 + ow;
 	const bool has_q = qual != 0;
 	uint32_t ec_code = 1, brute = 0, n_ec = 0, n_ec_high = 0, n_absent = 0, mh = 0;
 	int start = 0, end = 0, n_n = 0;
+	bool island = false;
 
-	// bfc_seq_conv (correct.c:23-37)
+	// bfc_seq_conv (correct.c:23-37) + the solid / high flags of bfc_ec_kcov (correct.c:106-108)
 	for (int i = 0; i < n; ++i) {
 		const int b = base_code(seq[i]);
 		const int q = b > 3 ? 0 : !has_q ? 1 : (int)qual[i] - 33 >= P.q;
-		fb[i] = (uint8_t)(b | (q ? FB_Q : 0));
+		uint32_t f = (uint32_t)b | (q ? FB_Q : 0);
+		const uint32_t v = occ[i];
+		if (v != OCC_NONE && (int)(v & 0xff) >= P.min_cov)
+			f |= FB_SOLID | ((int)(v >> 8 & 0x3f) >= P.min_cov + 1 ? FB_HSOLID : 0);
+		fb[i] = (uint8_t)f;
 		n_n += b > 3;
 	}
 	do {
 		if (n_n > n * .05) { ec_code = 2; break; }
-		// bfc_ec_kcov (correct.c:96-117): one lookup per k-mer, then the per-base coverage
-		{
-			uint64_t x[4] = {0, 0, 0, 0};
-			int l = 0;
-			for (int i = 0; i < n; ++i) {
-				const int b = FB_B(fb[i]);
-				if (b >= 4) { l = 0, x[0] = x[1] = x[2] = x[3] = 0; continue; }
-				bfc_kmer_append(k, x, b);
-				if (++l < k) continue;
-				const int occ = tab_kmer_occ(P.tab, x);
-				++n_lookups;
-				if (occ >= 0 && (occ & 0xff) >= P.min_cov)
-					fb[i] |= FB_SOLID | ((occ >> 8 & 0x3f) >= P.min_cov + 1 ? FB_HSOLID : 0);
-			}
-			// lcov[j] = #solid k-mers ending in [j, j+k-1]; hcov likewise for solid && high_end
+		{ // lcov[j] = #solid k-mers ending in [j, j+k-1]; hcov likewise for solid && high_end (correct.c:109-112)
 			int lc = 0, hc = 0;
 			for (int j = n - 1; j >= 0; --j) {
 				lc += (fb[j] & FB_SOLID) != 0, hc += (fb[j] & FB_HSOLID) != 0;
@@ -329,8 +406,7 @@ __device__ int ec_read(const EcParams &P, int64_t r, HeapEnt *heap, StackEnt *st
 				if (4 * hc > 3 * k) fb[j] |= FB_HCOV; // hcov > k * .75
 			}
 		}
-		// bfc_ec_best_island (correct.c:119-130)
-		{
+		{ // bfc_ec_best_island (correct.c:119-130)
 			int l = 0, max = 0, max_i = -1, i;
 			for (i = k - 1; i < n; ++i) {
 				if (!(fb[i] & FB_SOLID)) {
@@ -339,10 +415,9 @@ __device__ int ec_read(const EcParams &P, int64_t r, HeapEnt *heap, StackEnt *st
 				} else ++l;
 			}
 			if (l > max) max = l, max_i = i;
-			if (max > 0) start = max_i - max - k + 1, end = max_i;
+			if (max > 0) start = max_i - max - k + 1, end = max_i, island = true;
 		}
-		if (end == 0 && start == 0) { // no solid k-mer: single-edit rescue (correct.c:405-421)
-			// NB: the reference tests the packed (start<<32|end) == 0; start == end == 0 is the only such island
+		if (!island) { // no solid k-mer: single-edit rescue (correct.c:405-421)
 			uint64_t x[4];
 			int ec = -1;
 			while ((end = ec_first_kmer(k, fb, n, start, x)) < n) {
@@ -358,20 +433,21 @@ __device__ int ec_read(const EcParams &P, int64_t r, HeapEnt *heap, StackEnt *st
 			} else { ec_code = 3; break; }
 		}
 		RView rv;
-		rv.fb = fb, rv.n = n;
+		rv.fb = fb, rv.seq = seq, rv.occ = occ, rv.n = n, rv.k = k;
 		int mh0 = 0, mh1 = 0, rv0, rv1;
 		rv.dir = 0;
-		rv0 = ec_search(P, rv, start, n, heap, stack, P.stack_cap, P.p0 + o, mh0, n_lookups);
+		rv0 = ec_search(P, rv, start, n, S, P.p0 + ow, mh0, true, n_lookups);
 		if (rv0 == EC_OVERFLOW) return EC_OVERFLOW;
 		if (rv0 < 0) { ec_code = rv0 == -2 ? 4 : rv0 == -3 ? 5 : 1; break; }
 		rv.dir = 1;
-		rv1 = ec_search(P, rv, n - end, n, heap, stack, P.stack_cap, P.p1 + o, mh1, n_lookups);
+		// the reverse-complement k-mer hashes like the forward one only for odd k (kmer.h:81)
+		rv1 = ec_search(P, rv, n - end, n, S, P.p1 + ow, mh1, (k & 1) != 0, n_lookups);
 		if (rv1 == EC_OVERFLOW) return EC_OVERFLOW;
 		if (rv1 < 0) { ec_code = rv1 == -2 ? 4 : rv1 == -3 ? 5 : 1; break; }
 		mh = mh0 > mh1 ? mh0 : mh1;
 		ec_code = 0, n_absent = rv0 + rv1;
 		// merge the two directions and rewrite the read (correct.c:443-459)
-		const uint8_t *p0 = P.p0 + o, *p1 = P.p1 + o;
+		const uint8_t *p0 = P.p0 + ow, *p1 = P.p1 + ow;
 		for (int i = 0; i < n; ++i) {
 			const int f = p0[i], g = p1[i], cur = FB_B(fb[i]), ob = base_code(seq[i]);
 			int nb;
@@ -391,65 +467,18 @@ __device__ int ec_read(const EcParams &P, int64_t r, HeapEnt *heap, StackEnt *st
 	return 0;
 }
 
-__global__ void __launch_bounds__(128) k_correct(EcParams P)
+__global__ void __launch_bounds__(128) k_ec_read(EcParams P)
 {
 	const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, n_slots = (int64_t)gridDim.x * blockDim.x;
-	HeapEnt *heap = P.heap + slot * P.heap_cap;
-	StackEnt *stack = P.stack + slot * P.stack_cap;
+	SearchState S;
+	S.heap = P.heap + slot * P.heap_cap, S.stack = P.stack + slot * P.stack_cap;
+	S.heap_cap = P.heap_cap, S.stack_cap = P.stack_cap;
+	S.heap_n = S.stack_n = 0, S.top_valid = false;
 	unsigned long long n_lookups = 0;
 	for (int64_t s = slot; s < P.n_reads; s += n_slots) {
 		const int64_t r = P.redo ? (int64_t)P.redo[s] : s;
-		if (ec_read(P, r, heap, stack, n_lookups) == EC_OVERFLOW)
+		if (ec_read(P, r, S, n_lookups) == EC_OVERFLOW)
 			P.overflow[atomicAdd(P.ctr, 1ULL)] = (uint32_t)r;
-	}
-	block_add(P.ctr + 1, n_lookups);
-}
-
-// ------------------------------------------------------------------ trim
-
-struct TrimParams {
-	const uint64_t *off;
-	const uint8_t *seq;
-	int64_t n_reads;
-	BloomView bf;
-	int k;
-	float min_frac;
-	uint8_t *keep;
-	int32_t *tstart, *tend;
-	unsigned long long *ctr; // [1] n_lookups
-};
-
-// reference correct.c:478-497 (max_streak) + the keep rule of worker_ec (correct.c:555-569)
-__global__ void __launch_bounds__(256) k_trim(TrimParams P)
-{
-	unsigned long long n_lookups = 0;
-	for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < P.n_reads; r += (int64_t)gridDim.x * blockDim.x) {
-		const uint64_t o = P.off[r];
-		const int n = (int)(P.off[r + 1] - o - 1), k = P.k;
-		const uint8_t *seq = P.seq + o;
-		uint64_t x[4] = {0, 0, 0, 0}, max = 0, t = 0;
-		int l = 0;
-		for (int i = 0; i < n; ++i) {
-			const int c = base_code(seq[i]);
-			if (c < 4) {
-				bfc_kmer_append(k, x, c);
-				if (++l >= k) {
-					uint64_t y[2];
-					const BloomProbe pr = bloom_locate(bfc_kmer_hash(k, x, y), P.bf.n_shift);
-					++n_lookups;
-					if (bloom_count_set<false>(P.bf.w + (pr.blk << 4), pr, P.bf.n_hashes) == P.bf.n_hashes) t += 1ULL << 32;
-					else t = i + 1;
-				} else t = i + 1;
-			} else l = 0, x[0] = x[1] = x[2] = x[3] = 0, t = i + 1;
-			max = max > t ? max : t;
-		}
-		uint8_t keep = 0;
-		int32_t ts = 0, te = 0;
-		if (max >> 32 && (double)((max >> 32) + k) / n > P.min_frac) { // float min_frac promoted, as in C
-			const int start = (int)(uint32_t)max;
-			te = start + (int)(max >> 32), ts = start - (k - 1), keep = 1;
-		}
-		P.keep[r] = keep, P.tstart[r] = ts, P.tend[r] = te;
 	}
 	block_add(P.ctr + 1, n_lookups);
 }
@@ -488,7 +517,7 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 	const uint64_t limit = batch_bytes_limit();
 	const int threads = 128;
 	const int64_t max_slots = (int64_t)rt.sm_count * 1024;
-	const int heap_cap = opt->max_heap + 5; // the search never holds more than max_heap + 4 states
+	const int heap_cap = opt->max_heap + 6; // the search never holds more than max_heap + 4 states
 	const int stack_cap0 = 512;
 
 	BfcgTimer timer(stats);
@@ -497,8 +526,9 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 		while (r1 < n && h_off[r1 + 1] - h_off[r0] <= limit) ++r1;
 		const int64_t nr = r1 - r0;
 		const uint64_t b0 = h_off[r0], nb = h_off[r1] - b0;
+		const uint64_t n_rec = enum_padded(nb);
 		const int64_t slots = std::min<int64_t>(max_slots, (nr + threads - 1) / threads * threads);
-		size_t tot = 0, o_seq = 0, o_qual = 0, o_off = 0, o_aux = 0, o_fb, o_p0, o_p1, o_heap, o_stack, o_ovf, o_ctr;
+		size_t tot = 0, o_seq = 0, o_qual = 0, o_off = 0, o_aux = 0, o_fb, o_p0, o_p1, o_y0, o_y1, o_occ, o_heap, o_stack, o_ovf, o_ctr;
 		if (host) {
 			o_seq = tot; tot = align_up(tot + nb, 256);
 			o_qual = tot; tot = align_up(tot + nb, 256);
@@ -508,6 +538,9 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 		o_fb = tot; tot = align_up(tot + nb, 256);
 		o_p0 = tot; tot = align_up(tot + nb, 256);
 		o_p1 = tot; tot = align_up(tot + nb, 256);
+		o_y0 = tot; tot = align_up(tot + n_rec * 8, 256);
+		o_y1 = tot; tot = align_up(tot + n_rec * 8, 256);
+		o_occ = tot; tot = align_up(tot + n_rec * 2, 256);
 		o_heap = tot; tot = align_up(tot + (size_t)slots * heap_cap * sizeof(HeapEnt), 256);
 		o_stack = tot; tot = align_up(tot + (size_t)slots * stack_cap0 * sizeof(StackEnt), 256);
 		o_ovf = tot; tot = align_up(tot + nr * 4, 256);
@@ -526,12 +559,14 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 			BFCG_CUDA(cudaMemcpyAsync(a + o_off, rel.data(), (nr + 1) * 8, cudaMemcpyHostToDevice, rt.stream));
 			P.off = (const uint64_t*)(a + o_off), P.seq = a + o_seq, P.qual = batch->qual ? a + o_qual : 0;
 			P.aux = (uint32_t*)(a + o_aux);
-			P.fb = a + o_fb, P.p0 = a + o_p0, P.p1 = a + o_p1;
-		} else { // device batch: offsets are absolute, scratch is indexed relative to b0
+			P.base0 = 0;
+		} else { // device batch: offsets are absolute, the window starts at b0
 			P.off = batch->off + r0, P.seq = batch->seq, P.qual = batch->qual;
 			P.aux = aux + 2 * r0;
-			P.fb = a + o_fb - b0, P.p0 = a + o_p0 - b0, P.p1 = a + o_p1 - b0;
+			P.base0 = b0;
 		}
+		P.fb = a + o_fb, P.p0 = a + o_p0, P.p1 = a + o_p1;
+		P.occ16 = (const uint16_t*)(a + o_occ);
 		P.n_reads = nr;
 		P.tab = tab_view(ch);
 		P.k = opt->k, P.q = opt->q, P.min_cov = opt->min_cov, P.win_multi_ec = opt->win_multi_ec, P.max_end_ext = opt->max_end_ext;
@@ -541,7 +576,17 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 		P.heap_cap = heap_cap, P.stack_cap = stack_cap0;
 		P.overflow = (uint32_t*)(a + o_ovf), P.ctr = (unsigned long long*)(a + o_ctr);
 		BFCG_CUDA(cudaMemsetAsync(P.ctr, 0, 64, rt.stream));
-		{ KTime kt(KT_CORRECT); k_correct<<<(unsigned)(slots / threads), threads, 0, rt.stream>>>(P); }
+
+		EnumParams ep;
+		memset(&ep, 0, sizeof(ep));
+		ep.seq = (host ? a + o_seq : batch->seq + b0), ep.qual = 0; // the quality flag of a record is not used here
+		ep.len = nb, ep.emit_from = 0, ep.k = opt->k, ep.q = opt->q;
+		ep.rec_y0 = (unsigned long long*)(a + o_y0), ep.rec_y1 = (unsigned long long*)(a + o_y1);
+		{ KTime kt(KT_ENUM); k_enum<<<(unsigned)(n_rec / ENUM_SEG), ENUM_THREADS, 0, rt.stream>>>(ep); }
+		BFCG_LAUNCH_CHECK();
+		{ KTime kt(KT_EC_LOOKUP); k_ec_lookup<<<(unsigned)(n_rec / ENUM_SEG), ENUM_THREADS, 0, rt.stream>>>(P.tab, ep.rec_y0, ep.rec_y1, (uint16_t*)(a + o_occ), nb, P.ctr); }
+		BFCG_LAUNCH_CHECK();
+		{ KTime kt(KT_CORRECT); k_ec_read<<<(unsigned)(slots / threads), threads, 0, rt.stream>>>(P); }
 		BFCG_LAUNCH_CHECK();
 		unsigned long long c[2];
 		BFCG_CUDA(cudaMemcpyAsync(c, P.ctr, sizeof(c), cudaMemcpyDeviceToHost, rt.stream));
@@ -562,7 +607,7 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 			BFCG_CUDA(cudaMemsetAsync(P.ctr, 0, 8, rt.stream));
 			EcParams Q = P;
 			Q.redo = redo, Q.n_reads = (int64_t)n_redo, Q.stack = big, Q.stack_cap = cap;
-			{ KTime kt(KT_CORRECT_REDO); k_correct<<<(unsigned)(rs / 32), 32, 0, rt.stream>>>(Q); }
+			{ KTime kt(KT_CORRECT_REDO); k_ec_read<<<(unsigned)(rs / 32), 32, 0, rt.stream>>>(Q); }
 			BFCG_LAUNCH_CHECK();
 			BFCG_CUDA(cudaMemcpyAsync(c, P.ctr, sizeof(c), cudaMemcpyDeviceToHost, rt.stream));
 			BFCG_CUDA(cudaStreamSynchronize(rt.stream));
@@ -579,71 +624,5 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 	}
 	timer.stop();
 	BFCG_CUDA(cudaStreamSynchronize(rt.stream));
-	return BFCG_OK;
-}
-
-extern "C" int bfcg_trim_batch(const bfc_opt_t *opt, const bfc_bf_t *bf_high, const bfcg_batch_t *batch,
-                               uint8_t *keep, int32_t *tstart, int32_t *tend, bfcg_stats_t *stats)
-{
-	int r;
-	if ((r = bfcg_rt_init()) != BFCG_OK) return r;
-	BfcgRuntime &rt = bfcg_rt();
-	if (!opt || !bf_high || !batch || !batch->off || !keep || !tstart || !tend || opt->k < 1 || opt->k > BFC_MAX_KMER)
-		return bfcg_fail(__func__, "invalid arguments", cudaSuccess), BFCG_ERR_ARG;
-	if (batch->n_reads == 0) return BFCG_OK;
-	const bool host = batch->where == BFCG_HOST;
-	const int64_t n = batch->n_reads;
-	const uint64_t limit = batch_bytes_limit();
-
-	BfcgTimer timer(stats);
-	if (!host) {
-		unsigned long long *ctr = (unsigned long long*)bfcg_arena(256), c[2];
-		if (!ctr) return BFCG_ERR_NOMEM;
-		TrimParams P;
-		P.off = batch->off, P.seq = batch->seq, P.n_reads = n, P.bf = bloom_view(bf_high), P.k = opt->k, P.min_frac = opt->min_frac;
-		P.keep = keep, P.tstart = tstart, P.tend = tend, P.ctr = ctr;
-		BFCG_CUDA(cudaMemsetAsync(ctr, 0, 64, rt.stream));
-		{ KTime kt(KT_TRIM); k_trim<<<(unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)rt.sm_count * 8), 256, 0, rt.stream>>>(P); }
-		BFCG_LAUNCH_CHECK();
-		BFCG_CUDA(cudaMemcpyAsync(c, ctr, sizeof(c), cudaMemcpyDeviceToHost, rt.stream));
-		timer.stop();
-		BFCG_CUDA(cudaStreamSynchronize(rt.stream));
-		if (stats) stats->n_lookups += c[1];
-		return BFCG_OK;
-	}
-	for (int64_t r0 = 0; r0 < n;) {
-		int64_t r1 = r0 + 1;
-		while (r1 < n && batch->off[r1 + 1] - batch->off[r0] <= limit) ++r1;
-		const int64_t nr = r1 - r0;
-		const uint64_t b0 = batch->off[r0], nb = batch->off[r1] - b0;
-		size_t tot = 0, o_seq, o_off, o_keep, o_ts, o_te, o_ctr;
-		o_seq = tot; tot = align_up(tot + nb, 256);
-		o_off = tot; tot = align_up(tot + (nr + 1) * 8, 256);
-		o_keep = tot; tot = align_up(tot + nr, 256);
-		o_ts = tot; tot = align_up(tot + nr * 4, 256);
-		o_te = tot; tot = align_up(tot + nr * 4, 256);
-		o_ctr = tot; tot += 256;
-		uint8_t *a = (uint8_t*)bfcg_arena(tot);
-		if (!a) return BFCG_ERR_NOMEM;
-		std::vector<uint64_t> rel(nr + 1);
-		for (int64_t i = 0; i <= nr; ++i) rel[i] = batch->off[r0 + i] - b0;
-		BFCG_CUDA(cudaMemcpyAsync(a + o_seq, batch->seq + b0, nb, cudaMemcpyHostToDevice, rt.stream));
-		BFCG_CUDA(cudaMemcpyAsync(a + o_off, rel.data(), (nr + 1) * 8, cudaMemcpyHostToDevice, rt.stream));
-		TrimParams P;
-		P.off = (const uint64_t*)(a + o_off), P.seq = a + o_seq, P.n_reads = nr, P.bf = bloom_view(bf_high), P.k = opt->k, P.min_frac = opt->min_frac;
-		P.keep = a + o_keep, P.tstart = (int32_t*)(a + o_ts), P.tend = (int32_t*)(a + o_te), P.ctr = (unsigned long long*)(a + o_ctr);
-		BFCG_CUDA(cudaMemsetAsync(P.ctr, 0, 64, rt.stream));
-		{ KTime kt(KT_TRIM); k_trim<<<(unsigned)std::min<int64_t>((nr + 255) / 256, (int64_t)rt.sm_count * 8), 256, 0, rt.stream>>>(P); }
-		BFCG_LAUNCH_CHECK();
-		unsigned long long c[2];
-		BFCG_CUDA(cudaMemcpyAsync(c, P.ctr, sizeof(c), cudaMemcpyDeviceToHost, rt.stream));
-		BFCG_CUDA(cudaMemcpyAsync(keep + r0, a + o_keep, nr, cudaMemcpyDeviceToHost, rt.stream));
-		BFCG_CUDA(cudaMemcpyAsync(tstart + r0, a + o_ts, nr * 4, cudaMemcpyDeviceToHost, rt.stream));
-		BFCG_CUDA(cudaMemcpyAsync(tend + r0, a + o_te, nr * 4, cudaMemcpyDeviceToHost, rt.stream));
-		BFCG_CUDA(cudaStreamSynchronize(rt.stream));
-		if (stats) stats->n_lookups += c[1];
-		r0 = r1;
-	}
-	timer.stop();
 	return BFCG_OK;
 }

@@ -4,15 +4,17 @@
 //
 // Order dependence (count.c:9-18): occurrence t of a k-mer "passes" iff all n_hashes
 // Bloom bits were set by occurrences < t.  All ordering constraints are local to one
-// 64-byte Bloom block, so a sub-batch is processed as
+// 64-byte Bloom block, so a sub-batch of the read stream is processed as
 //
-//   K1 k_count_probe    every occurrence tests its bits against the filter as it was
-//                       BEFORE the sub-batch (no data bit is written in K1).  All bits
-//                       set -> it passes regardless of order: table upsert (or bf_high
-//                       insert in trim mode) right away.  Otherwise it is "pending": it
-//                       is appended to a list and marks its Bloom block in the two
-//                       spare bits of the block's lock byte (bit 0: one pending
-//                       occurrence, bit 1: more than one).
+//   K0 k_enum           rolling canonical k-mer + hash per stream position (enum.cuh):
+//                       a dense array of 16-byte records (y0 | is_high << 63, y1).
+//   K1 k_count_probe    one thread per record: test its bits against the filter as it
+//                       was BEFORE the sub-batch (no data bit is written in K1).  All
+//                       bits set -> it passes regardless of order: table upsert (or
+//                       bf_high insert in trim mode) right away.  Otherwise it is
+//                       "pending": its index is appended to a list and it marks its
+//                       Bloom block in the two spare bits of the block's lock byte
+//                       (bit 0: one pending occurrence, bit 1: more than one).
 //   K2 k_count_resolve  a pending occurrence alone in its block sets a bit nobody else
 //                       touches in this sub-batch: it cannot pass; its bits are OR-ed in.
 //                       Pending occurrences that share a block go to the conflict list.
@@ -22,23 +24,17 @@
 //
 // The lock byte is 0 again when the sub-batch ends, as in the reference (bbf.c:43).
 #include "common.cuh"
+#include "enum.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
 
-#define CNT_THREADS 256
-#define CNT_CHUNK   36     // positions per thread; CHUNK/4 odd => conflict-free shared-memory reads
-#define CNT_SEG     (CNT_THREADS * CNT_CHUNK)
-#define CNT_HALO_MAX 64
-
 struct CountParams {
-	const uint8_t *seq, *qual;   // loaded stream window (device)
-	uint64_t len;                // bytes in the window
-	uint64_t emit_from;          // window positions < emit_from only warm the rolling k-mer up
-	int k, q;
+	const unsigned long long *rec_y0, *rec_y1; // records of the window, in k_enum's blocked order
+	uint64_t n_rec;              // records (= padded window positions)
+	int k;
 	BloomView bf, bf_high;       // bf_high.w == 0 in normal mode
 	TabView tab;                 // tab.slots == 0 in trim mode
-	unsigned long long *pend_y0, *pend_y1;
-	uint32_t *pend_t;
+	uint32_t *pend;              // record indices of the pending occurrences
 	unsigned long long *ctr;     // [0] n_pending [1] n_kmers [2] n_pass [3] n_conflict
 	unsigned long long *conf_key;
 	uint32_t *conf_val;
@@ -51,77 +47,45 @@ __device__ __forceinline__ uint64_t hash_from_y(int k, uint64_t y0, uint64_t y1)
 	return ((h0 ^ y1) << k) | y0;
 }
 
-__global__ void __launch_bounds__(CNT_THREADS) k_count_probe(CountParams p)
+__global__ void __launch_bounds__(256) k_count_probe(CountParams p)
 {
-	__shared__ uint8_t s_code[CNT_SEG + CNT_HALO_MAX];
-	const int halo = p.k - 1;
-	const int64_t seg0 = (int64_t)p.emit_from + (int64_t)blockIdx.x * CNT_SEG;
-
-	// stage the CTA's window as codes: bits 0-2 base (4 = not ACGT / outside), bit 3 Q >= q
-	for (int i = threadIdx.x; i < CNT_SEG + halo; i += CNT_THREADS) {
-		const int64_t pos = seg0 - halo + i;
-		uint32_t c = 4;
-		if (pos >= 0 && (uint64_t)pos < p.len) {
-			c = base_code(p.seq[pos]);
-			if (c < 4 && (p.qual == 0 || (int)p.qual[pos] - 33 >= p.q)) c |= 8;
-		}
-		s_code[i] = (uint8_t)c;
-	}
-	__syncthreads();
-
-	const int base = threadIdx.x * CNT_CHUNK;
-	const int k = p.k;
-	const uint64_t mask = (1ULL << k) - 1;
-	uint64_t x[4] = {0, 0, 0, 0}, qmer = 0;
-	int l = 0;
-	unsigned long long n_kmers = 0, n_pass = 0, n_new = 0;
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	const unsigned lane = threadIdx.x & 31;
-
-	for (int j = 0; j < CNT_CHUNK + halo; ++j) {
-		const uint32_t c = s_code[base + j];
-		bool pend = false, pass = false;
-		uint64_t y[2] = {0, 0};
-		BloomProbe pr;
-		pr.blk = 0, pr.h1 = pr.h2 = 0;
-		if ((c & 7) < 4) {
-			bfc_kmer_append(k, x, c & 3);
-			qmer = (qmer << 1 | (c >> 3)) & mask;
-			if (++l >= k && j >= halo) {
-				const uint64_t hash = bfc_kmer_hash(k, x, y);
-				pr = bloom_locate(hash, p.bf.n_shift);
-				const int cnt = bloom_count_set<false>(p.bf.w + (pr.blk << 4), pr, p.bf.n_hashes);
-				pass = cnt == p.bf.n_hashes;
-				pend = !pass;
-				++n_kmers;
-			}
-		} else l = 0, qmer = 0, x[0] = x[1] = x[2] = x[3] = 0;
-
-		// warp-aggregated append of the pending occurrences (the loop is uniform: all lanes are here)
-		const unsigned pm = __ballot_sync(0xffffffffu, pend);
-		if (pm) {
-			unsigned long long at = 0;
-			if (lane == (unsigned)(__ffs(pm) - 1)) at = atomicAdd(p.ctr, (unsigned long long)__popc(pm));
-			at = __shfl_sync(0xffffffffu, at, __ffs(pm) - 1);
-			if (pend) {
-				at += __popc(pm & ((1u << lane) - 1));
-				p.pend_y0[at] = y[0] | (unsigned long long)(qmer == mask) << 63;
-				p.pend_y1[at] = y[1];
-				p.pend_t[at] = (uint32_t)(seg0 + base + j - halo);
-				uint32_t *w0 = p.bf.w + (pr.blk << 4);
-				if (atomicOr(w0, 1u) & 1u) atomicOr(w0, 2u);
-			}
-		}
-		if (pass) {
-			++n_pass;
-			if (p.tab.slots) n_new += tab_upsert(p.tab, y[0], y[1], qmer == mask) == 1;
-			else {
-				const BloomProbe ph = bloom_locate(hash_from_y(k, y[0], y[1]), p.bf_high.n_shift);
-				bloom_set_atomic(p.bf_high.w + (ph.blk << 4), ph, p.bf_high.n_hashes);
-			}
+	bool pend = false, pass = false;
+	uint64_t y0f = 0, y1 = ~0ULL;
+	BloomProbe pr;
+	pr.blk = 0, pr.h1 = pr.h2 = 0;
+	if (i < p.n_rec) y1 = __ldg(p.rec_y1 + i);
+	const bool valid = y1 != ~0ULL;
+	if (valid) {
+		y0f = __ldg(p.rec_y0 + i);
+		pr = bloom_locate(hash_from_y(p.k, y0f & ~(1ULL << 63), y1), p.bf.n_shift);
+		pass = bloom_count_set<false>(p.bf.w + (pr.blk << 4), pr, p.bf.n_hashes) == p.bf.n_hashes;
+		pend = !pass;
+	}
+	// warp-aggregated append of the pending occurrences
+	const unsigned pm = __ballot_sync(0xffffffffu, pend);
+	if (pm) {
+		unsigned long long at = 0;
+		if (lane == (unsigned)(__ffs(pm) - 1)) at = atomicAdd(p.ctr, (unsigned long long)__popc(pm));
+		at = __shfl_sync(0xffffffffu, at, __ffs(pm) - 1);
+		if (pend) {
+			p.pend[at + __popc(pm & ((1u << lane) - 1))] = (uint32_t)i;
+			uint32_t *w0 = p.bf.w + (pr.blk << 4);
+			if (atomicOr(w0, 1u) & 1u) atomicOr(w0, 2u);
 		}
 	}
-	block_add(p.ctr + 1, n_kmers);
-	block_add(p.ctr + 2, n_pass);
+	unsigned long long n_new = 0;
+	if (pass) {
+		const uint64_t y0 = y0f & ~(1ULL << 63);
+		if (p.tab.slots) n_new = tab_upsert(p.tab, y0, y1, (int)(y0f >> 63)) == 1;
+		else {
+			const BloomProbe ph = bloom_locate(hash_from_y(p.k, y0, y1), p.bf_high.n_shift);
+			bloom_set_atomic(p.bf_high.w + (ph.blk << 4), ph, p.bf_high.n_hashes);
+		}
+	}
+	block_add(p.ctr + 1, valid ? 1ULL : 0ULL);
+	block_add(p.ctr + 2, pass ? 1ULL : 0ULL);
 	if (p.tab.slots) block_add(p.tab.counters, n_new);
 }
 
@@ -131,8 +95,10 @@ __global__ void __launch_bounds__(256) k_count_resolve(CountParams p, uint64_t n
 	const unsigned lane = threadIdx.x & 31;
 	bool conflict = false;
 	uint64_t blk = 0;
+	uint32_t r = 0;
 	if (i < n_pending) {
-		const uint64_t y0 = p.pend_y0[i] & ~(1ULL << 63), y1 = p.pend_y1[i];
+		r = p.pend[i];
+		const uint64_t y0 = p.rec_y0[r] & ~(1ULL << 63), y1 = p.rec_y1[r];
 		const BloomProbe pr = bloom_locate(hash_from_y(p.k, y0, y1), p.bf.n_shift);
 		uint32_t *w = p.bf.w + (pr.blk << 4);
 		blk = pr.blk;
@@ -149,8 +115,8 @@ __global__ void __launch_bounds__(256) k_count_resolve(CountParams p, uint64_t n
 		at = __shfl_sync(0xffffffffu, at, __ffs(cm) - 1);
 		if (conflict) {
 			at += __popc(cm & ((1u << lane) - 1));
-			p.conf_key[at] = blk << 32 | p.pend_t[i];
-			p.conf_val[at] = (uint32_t)i;
+			p.conf_key[at] = blk << 32 | enum_pos_of_record(r); // order inside a block = stream order
+			p.conf_val[at] = r;
 		}
 	}
 }
@@ -166,7 +132,7 @@ __global__ void __launch_bounds__(256) k_count_replay(CountParams p, const unsig
 			const int H = p.bf.n_hashes;
 			for (uint64_t j = i; j < n && (key[j] >> 32) == blk; ++j) {
 				const uint32_t r = val[j];
-				const uint64_t y0f = p.pend_y0[r], y0 = y0f & ~(1ULL << 63), y1 = p.pend_y1[r];
+				const uint64_t y0f = p.rec_y0[r], y0 = y0f & ~(1ULL << 63), y1 = p.rec_y1[r];
 				const int is_high = (int)(y0f >> 63);
 				const uint64_t hash = hash_from_y(p.k, y0, y1);
 				const BloomProbe pr = bloom_locate(hash, p.bf.n_shift);
@@ -225,32 +191,38 @@ extern "C" int bfcg_count_batch(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf
 	const uint64_t sub = sub_batch_positions(opt);
 	const uint64_t halo = opt->k - 1;
 	const uint64_t win_max = std::min<uint64_t>(sub, batch->n_bytes) + halo;
+	const uint64_t rec_max = enum_padded(win_max);
 	const bool host = batch->where == BFCG_HOST;
 
 	// carve the arena for the worst case (every occurrence pending and conflicting)
 	size_t temp_bytes = 0;
 	cub::DeviceRadixSort::SortPairs((void*)0, temp_bytes, (const unsigned long long*)0, (unsigned long long*)0,
-	                                (const uint32_t*)0, (uint32_t*)0, (size_t)win_max, 0, 64, rt.stream);
-	size_t o_seq = 0, o_qual = 0, o_y0, o_y1, o_t, o_ck0, o_ck1, o_cv0, o_cv1, o_tmp, o_ctr, tot = 0;
+	                                (const uint32_t*)0, (uint32_t*)0, (size_t)rec_max, 0, 64, rt.stream);
+	size_t o_seq = 0, o_qual = 0, o_y0, o_y1, o_pend, o_ck0, o_ck1, o_cv0, o_cv1, o_tmp, o_ctr, tot = 0;
 	if (host) { o_seq = tot; tot = align_up(tot + win_max, 256); o_qual = tot; tot = align_up(tot + win_max, 256); }
-	o_y0 = tot; tot = align_up(tot + win_max * 8, 256);
-	o_y1 = tot; tot = align_up(tot + win_max * 8, 256);
-	o_t = tot; tot = align_up(tot + win_max * 4, 256);
-	o_ck0 = tot; tot = align_up(tot + win_max * 8, 256);
-	o_ck1 = tot; tot = align_up(tot + win_max * 8, 256);
-	o_cv0 = tot; tot = align_up(tot + win_max * 4, 256);
-	o_cv1 = tot; tot = align_up(tot + win_max * 4, 256);
+	o_y0 = tot; tot = align_up(tot + rec_max * 8, 256);
+	o_y1 = tot; tot = align_up(tot + rec_max * 8, 256);
+	o_pend = tot; tot = align_up(tot + rec_max * 4, 256);
+	o_ck0 = tot; tot = align_up(tot + rec_max * 8, 256);
+	o_ck1 = tot; tot = align_up(tot + rec_max * 8, 256);
+	o_cv0 = tot; tot = align_up(tot + rec_max * 4, 256);
+	o_cv1 = tot; tot = align_up(tot + rec_max * 4, 256);
 	o_tmp = tot; tot = align_up(tot + temp_bytes, 256);
 	o_ctr = tot; tot += 256;
 	uint8_t *a = (uint8_t*)bfcg_arena(tot);
 	if (!a) return BFCG_ERR_NOMEM;
 
+	EnumParams ep;
+	memset(&ep, 0, sizeof(ep));
+	ep.k = opt->k, ep.q = opt->q;
+	ep.rec_y0 = (unsigned long long*)(a + o_y0), ep.rec_y1 = (unsigned long long*)(a + o_y1);
 	CountParams p;
 	memset(&p, 0, sizeof(p));
-	p.k = opt->k, p.q = opt->q;
+	p.k = opt->k;
+	p.rec_y0 = ep.rec_y0, p.rec_y1 = ep.rec_y1;
 	p.bf = bloom_view(bf);
 	if (bf_high) p.bf_high = bloom_view(bf_high);
-	p.pend_y0 = (unsigned long long*)(a + o_y0), p.pend_y1 = (unsigned long long*)(a + o_y1), p.pend_t = (uint32_t*)(a + o_t);
+	p.pend = (uint32_t*)(a + o_pend);
 	p.ctr = (unsigned long long*)(a + o_ctr);
 	p.conf_key = (unsigned long long*)(a + o_ck0), p.conf_val = (uint32_t*)(a + o_cv0);
 	unsigned long long *ck1 = (unsigned long long*)(a + o_ck1);
@@ -264,16 +236,18 @@ extern "C" int bfcg_count_batch(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf
 		if (host) {
 			BFCG_CUDA(cudaMemcpyAsync(a + o_seq, batch->seq + w0, len, cudaMemcpyHostToDevice, rt.stream));
 			if (batch->qual) BFCG_CUDA(cudaMemcpyAsync(a + o_qual, batch->qual + w0, len, cudaMemcpyHostToDevice, rt.stream));
-			p.seq = a + o_seq, p.qual = batch->qual ? a + o_qual : 0;
-		} else p.seq = batch->seq + w0, p.qual = batch->qual ? batch->qual + w0 : 0;
-		p.len = len, p.emit_from = s - w0;
+			ep.seq = a + o_seq, ep.qual = batch->qual ? a + o_qual : 0;
+		} else ep.seq = batch->seq + w0, ep.qual = batch->qual ? batch->qual + w0 : 0;
+		ep.len = len, ep.emit_from = s - w0;
+		p.n_rec = enum_padded(len - ep.emit_from);
 		if (ch) {
 			if ((r = bfcg_tab_reserve(ch, e - s)) != BFCG_OK) return r;
 			p.tab = tab_view(ch);
 		}
 		BFCG_CUDA(cudaMemsetAsync(p.ctr, 0, 64, rt.stream));
-		const unsigned grid = (unsigned)((e - s + CNT_SEG - 1) / CNT_SEG);
-		{ KTime kt(KT_COUNT_PROBE); k_count_probe<<<grid, CNT_THREADS, 0, rt.stream>>>(p); }
+		{ KTime kt(KT_ENUM); k_enum<<<(unsigned)(p.n_rec / ENUM_SEG), ENUM_THREADS, 0, rt.stream>>>(ep); }
+		BFCG_LAUNCH_CHECK();
+		{ KTime kt(KT_COUNT_PROBE); k_count_probe<<<(unsigned)((p.n_rec + 255) / 256), 256, 0, rt.stream>>>(p); }
 		BFCG_LAUNCH_CHECK();
 		unsigned long long c[4];
 		BFCG_CUDA(cudaMemcpyAsync(c, p.ctr, sizeof(c), cudaMemcpyDeviceToHost, rt.stream));
@@ -288,14 +262,13 @@ extern "C" int bfcg_count_batch(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf
 			n_conflict = c[3];
 		}
 		if (n_conflict) {
-			int pos_bits = 1;
-			while ((1ULL << pos_bits) < len) ++pos_bits;
 			size_t tb = temp_bytes;
 			KTime *kts = new KTime(KT_COUNT_SORT);
-			BFCG_CUDA(cub::DeviceRadixSort::SortPairs(a + o_tmp, tb, (const unsigned long long*)p.conf_key, ck1,
-			                                          (const uint32_t*)p.conf_val, cv1, (size_t)n_conflict, 0,
-			                                          32 + (bf->n_shift - BFC_BLK_SHIFT), rt.stream));
+			const cudaError_t se = cub::DeviceRadixSort::SortPairs(a + o_tmp, tb, (const unsigned long long*)p.conf_key, ck1,
+			                                                       (const uint32_t*)p.conf_val, cv1, (size_t)n_conflict, 0,
+			                                                       32 + (bf->n_shift - BFC_BLK_SHIFT), rt.stream);
 			delete kts;
+			BFCG_CUDA(se);
 			rt.n_launches += 1 + (32 + bf->n_shift - BFC_BLK_SHIFT + 7) / 8; // histogram + one onesweep pass per 8 bits
 			{ KTime kt(KT_COUNT_REPLAY); k_count_replay<<<(unsigned)((n_conflict + 255) / 256), 256, 0, rt.stream>>>(p, ck1, cv1, n_conflict); }
 			BFCG_LAUNCH_CHECK();

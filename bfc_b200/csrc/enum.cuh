@@ -1,0 +1,99 @@
+// enum.cuh -- K0 k_enum: canonical k-mer enumeration over a read stream.
+//
+// What worker_count (reference count.c:72-89) and bfc_ec_kcov (correct.c:96-117) do per
+// base -- map the character (bseq.c:9-26), roll the 4-plane k-mer (kmer.h:10-17), reset
+// on a non-ACGT character, track "all k bases have Q >= q" -- and, once k bases are in,
+// bfc_kmer_hash (kmer.h:79-88).  The stream is "reads back to back" (bfc_b200.h): the
+// 0 terminator between reads is a non-ACGT character, so read boundaries need no
+// special handling and the kernel never looks at the offsets.
+//
+// Work split: a CTA stages 256 x 36 stream positions (+ k-1 of warm-up) as 1-byte
+// codes in shared memory with coalesced loads; each thread then rolls over its own 36
+// positions (36 bytes apart = 9 words: conflict-free).  Output is one 16-byte record
+// per position, y1 = ~0 where no k-mer ends:
+//     rec_y0[i] = y[0] | is_high << 63,   rec_y1[i] = y[1]      (y as in bfc_kmer_hash)
+// written in a blocked order (record i of a segment = iteration j * 256 + thread t) so
+// that the stores of a warp are contiguous; enum_pos_of_record() maps back.
+#pragma once
+#include "common.cuh"
+
+#define ENUM_THREADS 256
+#define ENUM_CHUNK   36
+#define ENUM_SEG     (ENUM_THREADS * ENUM_CHUNK)
+#define ENUM_HALO_MAX 64
+
+struct EnumParams {
+	const uint8_t *seq, *qual;   // stream window (device); qual may be 0 (= every base has high quality)
+	uint64_t len;                // bytes in the window
+	uint64_t emit_from;          // window positions < emit_from only warm the rolling k-mer up
+	int k, q;
+	unsigned long long *rec_y0, *rec_y1;
+};
+
+static inline uint64_t enum_padded(uint64_t n_positions) { return (n_positions + ENUM_SEG - 1) / ENUM_SEG * ENUM_SEG; }
+
+// stream position (relative to emit_from) of record r
+__host__ __device__ __forceinline__ uint32_t enum_pos_of_record(uint32_t r)
+{
+	const uint32_t seg = r / ENUM_SEG, rem = r % ENUM_SEG;
+	return seg * ENUM_SEG + (rem % ENUM_THREADS) * ENUM_CHUNK + rem / ENUM_THREADS;
+}
+
+// record index of stream position pos (relative to emit_from)
+__host__ __device__ __forceinline__ uint64_t enum_record_of_pos(uint64_t pos)
+{
+	const uint64_t seg = pos / ENUM_SEG, rem = pos % ENUM_SEG;
+	return seg * ENUM_SEG + (rem % ENUM_CHUNK) * ENUM_THREADS + rem / ENUM_CHUNK;
+}
+
+#ifdef __CUDACC__
+static __global__ void __launch_bounds__(ENUM_THREADS) k_enum(EnumParams p)
+{
+	__shared__ uint8_t s_code[ENUM_SEG + ENUM_HALO_MAX];
+	const int halo = p.k - 1;
+	const int64_t seg0 = (int64_t)p.emit_from + (int64_t)blockIdx.x * ENUM_SEG;
+
+	// stage the CTA's window as codes: bits 0-2 base (4 = not ACGT / outside), bit 3 Q >= q
+	for (int i = threadIdx.x; i < ENUM_SEG + halo; i += ENUM_THREADS) {
+		const int64_t pos = seg0 - halo + i;
+		uint32_t c = 4;
+		if (pos >= 0 && (uint64_t)pos < p.len) {
+			c = base_code(__ldg(p.seq + pos));
+			if (c < 4 && (p.qual == 0 || (int)__ldg(p.qual + pos) - 33 >= p.q)) c |= 8;
+		}
+		s_code[i] = (uint8_t)c;
+	}
+	__syncthreads();
+
+	const int base = threadIdx.x * ENUM_CHUNK;
+	const int k = p.k;
+	const uint64_t mask = (1ULL << k) - 1;
+	uint64_t x[4] = {0, 0, 0, 0}, qmer = 0;
+	int l = 0;
+	unsigned long long *o0 = p.rec_y0 + (uint64_t)blockIdx.x * ENUM_SEG + threadIdx.x;
+	unsigned long long *o1 = p.rec_y1 + (uint64_t)blockIdx.x * ENUM_SEG + threadIdx.x;
+
+	for (int j = 0; j < halo; ++j) { // warm-up: roll only
+		const uint32_t c = s_code[base + j];
+		if ((c & 7) < 4) {
+			bfc_kmer_append(k, x, c & 3);
+			qmer = (qmer << 1 | (c >> 3)) & mask;
+			++l;
+		} else l = 0, qmer = 0, x[0] = x[1] = x[2] = x[3] = 0;
+	}
+	for (int j = 0; j < ENUM_CHUNK; ++j) {
+		const uint32_t c = s_code[base + halo + j];
+		uint64_t y[2] = {0, ~0ULL};
+		if ((c & 7) < 4) {
+			bfc_kmer_append(k, x, c & 3);
+			qmer = (qmer << 1 | (c >> 3)) & mask;
+			if (++l >= k) {
+				bfc_kmer_hash(k, x, y);
+				y[0] |= (unsigned long long)(qmer == mask) << 63;
+			}
+		} else l = 0, qmer = 0, x[0] = x[1] = x[2] = x[3] = 0;
+		o0[j * ENUM_THREADS] = y[0];
+		o1[j * ENUM_THREADS] = y[1];
+	}
+}
+#endif
