@@ -5,7 +5,7 @@
  * legs may load liboracle.so; the product library never does.
  *
  * Parity of this restatement is PINNED against the unmodified reference compiled
- * into oracle/_ref/ (see oracle/Makefile, tests/test_oracle_vs_ref.py) and against
+ * into oracle/_ref/ (see oracle/Makefile, tests/test_oracle_golden.py) and against
  * the golden fixtures under tests/golden/ that were produced by that reference
  * binary (tools/make_golden.py).  The reference ships no tests of its own.
  *
