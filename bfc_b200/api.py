@@ -145,7 +145,7 @@ def lib():
 
 
 KERNEL_NAMES = ["count_probe", "count_resolve", "conflict_sort", "count_replay", "correct", "correct_redo", "trim",
-                "tab_rehash", "tab_hist", "tab_apply", "enum", "ec_lookup"]
+                "tab_rehash", "tab_hist", "tab_apply", "enum", "ec_lookup", "ec_setup", "ec_merge"]
 
 
 def kernel_times():

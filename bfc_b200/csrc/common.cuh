@@ -42,7 +42,7 @@ struct BfcgRuntime {
 };
 
 enum { KT_COUNT_PROBE = 0, KT_COUNT_RESOLVE, KT_COUNT_SORT, KT_COUNT_REPLAY, KT_CORRECT, KT_CORRECT_REDO,
-       KT_TRIM, KT_TAB_REHASH, KT_TAB_HIST, KT_TAB_APPLY, KT_ENUM, KT_EC_LOOKUP, KT_N };
+       KT_TRIM, KT_TAB_REHASH, KT_TAB_HIST, KT_TAB_APPLY, KT_ENUM, KT_EC_LOOKUP, KT_EC_SETUP, KT_EC_MERGE, KT_N };
 
 int  bfcg_kt_begin(int id);   // records a start event on the stream when timing is on; returns a span index or -1
 void bfcg_kt_end(int idx);

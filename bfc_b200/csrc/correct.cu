@@ -2,25 +2,40 @@
 // kt_for(..., worker_ec, ...) (correct.c:587): bfc_ec1 per read (correct.c:388-472)
 // with its two bfc_ec1dir heap searches (correct.c:249-386).
 //
-// Three kernels per batch:
-//   K0 k_enum         (enum.cuh) canonical k-mer hash of every stream position
-//   K5 k_ec_lookup    bfc_ec_kcov's one-lookup-per-k-mer (correct.c:106) for the whole
-//                     batch at once: a thread does 36 independent table probes, results
-//                     go to occ16[position] through shared memory (coalesced both ways)
-//   K6 k_ec_read      one read per thread: per-base coverage flags, longest solid
-//                     island, rescue, the two heap searches, merge, rewrite.
+// The read stream of a batch window is turned into BIT PLANES (one bit per stream
+// position) and a 16-bit flag word per base; the search then works on those:
 //
-// The search is a chain of dependent table lookups, so throughput comes from reads in
-// flight.  Two things keep a search step cheap without changing its result:
-//   * the heap lives in global memory, but while it holds a single state (the common,
-//     unbranched walk) that state stays in registers -- states enter the memory heap
-//     in exactly the reference's push order, so ties pop identically (ksort.h:125-146);
-//   * the lookup of the READ's own k-mer at a position (`os`, correct.c:299) is the
-//     value K5 already fetched whenever the path has matched the original read for the
-//     last k-1 bases; only k-mers that contain an edit are hashed and probed again.
-// Each thread owns a fixed heap (max_heap + 4 states suffice: growth stops at
-// max_heap, correct.c:349) and a fixed stack; a read whose stack overflows is re-run by
-// the same kernel with a larger stack (never on the CPU).
+//   K0  k_enum       (enum.cuh) canonical k-mer hash of every stream position
+//   K5  k_ec_lookup  bfc_ec_kcov's one-lookup-per-k-mer (correct.c:106) for the whole
+//                    window at once (36 independent probes per thread) -> planes
+//                    B0 B1 NB Q (base bits, non-ACGT, Q >= q) and SOL HS A H (what
+//                    the search ever asks about a read k-mer's table value)
+//   K5b k_ec_cov     lcov / hcov thresholds (correct.c:109-112) as sliding popcounts
+//                    over SOL / HS -> the per-base flag word, and the two "jump" planes
+//                    (positions a lone search state steps over without any decision)
+//   K6a k_ec_setup   one read per thread: >5 % N, longest solid island (correct.c:119-130)
+//                    by run scanning, the rare single-edit rescue (correct.c:63-94, 405-421)
+//   K6b k_ec_search  the heap search, one (read, direction) JOB per thread at a time,
+//                    persistent threads.  The thread is a resumable state machine whose
+//                    only table lookup sits at ONE place in the loop, so the lanes of
+//                    a warp hash and probe together whatever step each of them is in.
+//   K6c k_ec_merge   one read per warp: merge the two directions, rewrite seq / qual
+//                    (correct.c:443-459), pack aux / aux2 (correct.c:552-553); coalesced.
+//
+// What keeps a search step cheap without changing its result:
+//   * the lookup of the READ's own k-mer at a position (`os`, correct.c:299) is what K5
+//     fetched whenever the path has matched the original read for the last k-1 bases;
+//   * while the search holds a single state and the next positions are "fixed" with no
+//     penalty, the state moves over all of them at once (count-trailing-ones on the
+//     jump plane) and its k-mer is re-extracted from the base planes in O(1);
+//   * the heap orders 4-byte keys (penalty, slot); states sit in a slot pool; a lone
+//     state never leaves registers.  States enter the heap in exactly the reference's
+//     push order and the sift rules are klib's (ksort.h:125-146), so ties pop identically;
+//   * the reference's per-push stack (correct.c:162-167) is only ever read to recover
+//     the edited bases, the absent count and the final penalty of a path: states carry
+//     the latter two, and only pushes that CHANGE a base get a (parent-linked) entry.
+// A job whose edit list overflows its fixed scratch is re-run by the same kernel with a
+// larger one (never on the CPU).
 //
 // Pop/push order and every threshold follow the reference exactly: the `ec:Z:` tag
 // exposes max_heap / n_absent, so the search internals are part of byte parity.
@@ -30,310 +45,195 @@
 #include <climits>
 #include <vector>
 
-#define EC_OVERFLOW (-100)
-#define OCC_NONE 0xFFFFu
+// plane indices (bit i of a plane = stream position i - PL_PAD of the window)
+enum { PL_B0 = 0, PL_B1, PL_NB, PL_Q, PL_SOL, PL_HS, PL_A, PL_H, PL_J0, PL_J1,
+       PL_E0V, PL_E0L, PL_E0H, PL_E1V, PL_E1L, PL_E1H, PL_N };
+#define PL_PAD 64  // leading zero bits so that "64 bits ending at position p" never underflows
 
-struct HeapEnt {                 // reference correct.c:153-160 (echeap1_t) + `clean`
-	int tot_pen, i, k;
+// per-base flag word (k_ec_cov)
+#define FL_OB(v)   ((v) & 7)   // original base code 0..4
+#define FL_Q       8           // Q >= q (0 for non-ACGT)
+#define FL_LC      16          // lcov >= min_cov + 1
+#define FL_HC      32          // hcov > 0.75 k
+#define FL_SOL     64          // the k-mer ENDING here: in the table with cnt >= min_cov
+#define FL_A       128         //   (os & 0xff) >= min_cov + 1, os = -1 counting as 255 (correct.c:299-300)
+#define FL_H       256         //   in the table with high count >= min_cov
+
+struct ReadDesc {              // k_ec_setup -> k_ec_search / k_ec_merge
+	int start0, start1;        // search starts of the two directions; start0 < 0: no search
+	int brute;                 // rescue edit: pos << 2 | base, or -1
+	int code;                  // ec_code decided by the setup (2, 3) or 0
+};
+
+struct EcState {               // reference correct.c:153-160 (echeap1_t); see the header for `edit` / `n_absent`
+	int tot_pen, i;
+	int edit;                  // most recent edit entry on this path, -1 = none
+	int n_absent;              // pushes with pen.absent at positions < n along this path
+	int clean;                 // trailing path bases equal to the ORIGINAL read (memoised lookups)
 	int ecpos_high[BFC_EC_HIST_HIGH];
 	int ecpos[BFC_EC_HIST];
-	int clean;                   // trailing path bases equal to the original read (memoised lookups)
 	uint64_t x[4];
 };
-
-struct StackEnt {                // reference correct.c:162-167 (ecstack1_t), cnt dropped (only logged)
-	int parent, i, tot_pen;
-	uint32_t info;               // b | ec << 4 | ec_high << 5 | absent << 6 | absent_high << 7
-};
-
-struct Pen { int ec, ec_high, absent, absent_high, b; };
 
 struct EcParams {
 	const uint64_t *off;
 	uint8_t *seq, *qual;
 	int64_t n_reads;
-	uint64_t base0;              // stream offset of the window: occ16 / scratch index = off - base0
+	uint64_t base0;              // stream offset of the window: plane / flag index = off - base0
 	uint32_t *aux;
-	const uint16_t *occ16;       // per window position: bfc_ch_kmer_occ of the k-mer ending there, OCC_NONE = absent / no k-mer
-	uint8_t *fb, *p0, *p1;       // per-base scratch (window-relative)
+	const uint64_t *pl;          // PL_N planes of pl_words 64-bit words each
+	uint64_t pl_words;
+	const uint16_t *fl;          // per window position
+	ReadDesc *desc;
+	int2 *res;                   // per job: (return value of bfc_ec1dir, max_heap)
 	TabView tab;
 	int k, q, min_cov, win_multi_ec, max_end_ext;
 	int w_ec, w_ec_high, w_absent, w_absent_high, max_path_diff, max_heap, mode;
-	HeapEnt *heap;               // heap_cap entries per thread slot
-	StackEnt *stack;             // stack_cap entries per thread slot
-	int heap_cap, stack_cap;
-	const uint32_t *redo;        // when set: thread slot s handles read redo[s]; n_reads = #redo
-	uint32_t *overflow;          // read indices whose stack overflowed
+	EcState *pool;               // heap_cap states per thread slot
+	uint32_t *heapk;             // heap_cap keys per thread slot: tot_pen << 12 | pool slot
+	uint2 *edits;                // edit_cap entries per thread slot: (parent, pos << 3 | base), forward coordinates
+	int heap_cap, edit_cap;
+	const uint32_t *redo;        // when set: thread job list (job = read * 2 + dir); n_jobs = its length
+	int64_t n_jobs;
+	uint32_t *overflow;          // jobs whose edit list overflowed
 	unsigned long long *ctr;     // [0] n_overflow, [1] n_lookups
 };
 
-// per-base scratch byte
-#define FB_B(v)        ((v) & 7)
-#define FB_Q           8
-#define FB_LCOV        16   // lcov >= min_cov + 1
-#define FB_HCOV        32   // hcov > 0.75 k
-#define FB_SOLID       64   // solid_end
-#define FB_HSOLID      128  // solid_end && high_end
-
 __device__ __forceinline__ int comp_b(int b) { return b < 4 ? 3 - b : 4; }
 
-// ------------------------------------------------------------------ K5: batched k-mer lookups
+__device__ __forceinline__ const uint64_t *plane(const EcParams &P, int which) { return P.pl + (uint64_t)which * P.pl_words; }
 
-__global__ void __launch_bounds__(ENUM_THREADS) k_ec_lookup(TabView tab, const unsigned long long *rec_y0, const unsigned long long *rec_y1,
-                                                              uint16_t *occ16, uint64_t n_pos, unsigned long long *ctr)
+// 64 plane bits starting at window position `pos` (pos >= -PL_PAD)
+__device__ __forceinline__ uint64_t bits64(const uint64_t *pl, int64_t pos)
 {
-	__shared__ uint16_t s_occ[ENUM_SEG];
+	const uint64_t p = (uint64_t)(pos + PL_PAD);
+	const uint64_t *w = pl + (p >> 6);
+	const int r = (int)(p & 63);
+	const uint64_t lo = __ldg(w), hi = __ldg(w + 1);
+	return r ? (lo >> r) | (hi << (64 - r)) : lo;
+}
+
+__device__ __forceinline__ int bit1(const uint64_t *pl, int64_t pos)
+{
+	const uint64_t p = (uint64_t)(pos + PL_PAD);
+	return (int)(__ldg(pl + (p >> 6)) >> (p & 63)) & 1;
+}
+
+// ------------------------------------------------------------------ K5: batched k-mer lookups -> planes
+
+struct LookupParams {
+	TabView tab;
+	const unsigned long long *rec_y0, *rec_y1;
+	const uint8_t *seq, *qual;
+	uint64_t n_pos;
+	uint64_t *pl;
+	uint64_t pl_words;
+	int q, min_cov;
+	unsigned long long *ctr;
+};
+
+__global__ void __launch_bounds__(ENUM_THREADS) k_ec_lookup(LookupParams p)
+{
+	__shared__ uint8_t s_fl[ENUM_SEG];
 	const uint64_t seg = blockIdx.x;
 	unsigned long long n_lookups = 0;
 	for (int j = 0; j < ENUM_CHUNK; ++j) {
 		const uint64_t i = seg * ENUM_SEG + (uint64_t)j * ENUM_THREADS + threadIdx.x;
-		const unsigned long long y1 = __ldg(rec_y1 + i);
-		uint32_t v = OCC_NONE;
+		const unsigned long long y1 = __ldg(p.rec_y1 + i);
+		uint32_t f = 4; // bit 0 SOL, 1 HS, 2 A, 3 H
 		if (y1 != ~0ULL) {
-			const int r = tab_get(tab, __ldg(rec_y0 + i) & ~(1ULL << 63), y1);
-			if (r >= 0) v = (uint32_t)r;
+			const int r = tab_get(p.tab, __ldg(p.rec_y0 + i) & ~(1ULL << 63), y1);
+			if (r >= 0) {
+				const int cnt = r & 0xff, high = r >> 8 & 0x3f;
+				f = (cnt >= p.min_cov ? 1u : 0u) | (cnt >= p.min_cov && high >= p.min_cov + 1 ? 2u : 0u) |
+				    (cnt >= p.min_cov + 1 ? 4u : 0u) | (high >= p.min_cov ? 8u : 0u);
+			}
 			++n_lookups;
 		}
-		s_occ[threadIdx.x * ENUM_CHUNK + j] = (uint16_t)v;
+		s_fl[threadIdx.x * ENUM_CHUNK + j] = (uint8_t)f;
 	}
 	__syncthreads();
+	uint32_t *pl32 = (uint32_t*)p.pl;
+	const uint64_t stride32 = p.pl_words * 2;
 	for (int idx = threadIdx.x; idx < ENUM_SEG; idx += ENUM_THREADS) {
 		const uint64_t pos = seg * ENUM_SEG + idx;
-		if (pos < n_pos) occ16[pos] = s_occ[idx];
-	}
-	block_add(ctr + 1, n_lookups);
-}
-
-// ------------------------------------------------------------------ K6: per-read search
-
-// view of the read in search coordinates (dir 1 = reverse complement, correct.c:39-57)
-struct RView {
-	const uint8_t *fb, *seq;
-	const uint16_t *occ;
-	int n, dir, k;
-	__device__ __forceinline__ uint8_t raw(int i) const { return fb[dir ? n - 1 - i : i]; }
-	__device__ __forceinline__ int b(int i) const { const int v = FB_B(raw(i)); return dir ? comp_b(v) : v; }
-	// the ORIGINAL read base (what K5's k-mers were made of)
-	__device__ __forceinline__ int ob(int i) const { const int v = base_code(seq[dir ? n - 1 - i : i]); return dir ? comp_b(v) : v; }
-	// K5's value for the read k-mer that ends at search position i
-	__device__ __forceinline__ int occ_end(int i) const
-	{
-		const uint32_t v = occ[dir ? n - 1 - i + k - 1 : i];
-		return v == OCC_NONE ? -1 : (int)v;
-	}
-};
-
-// klib heap with "less" = larger tot_pen: root = smallest penalty (correct.c:179, ksort.h:125-146)
-__device__ __forceinline__ void heap_down(HeapEnt *l, int n)
-{
-	int i = 0, c;
-	const HeapEnt tmp = l[0];
-	while ((c = 2 * i + 1) < n) {
-		if (c != n - 1 && l[c].tot_pen > l[c + 1].tot_pen) ++c;
-		if (l[c].tot_pen > tmp.tot_pen) break;
-		l[i] = l[c]; i = c;
-	}
-	l[i] = tmp;
-}
-
-__device__ __forceinline__ void heap_up(HeapEnt *l, int n)
-{
-	int c = n - 1;
-	const HeapEnt tmp = l[c];
-	while (c) {
-		const int par = (c - 1) >> 1;
-		if (tmp.tot_pen > l[par].tot_pen) break;
-		l[c] = l[par]; c = par;
-	}
-	l[c] = tmp;
-}
-
-__device__ __forceinline__ int pen_weight(const EcParams &P, const Pen &p)
-{
-	return P.w_ec * p.ec + P.w_ec_high * p.ec_high + P.w_absent * p.absent + P.w_absent_high * p.absent_high;
-}
-
-// Logical heap = memory heap[0..heap_n) plus, when `top_valid`, one state held in
-// registers (`top`).  Invariant: top_valid implies heap_n == 0, so the logical heap is
-// either {top} or the memory heap; states reach the memory heap in push order.
-struct SearchState {
-	HeapEnt *heap;
-	StackEnt *stack;
-	int heap_n, stack_n, stack_cap, heap_cap;
-	bool top_valid;
-	HeapEnt top;
-	__device__ __forceinline__ int size() const { return heap_n + (top_valid ? 1 : 0); }
-};
-
-// reference correct.c:198-230 (buf_update); false when the stack is full
-__device__ __forceinline__ bool push_state(const EcParams &P, SearchState &S, const HeapEnt &prev, const Pen &pen, int ob_prev)
-{
-	if (S.stack_n >= S.stack_cap || S.heap_n + 2 > S.heap_cap) return false;
-	StackEnt q;
-	q.parent = prev.k, q.i = prev.i;
-	q.info = (uint32_t)pen.b | pen.ec << 4 | pen.ec_high << 5 | pen.absent << 6 | pen.absent_high << 7;
-	q.tot_pen = prev.tot_pen + pen_weight(P, pen);
-	S.stack[S.stack_n++] = q;
-	HeapEnt r;
-	r.i = prev.i + 1;
-	r.k = S.stack_n - 1;
-	r.x[0] = prev.x[0], r.x[1] = prev.x[1], r.x[2] = prev.x[2], r.x[3] = prev.x[3];
-	if (pen.ec_high) r.ecpos_high[0] = prev.i, r.ecpos_high[1] = prev.ecpos_high[0];
-	else r.ecpos_high[0] = prev.ecpos_high[0], r.ecpos_high[1] = prev.ecpos_high[1];
-	if (pen.ec) {
-		r.ecpos[0] = prev.i;
-#pragma unroll
-		for (int t = 1; t < BFC_EC_HIST; ++t) r.ecpos[t] = prev.ecpos[t - 1];
-	} else {
-#pragma unroll
-		for (int t = 0; t < BFC_EC_HIST; ++t) r.ecpos[t] = prev.ecpos[t];
-	}
-	r.tot_pen = q.tot_pen;
-	r.clean = pen.b == ob_prev ? prev.clean + 1 : 0;
-	bfc_kmer_append(P.k, r.x, pen.b);
-	if (S.heap_n == 0 && !S.top_valid) { S.top = r; S.top_valid = true; return true; }
-	if (S.top_valid) { // a second state arrives: the register state goes to memory first (same order as the reference)
-		S.heap[S.heap_n++] = S.top;
-		heap_up(S.heap, S.heap_n);
-		S.top_valid = false;
-	}
-	S.heap[S.heap_n++] = r;
-	heap_up(S.heap, S.heap_n);
-	return true;
-}
-
-// reference correct.c:249-386 (bfc_ec1dir).  `path` receives ec[].b in FORWARD read
-// coordinates (for dir 1 that is the result after the reference's final revcomp).
-__device__ int ec_search(const EcParams &P, const RView &rv, int start, int end, SearchState &S, uint8_t *path,
-                         int &max_heap, bool memo, unsigned long long &n_lookups)
-{
-	const int k = P.k, n = rv.n;
-	HeapEnt z;
-	int rvl = -1, n_paths = 0, best = -1, best_pen = INT_MAX, n_fail = 0, run = 0;
-	int paths[BFC_MAX_PATHS];
-	S.heap_n = S.stack_n = 0, S.top_valid = false;
-	max_heap = 0;
-	z.tot_pen = 0, z.k = -1, z.clean = 0;
-	z.x[0] = z.x[1] = z.x[2] = z.x[3] = 0;
-	for (z.i = start; z.i < end; ++z.i) { // seed: k-1 bases (correct.c:260-267)
-		const int c = rv.b(z.i);
-		if (c < 4) {
-			if (++run == k) break;
-			bfc_kmer_append(k, z.x, c);
-			z.clean = c == rv.ob(z.i) ? z.clean + 1 : 0;
-		} else run = 0, z.clean = 0, z.x[0] = z.x[1] = z.x[2] = z.x[3] = 0;
-	}
-	if (z.i >= end) return -1; // the reference asserts; cannot happen after an island / rescue was found
-#pragma unroll
-	for (int t = 0; t < BFC_EC_HIST; ++t) z.ecpos[t] = -1;
-#pragma unroll
-	for (int t = 0; t < BFC_EC_HIST_HIGH; ++t) z.ecpos_high[t] = -1;
-	S.top = z, S.top_valid = true;
-
-	for (;;) {
-		bool stop = false;
-		{
-			const int hs = S.size();
-			max_heap = max_heap > 255 ? 255 : max_heap > hs ? max_heap : hs;
-			if (hs == 0) { rvl = -2; break; }
+		uint32_t c = 4, q = 0;
+		if (pos < p.n_pos) {
+			c = base_code(__ldg(p.seq + pos));
+			q = c < 4 && (p.qual == 0 || (int)__ldg(p.qual + pos) - 33 >= p.q);
 		}
-		if (S.top_valid) { z = S.top; S.top_valid = false; }
-		else {
-			z = S.heap[0];
-			S.heap[0] = S.heap[--S.heap_n];
-			heap_down(S.heap, S.heap_n);
-		}
-		if (best >= 0 && z.tot_pen > best_pen + P.max_path_diff) break;
-		if (z.i - end > P.max_end_ext) stop = true;
-		if (!stop) {
-			const bool has_c = z.i < n;
-			const uint8_t craw = has_c ? rv.raw(z.i) : 0;
-			const int cb = has_c ? (rv.dir ? comp_b(FB_B(craw)) : FB_B(craw)) : -1;
-			const int cq = (craw & FB_Q) != 0;
-			const int cob = has_c ? rv.ob(z.i) : -1;
-			int os = -1, other_ext = 0, n_added = 0;
-			bool fixed = z.i > end;
-			Pen added[4];
-			if (has_c && cb < 4) {
-				if (memo && z.clean >= k - 1 && cb == cob) os = rv.occ_end(z.i); // the read's own k-mer: fetched by K5
-				else {
-					uint64_t x[4] = { z.x[0], z.x[1], z.x[2], z.x[3] };
-					bfc_kmer_append(k, x, cb);
-					os = tab_kmer_occ(P.tab, x);
-					++n_lookups;
-				}
-				if (cq && (os & 0xff) >= P.min_cov + 1 && (craw & FB_LCOV)) fixed = true;
-				else if (craw & FB_HCOV) fixed = true;
-			}
-			for (int b = 0; b < 4; ++b) {
-				Pen pen;
-				if (fixed && has_c && b != cb) continue;
-				if (!has_c || b != cb) {
-					if (has_c) {
-						if (cq && z.ecpos_high[BFC_EC_HIST_HIGH - 1] >= 0 && z.i - z.ecpos_high[BFC_EC_HIST_HIGH - 1] < P.win_multi_ec) continue;
-						if (z.ecpos[BFC_EC_HIST - 1] >= 0 && z.i - z.ecpos[BFC_EC_HIST - 1] < P.win_multi_ec) continue;
-					}
-					uint64_t x[4] = { z.x[0], z.x[1], z.x[2], z.x[3] };
-					bfc_kmer_append(k, x, b);
-					const int s = tab_kmer_occ(P.tab, x);
-					++n_lookups;
-					if (s < 0 || (s & 0xff) < P.min_cov) continue;
-					pen.ec = has_c && cb < 4 ? 1 : 0;
-					pen.ec_high = pen.ec ? cq : 0; // oq == q for every base (correct.c:32-33)
-					pen.absent = 0;
-					pen.absent_high = ((s >> 8 & 0xff) < P.min_cov);
-					pen.b = b;
-					added[n_added++] = pen;
-					++other_ext;
-				} else {
-					pen.ec = pen.ec_high = 0;
-					pen.absent = (os < 0 || (os & 0xff) < P.min_cov);
-					pen.absent_high = (os < 0 || (os >> 8 & 0xff) < P.min_cov);
-					pen.b = b;
-					added[n_added++] = pen;
-				}
-			}
-			if (!fixed && other_ext == 0) ++n_fail;
-			if (n_fail > n * 2) { rvl = -3; break; }
-			if (has_c || n_added == 1) {
-				if (n_added > 1 && S.size() > P.max_heap) { // keep only the cheapest extension (first on ties)
-					int min_b = -1, min = INT_MAX;
-					for (int b = 0; b < n_added; ++b) {
-						const int t = pen_weight(P, added[b]);
-						if (min > t) min = t, min_b = b;
-					}
-					if (!push_state(P, S, z, added[min_b], cob)) return EC_OVERFLOW;
-				} else {
-					for (int b = 0; b < n_added; ++b)
-						if (!push_state(P, S, z, added[b], cob)) return EC_OVERFLOW;
-				}
-			} else {
-				if (n_added == 0) S.stack[z.k].tot_pen += P.w_absent * (P.max_end_ext - (z.i - end));
-				stop = true;
-			}
-		}
-		if (stop) {
-			if (S.stack[z.k].tot_pen < best_pen) best_pen = S.stack[z.k].tot_pen, best = n_paths;
-			paths[n_paths++] = z.k;
-			if (n_paths == BFC_MAX_PATHS) break;
+		const uint32_t f = s_fl[idx];
+		const uint32_t b0 = __ballot_sync(0xffffffffu, c & 1), b1 = __ballot_sync(0xffffffffu, c & 2);
+		const uint32_t nb = __ballot_sync(0xffffffffu, c > 3), bq = __ballot_sync(0xffffffffu, q);
+		const uint32_t sol = __ballot_sync(0xffffffffu, f & 1), hs = __ballot_sync(0xffffffffu, f & 2);
+		const uint32_t fa = __ballot_sync(0xffffffffu, f & 4), fh = __ballot_sync(0xffffffffu, f & 8);
+		if ((threadIdx.x & 31) == 0) {
+			uint32_t *w = pl32 + (pos + PL_PAD) / 32;
+			w[PL_B0 * stride32] = b0, w[PL_B1 * stride32] = b1, w[PL_NB * stride32] = nb, w[PL_Q * stride32] = bq;
+			w[PL_SOL * stride32] = sol, w[PL_HS * stride32] = hs, w[PL_A * stride32] = fa, w[PL_H * stride32] = fh;
 		}
 	}
-	if (n_paths == 0) return rvl;
-	// ec[].b := read bases, then the best path (buf_backtrack, correct.c:232-247), then the mask (correct.c:378-379)
-	for (int j = 0; j < n; ++j) path[j] = FB_B(rv.fb[j]);
-	int n_absent = 0;
-	for (int e = paths[best]; e >= 0; e = S.stack[e].parent) {
-		const int i = S.stack[e].i;
-		if (i < n) {
-			const int b = S.stack[e].info & 15;
-			path[rv.dir ? n - 1 - i : i] = (uint8_t)(rv.dir ? comp_b(b) : b);
-			n_absent += S.stack[e].info >> 6 & 1;
-		}
-	}
-	for (int i = 0; i < n; ++i)
-		if (i < start + k || i >= end) path[rv.dir ? n - 1 - i : i] = 4;
-	return n_absent;
+	block_add(p.ctr + 1, n_lookups);
 }
+
+// ------------------------------------------------------------------ K5b: coverage flags + jump planes
+
+// reference correct.c:109-112: lcov[j] / hcov[j] = number of solid (solid && high_end)
+// k-mers covering base j = those ENDING in [j, j+k-1].  A window never picks up bits of
+// the next read: no k-mer ends on a terminator or on the first k-1 bases of a read.
+__global__ void __launch_bounds__(256) k_ec_cov(EcParams P, uint64_t n_pos, uint16_t *fl, uint64_t *pl_out)
+{
+	const uint64_t pos = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; // n_pos is a multiple of 32
+	const int k = P.k;
+	const uint64_t kmask = (1ULL << k) - 1;
+	uint32_t f = 4;
+	bool j0 = false, j1 = false;
+	if (pos < n_pos) {
+		const int64_t p = (int64_t)pos;
+		const int b = bit1(plane(P, PL_B0), p) | bit1(plane(P, PL_B1), p) << 1, nb = bit1(plane(P, PL_NB), p);
+		const int q = bit1(plane(P, PL_Q), p);
+		const int lc = __popcll(bits64(plane(P, PL_SOL), p) & kmask) >= P.min_cov + 1;
+		const int hc = 4 * __popcll(bits64(plane(P, PL_HS), p) & kmask) > 3 * k; // hcov > k * .75
+		const int sol = bit1(plane(P, PL_SOL), p), a = bit1(plane(P, PL_A), p), h = bit1(plane(P, PL_H), p);
+		f = (uint32_t)(nb ? 4 : b) | (q ? FL_Q : 0) | (lc ? FL_LC : 0) | (hc ? FL_HC : 0) | (sol ? FL_SOL : 0) | (a ? FL_A : 0) | (h ? FL_H : 0);
+		// a lone state whose last k-1 bases are the read's steps over this base without a decision when the
+		// base is "fixed" (correct.c:299-301) and its own k-mer costs nothing (correct.c:334-336)
+		j0 = !nb && ((q && a && lc) || hc) && sol && h;
+		// reverse direction: the k-mer ending (in search order) on this base ends k-1 positions further in the stream
+		const int sol1 = bit1(plane(P, PL_SOL), p + k - 1), a1 = bit1(plane(P, PL_A), p + k - 1), h1 = bit1(plane(P, PL_H), p + k - 1);
+		j1 = !nb && ((q && a1 && lc) || hc) && sol1 && h1;
+		fl[pos] = (uint16_t)f;
+	}
+	const uint32_t m0 = __ballot_sync(0xffffffffu, j0), m1 = __ballot_sync(0xffffffffu, j1);
+	if ((threadIdx.x & 31) == 0 && pos < n_pos) {
+		uint32_t *w = (uint32_t*)pl_out + (pos + PL_PAD) / 32;
+		w[(uint64_t)PL_J0 * P.pl_words * 2] = m0, w[(uint64_t)PL_J1 * P.pl_words * 2] = m1;
+	}
+}
+
+// ------------------------------------------------------------------ k-mer extraction from the base planes
+
+// The 4-plane k-mer state (kmer.h:10-17) after appending, to an empty state, the m <= 63
+// ORIGINAL read bases that end at search position e of direction dir (read at window
+// position o, length n).  `bp`/`bb`: optional base override (rescue edit) in forward coordinates.
+__device__ __forceinline__ void extract_kmer(const EcParams &P, int64_t o, int n, int dir, int e, int m, int bp, int bb, uint64_t x[4])
+{
+	const int ws = dir ? n - 1 - e : e - m + 1; // forward position of the lowest window bit
+	const uint64_t mm = m >= 64 ? ~0ULL : (1ULL << m) - 1;
+	uint64_t w0 = bits64(plane(P, PL_B0), o + ws) & mm, w1 = bits64(plane(P, PL_B1), o + ws) & mm;
+	if (bp >= ws && bp < ws + m) {
+		const int t = bp - ws;
+		w0 = (w0 & ~(1ULL << t)) | (uint64_t)(bb & 1) << t;
+		w1 = (w1 & ~(1ULL << t)) | (uint64_t)(bb >> 1) << t;
+	}
+	const uint64_t r0 = m ? __brevll(w0) >> (64 - m) : 0, r1 = m ? __brevll(w1) >> (64 - m) : 0;
+	const uint64_t c0 = ~w0 & mm, c1 = ~w1 & mm;
+	const int up = P.k - m;
+	if (!dir) x[0] = r0, x[1] = r1, x[2] = c0 << up, x[3] = c1 << up;
+	else x[0] = c0, x[1] = c1, x[2] = r0 << up, x[3] = r1 << up;
+}
+
+// ------------------------------------------------------------------ K6a: per-read setup
 
 // reference correct.c:63-80
 __device__ int ec_greedy_k(const EcParams &P, const uint64_t x[4], unsigned long long &n_lookups)
@@ -356,131 +256,448 @@ __device__ int ec_greedy_k(const EcParams &P, const uint64_t x[4], unsigned long
 	return (max & 0xff) * 3 > P.mode && (max2 & 0xff) < 3 ? max_ec : -1;
 }
 
-// reference correct.c:82-94
-__device__ int ec_first_kmer(int k, const uint8_t *fb, int n, int start, uint64_t x[4])
+// reference correct.c:82-94: position of the k-th base of the first run of k ACGT bases at or after `start` (n if none)
+__device__ int ec_first_kmer_end(const EcParams &P, int64_t o, int n, int start)
 {
-	int i, l = 0;
-	x[0] = x[1] = x[2] = x[3] = 0;
-	for (i = start; i < n; ++i) {
-		const int b = FB_B(fb[i]);
-		if (b < 4) {
-			bfc_kmer_append(k, x, b);
-			if (++l == k) break;
-		} else l = 0, x[0] = x[1] = x[2] = x[3] = 0;
+	const int k = P.k;
+	const uint64_t kmask = (1ULL << k) - 1;
+	int p = start;
+	while (p + k <= n) {
+		const uint64_t w = bits64(plane(P, PL_NB), o + p) & kmask;
+		if (w == 0) return p + k - 1;
+		p += 64 - __clzll(w); // just past the last non-ACGT base of the window
 	}
-	return i;
+	return n;
 }
 
-// reference correct.c:388-472 (bfc_ec1) + the packing of worker_ec (correct.c:552-553)
-__device__ int ec_read(const EcParams &P, int64_t r, SearchState &S, unsigned long long &n_lookups)
+__global__ void __launch_bounds__(128) k_ec_setup(EcParams P)
 {
-	const uint64_t o = P.off[r], ow = o - P.base0;
-	const int n = (int)(P.off[r + 1] - o - 1), k = P.k;
-	uint8_t *seq = P.seq + o, *fb = P.fb + ow;
-	uint8_t *qual = P.qual && n > 0 && P.qual[o] != 0xFF ? P.qual + o : 0;
-	const uint16_t *occ = P.occ16 + ow;
-	const bool has_q = qual != 0;
-	uint32_t ec_code = 1, brute = 0, n_ec = 0, n_ec_high = 0, n_absent = 0, mh = 0;
-	int start = 0, end = 0, n_n = 0;
-	bool island = false;
-
-	// bfc_seq_conv (correct.c:23-37) + the solid / high flags of bfc_ec_kcov (correct.c:106-108)
-	for (int i = 0; i < n; ++i) {
-		const int b = base_code(seq[i]);
-		const int q = b > 3 ? 0 : !has_q ? 1 : (int)qual[i] - 33 >= P.q;
-		uint32_t f = (uint32_t)b | (q ? FB_Q : 0);
-		const uint32_t v = occ[i];
-		if (v != OCC_NONE && (int)(v & 0xff) >= P.min_cov)
-			f |= FB_SOLID | ((int)(v >> 8 & 0x3f) >= P.min_cov + 1 ? FB_HSOLID : 0);
-		fb[i] = (uint8_t)f;
-		n_n += b > 3;
-	}
-	do {
-		if (n_n > n * .05) { ec_code = 2; break; }
-		{ // lcov[j] = #solid k-mers ending in [j, j+k-1]; hcov likewise for solid && high_end (correct.c:109-112)
-			int lc = 0, hc = 0;
-			for (int j = n - 1; j >= 0; --j) {
-				lc += (fb[j] & FB_SOLID) != 0, hc += (fb[j] & FB_HSOLID) != 0;
-				if (j + k < n) lc -= (fb[j + k] & FB_SOLID) != 0, hc -= (fb[j + k] & FB_HSOLID) != 0;
-				if (lc >= P.min_cov + 1) fb[j] |= FB_LCOV;
-				if (4 * hc > 3 * k) fb[j] |= FB_HCOV; // hcov > k * .75
-			}
-		}
-		{ // bfc_ec_best_island (correct.c:119-130)
-			int l = 0, max = 0, max_i = -1, i;
-			for (i = k - 1; i < n; ++i) {
-				if (!(fb[i] & FB_SOLID)) {
-					if (l > max) max = l, max_i = i;
-					l = 0;
-				} else ++l;
-			}
-			if (l > max) max = l, max_i = i;
-			if (max > 0) start = max_i - max - k + 1, end = max_i, island = true;
-		}
-		if (!island) { // no solid k-mer: single-edit rescue (correct.c:405-421)
-			uint64_t x[4];
-			int ec = -1;
-			while ((end = ec_first_kmer(k, fb, n, start, x)) < n) {
-				ec = ec_greedy_k(P, x, n_lookups);
-				if (ec >= 0) break;
-				if (end + (k >> 1) >= n) break;
-				start = end - (k >> 1);
-			}
-			if (ec >= 0) {
-				fb[end - (ec >> 2)] = (uint8_t)((fb[end - (ec >> 2)] & ~7) | (ec & 3));
-				++end; start = end - k;
-				brute = 1;
-			} else { ec_code = 3; break; }
-		}
-		RView rv;
-		rv.fb = fb, rv.seq = seq, rv.occ = occ, rv.n = n, rv.k = k;
-		int mh0 = 0, mh1 = 0, rv0, rv1;
-		rv.dir = 0;
-		rv0 = ec_search(P, rv, start, n, S, P.p0 + ow, mh0, true, n_lookups);
-		if (rv0 == EC_OVERFLOW) return EC_OVERFLOW;
-		if (rv0 < 0) { ec_code = rv0 == -2 ? 4 : rv0 == -3 ? 5 : 1; break; }
-		rv.dir = 1;
-		// the reverse-complement k-mer hashes like the forward one only for odd k (kmer.h:81)
-		rv1 = ec_search(P, rv, n - end, n, S, P.p1 + ow, mh1, (k & 1) != 0, n_lookups);
-		if (rv1 == EC_OVERFLOW) return EC_OVERFLOW;
-		if (rv1 < 0) { ec_code = rv1 == -2 ? 4 : rv1 == -3 ? 5 : 1; break; }
-		mh = mh0 > mh1 ? mh0 : mh1;
-		ec_code = 0, n_absent = rv0 + rv1;
-		// merge the two directions and rewrite the read (correct.c:443-459)
-		const uint8_t *p0 = P.p0 + ow, *p1 = P.p1 + ow;
-		for (int i = 0; i < n; ++i) {
-			const int f = p0[i], g = p1[i], cur = FB_B(fb[i]), ob = base_code(seq[i]);
-			int nb;
-			if (f == g) nb = f > 3 ? cur : f;
-			else if (g > 3) nb = f;
-			else if (f > 3) nb = g;
-			else nb = ob;
-			const bool diff = nb != ob;
-			const int q = (fb[i] & FB_Q) != 0;
-			if (diff) { ++n_ec; n_ec_high += q; }
-			seq[i] = (uint8_t)((diff ? "acgtn" : "ACGTN")[nb]);
-			if (has_q) qual[i] = (uint8_t)(diff ? 34 + ob : (q ? '?' : '+'));
-		}
-	} while (0);
-	P.aux[2 * r] = (n_ec & 0x3fff) << 18 | (n_ec_high & 0x3fff) << 4 | brute << 3 | ec_code;
-	P.aux[2 * r + 1] = (n_absent & 0x3fffff) << 10 | 0u << 8 | (mh & 0xff);
-	return 0;
-}
-
-__global__ void __launch_bounds__(128) k_ec_read(EcParams P)
-{
-	const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, n_slots = (int64_t)gridDim.x * blockDim.x;
-	SearchState S;
-	S.heap = P.heap + slot * P.heap_cap, S.stack = P.stack + slot * P.stack_cap;
-	S.heap_cap = P.heap_cap, S.stack_cap = P.stack_cap;
-	S.heap_n = S.stack_n = 0, S.top_valid = false;
+	const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	unsigned long long n_lookups = 0;
-	for (int64_t s = slot; s < P.n_reads; s += n_slots) {
-		const int64_t r = P.redo ? (int64_t)P.redo[s] : s;
-		if (ec_read(P, r, S, n_lookups) == EC_OVERFLOW)
-			P.overflow[atomicAdd(P.ctr, 1ULL)] = (uint32_t)r;
+	if (r < P.n_reads) {
+		const uint64_t ob = P.off[r];
+		const int64_t o = (int64_t)(ob - P.base0);
+		const int n = (int)(P.off[r + 1] - ob - 1), k = P.k;
+		ReadDesc d;
+		d.start0 = d.start1 = -1, d.brute = -1, d.code = 0;
+		int n_n = 0;
+		for (int p = 0; p < n; p += 64) {
+			const int len = n - p < 64 ? n - p : 64;
+			n_n += __popcll(bits64(plane(P, PL_NB), o + p) & (len == 64 ? ~0ULL : (1ULL << len) - 1));
+		}
+		if (n_n > n * .05) d.code = 2; // correct.c:397-402
+		else {
+			// bfc_ec_best_island (correct.c:119-130): longest run of solid k-mer ends in [k-1, n), first wins
+			int l = 0, max = 0, max_i = -1;
+			for (int p = k - 1; p < n; p += 64) {
+				const int len = n - p < 64 ? n - p : 64;
+				const uint64_t w = bits64(plane(P, PL_SOL), o + p) & (len == 64 ? ~0ULL : (1ULL << len) - 1);
+				int c = 0;
+				while (c < len) {
+					const uint64_t v = w >> c;
+					if (v & 1) {
+						const uint64_t nv = ~v;
+						int ones = nv ? __ffsll((long long)nv) - 1 : 64;
+						if (ones > len - c) ones = len - c;
+						l += ones, c += ones;
+					} else {
+						if (l > max) max = l, max_i = p + c;
+						l = 0;
+						int zeros = v ? __ffsll((long long)v) - 1 : 64;
+						if (zeros > len - c) zeros = len - c;
+						c += zeros;
+					}
+				}
+			}
+			if (l > max) max = l, max_i = n;
+			if (max > 0) d.start0 = max_i - max - k + 1, d.start1 = n - max_i;
+			else { // no solid k-mer: single-edit rescue (correct.c:405-421)
+				int start = 0, end, ec = -1;
+				while ((end = ec_first_kmer_end(P, o, n, start)) < n) {
+					uint64_t x[4];
+					extract_kmer(P, o, n, 0, end, k, -1, 0, x);
+					ec = ec_greedy_k(P, x, n_lookups);
+					if (ec >= 0) break;
+					if (end + (k >> 1) >= n) break;
+					start = end - (k >> 1);
+				}
+				if (ec >= 0) {
+					d.brute = (end - (ec >> 2)) << 2 | (ec & 3);
+					++end;
+					d.start0 = end - k, d.start1 = n - end;
+				} else d.code = 3;
+			}
+		}
+		P.desc[r] = d;
 	}
 	block_add(P.ctr + 1, n_lookups);
+}
+
+// ------------------------------------------------------------------ K6b: the search
+
+enum { PC_NEWJOB = 0, PC_POP, PC_STEP, PC_OWN_DONE, PC_AFTER_OWN, PC_ALT_NEXT, PC_ALT_DONE, PC_FINISH, PC_EXIT };
+
+#define EC_OVERFLOW (-100)
+
+__device__ __forceinline__ uint32_t hk_pen(uint32_t key) { return key >> 12; }
+
+// klib heap with "less" = larger tot_pen: root = smallest penalty (correct.c:179, ksort.h:125-146)
+__device__ __forceinline__ void heapk_down(uint32_t *l, int n)
+{
+	int i = 0, c;
+	const uint32_t tmp = l[0];
+	while ((c = 2 * i + 1) < n) {
+		uint32_t vc = l[c];
+		if (c != n - 1) {
+			const uint32_t vr = l[c + 1];
+			if (hk_pen(vc) > hk_pen(vr)) ++c, vc = vr;
+		}
+		if (hk_pen(vc) > hk_pen(tmp)) break;
+		l[i] = vc; i = c;
+	}
+	l[i] = tmp;
+}
+
+__device__ __forceinline__ void heapk_up(uint32_t *l, int n)
+{
+	int c = n - 1;
+	const uint32_t tmp = l[c];
+	while (c) {
+		const int par = (c - 1) >> 1;
+		const uint32_t vp = l[par];
+		if (hk_pen(tmp) > hk_pen(vp)) break;
+		l[c] = vp; c = par;
+	}
+	l[c] = tmp;
+}
+
+// packed candidate of one step: bit 0 valid, 1 ec, 2 ec_high, 3 absent, 4 absent_high
+__device__ __forceinline__ int cand_weight(const EcParams &P, uint32_t c)
+{
+	return P.w_ec * (int)(c >> 1 & 1) + P.w_ec_high * (int)(c >> 2 & 1) + P.w_absent * (int)(c >> 3 & 1) + P.w_absent_high * (int)(c >> 4 & 1);
+}
+
+__global__ void __launch_bounds__(128, 4) k_ec_search(EcParams P)
+{
+	const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, n_slots = (int64_t)gridDim.x * blockDim.x;
+	EcState *const pool = P.pool + slot * P.heap_cap;
+	uint32_t *const heapk = P.heapk + slot * P.heap_cap;
+	uint2 *const edits = P.edits + slot * P.edit_cap;
+	const int k = P.k;
+
+	// job context
+	int64_t job = slot - n_slots, o = 0;
+	int jid = 0, n = 0, dir = 0, bp = -1, bb = 0;
+	bool memo_dir = false;
+	// search context (reference bfc_ec1dir locals)
+	EcState z;
+	int heap_n = 0, n_init = 0, n_edits = 0, max_heap = 0, n_fail = 0, n_paths = 0, rvl = -1;
+	int best_pen = INT_MAX, best_edit = -1, best_absent = 0;
+	bool top_valid = false, have_best = false;
+	// step context
+	int cb = -1, cob = -1, ff = 0, osf = 0, alt_mask = 0, other_ext = 0, cur_alt = 0;
+	uint32_t cand = 0; // 4 x 8 bits, one per base
+	bool has_c = false, fixed = false;
+	// lookup hand-over
+	int req_b = 0, res = -1;
+	int pc = PC_NEWJOB;
+	unsigned long long n_lookups = 0;
+	z.tot_pen = z.i = z.n_absent = z.clean = 0, z.edit = -1;
+	z.x[0] = z.x[1] = z.x[2] = z.x[3] = 0;
+#pragma unroll
+	for (int t = 0; t < BFC_EC_HIST; ++t) z.ecpos[t] = -1;
+#pragma unroll
+	for (int t = 0; t < BFC_EC_HIST_HIGH; ++t) z.ecpos_high[t] = -1;
+
+	for (;;) {
+		// ---------------- divergent part: run this thread's state machine up to its next lookup
+		bool yield = false;
+		while (!yield) {
+			bool job_done = false;
+			switch (pc) {
+			case PC_NEWJOB: {
+				job += n_slots;
+				if (job >= P.n_jobs) { pc = PC_EXIT; yield = true; break; }
+				jid = P.redo ? (int)P.redo[job] : (int)job;
+				const int r = jid >> 1;
+				const ReadDesc d = P.desc[r];
+				if (d.start0 < 0) break; // nothing to search for this read
+				dir = jid & 1;
+				const uint64_t ob = P.off[r];
+				o = (int64_t)(ob - P.base0);
+				n = (int)(P.off[r + 1] - ob - 1);
+				bp = d.brute >= 0 ? d.brute >> 2 : -1, bb = d.brute & 3;
+				// the reverse-complement k-mer hashes like the forward one only for odd k (kmer.h:81)
+				memo_dir = dir == 0 || (k & 1) != 0;
+				const int start = dir ? d.start1 : d.start0;
+				heap_n = n_init = n_edits = 0, max_heap = 0, n_fail = 0, n_paths = 0, rvl = -1;
+				best_pen = INT_MAX, best_edit = -1, best_absent = 0, have_best = false;
+				// seed: the k-1 bases before position z.i (correct.c:260-267); [start, start+k) is a k-mer of ACGT
+				z.i = start + k - 1;
+				z.tot_pen = 0, z.edit = -1, z.n_absent = 0;
+#pragma unroll
+				for (int t = 0; t < BFC_EC_HIST; ++t) z.ecpos[t] = -1;
+#pragma unroll
+				for (int t = 0; t < BFC_EC_HIST_HIGH; ++t) z.ecpos_high[t] = -1;
+				if (start < 0 || z.i >= n) { rvl = -1; job_done = true; break; } // the reference asserts
+				extract_kmer(P, o, n, dir, z.i - 1, k - 1, bp, bb, z.x);
+				z.clean = k - 1;
+				if (bp >= 0) { // bases after the rescue edit are the original ones
+					const int ib = dir ? n - 1 - bp : bp; // search position of the edit
+					if (ib >= start && ib <= z.i - 1) z.clean = z.i - 1 - ib;
+				}
+				top_valid = true;
+				pc = PC_POP;
+				break;
+			}
+			case PC_POP: {
+				const int hs = heap_n + (top_valid ? 1 : 0);
+				max_heap = max_heap > 255 ? 255 : max_heap > hs ? max_heap : hs; // correct.c:276
+				if (hs == 0) { rvl = -2; job_done = true; break; }
+				if (top_valid) top_valid = false;
+				else { // ks_heapdown-based pop (correct.c:281-283); the freed slot id parks behind the live keys
+					const uint32_t key = heapk[0];
+					--heap_n;
+					heapk[0] = heapk[heap_n];
+					heapk[heap_n] = key;
+					if (heap_n > 1) heapk_down(heapk, heap_n);
+					z = pool[key & 0xfff];
+				}
+				if (have_best && z.tot_pen > best_pen + P.max_path_diff) { job_done = true; break; } // correct.c:288
+				if (z.i - n > P.max_end_ext) { // correct.c:289, 366-372
+					if (z.tot_pen < best_pen) best_pen = z.tot_pen, best_edit = z.edit, best_absent = z.n_absent, have_best = true;
+					if (++n_paths == BFC_MAX_PATHS) job_done = true;
+					break; // next pop
+				}
+				pc = PC_STEP;
+				break;
+			}
+			case PC_STEP: {
+				has_c = z.i < n;
+				cand = 0, other_ext = 0, osf = 0, cb = cob = -1, ff = 0;
+				if (has_c) {
+					const int f = dir ? n - 1 - z.i : z.i;
+					ff = __ldg(P.fl + o + f);
+					const int ob = FL_OB(ff), cur = f == bp ? bb : ob;
+					cb = dir ? comp_b(cur) : cur, cob = dir ? comp_b(ob) : ob;
+					if (cb < 4) {
+						if (memo_dir && z.clean >= k - 1 && cb == cob) { // the read's own k-mer: K5 fetched it
+							if (heap_n == 0) { // a lone state: step over every decision-free base at once
+								int run;
+								if (!dir) { const uint64_t w = ~bits64(plane(P, PL_J0), o + f); run = w ? __ffsll((long long)w) - 1 : 64; }
+								else { const uint64_t w = ~bits64(plane(P, PL_J1), o + f - 63); run = w ? __clzll((long long)w) : 64; }
+								if (bp >= 0) { // the rescued base is not the original one: stop in front of it
+									const int ib = dir ? n - 1 - bp : bp;
+									if (ib >= z.i && ib < z.i + run) run = ib - z.i;
+								}
+								if (run > 0) {
+									max_heap = max_heap > 1 ? max_heap : 1;
+									z.i += run, z.clean += run;
+									extract_kmer(P, o, n, dir, z.i - 1, k - 1, -1, 0, z.x);
+									break; // PC_STEP again at the new position
+								}
+							}
+							osf = __ldg(P.fl + o + (dir ? f + k - 1 : f));
+							pc = PC_AFTER_OWN;
+						} else { req_b = cb; pc = PC_OWN_DONE; yield = true; }
+					} else pc = PC_AFTER_OWN;
+				} else pc = PC_AFTER_OWN;
+				break;
+			}
+			case PC_OWN_DONE: { // os = res (correct.c:299)
+				osf = (res >= 0 && (res & 0xff) >= P.min_cov ? FL_SOL : 0) | ((res & 0xff) >= P.min_cov + 1 ? FL_A : 0) |
+				      (res >= 0 && (res >> 8 & 0xff) >= P.min_cov ? FL_H : 0);
+				pc = PC_AFTER_OWN;
+				break;
+			}
+			case PC_AFTER_OWN: {
+				fixed = z.i > n; // correct.c:295 with end == n
+				if (has_c && cb < 4) {
+					if ((ff & FL_Q) && (osf & FL_A) && (ff & FL_LC)) fixed = true; // correct.c:299-301
+					else if (ff & FL_HC) fixed = true;
+					// the read base itself (correct.c:334-337)
+					cand |= (1u | ((osf & FL_SOL) ? 0u : 8u) | ((osf & FL_H) ? 0u : 16u)) << (8 * cb);
+				}
+				alt_mask = 0;
+				if (!(fixed && has_c)) {
+					bool allowed = true;
+					if (has_c) { // correct.c:316-317
+						if ((ff & FL_Q) && z.ecpos_high[BFC_EC_HIST_HIGH - 1] >= 0 && z.i - z.ecpos_high[BFC_EC_HIST_HIGH - 1] < P.win_multi_ec) allowed = false;
+						if (z.ecpos[BFC_EC_HIST - 1] >= 0 && z.i - z.ecpos[BFC_EC_HIST - 1] < P.win_multi_ec) allowed = false;
+					}
+					if (allowed) alt_mask = has_c && cb < 4 ? 0xF & ~(1 << cb) : 0xF;
+				}
+				pc = PC_ALT_NEXT;
+				break;
+			}
+			case PC_ALT_NEXT: {
+				if (alt_mask) {
+					cur_alt = __ffs(alt_mask) - 1;
+					alt_mask &= alt_mask - 1;
+					req_b = cur_alt; pc = PC_ALT_DONE; yield = true;
+				} else pc = PC_FINISH;
+				break;
+			}
+			case PC_ALT_DONE: { // correct.c:320-333
+				if (res >= 0 && (res & 0xff) >= P.min_cov) {
+					const uint32_t ec = has_c && cb < 4 ? 1u : 0u;
+					cand |= (1u | ec << 1 | (ec && (ff & FL_Q) ? 4u : 0u) | ((res >> 8 & 0xff) < P.min_cov ? 16u : 0u)) << (8 * cur_alt);
+					++other_ext;
+				}
+				pc = PC_ALT_NEXT;
+				break;
+			}
+			case PC_FINISH: {
+				const int n_added = (int)((cand & 1) + (cand >> 8 & 1) + (cand >> 16 & 1) + (cand >> 24 & 1));
+				pc = PC_POP;
+				if (!fixed && other_ext == 0) ++n_fail;
+				if (n_fail > n * 2) { rvl = -3; job_done = true; break; } // correct.c:342-347
+				if (has_c || n_added == 1) {
+					uint32_t push = cand;
+					if (n_added > 1 && heap_n > P.max_heap) { // keep only the cheapest extension, first on ties (correct.c:349-355)
+						int min = INT_MAX, min_b = -1;
+#pragma unroll
+						for (int b = 0; b < 4; ++b)
+							if (cand >> (8 * b) & 1) {
+								const int t = cand_weight(P, cand >> (8 * b) & 0xff);
+								if (min > t) min = t, min_b = b;
+							}
+						push = cand & (0xffu << (8 * min_b));
+					}
+					const bool in_place = heap_n == 0 && (push & 0x01010101u) != 0 && ((push & 0x01010101u) & ((push & 0x01010101u) - 1)) == 0;
+					const EcState zz = z;
+#pragma unroll
+					for (int b = 0; b < 4; ++b) { // buf_update (correct.c:198-230), in base order
+						const uint32_t c = push >> (8 * b) & 0xff;
+						if (!(c & 1)) continue;
+						EcState s = zz;
+						s.i = zz.i + 1;
+						s.tot_pen = zz.tot_pen + cand_weight(P, c);
+						if (c & 4) s.ecpos_high[0] = zz.i, s.ecpos_high[1] = zz.ecpos_high[0];
+						if (c & 2) {
+							s.ecpos[0] = zz.i;
+#pragma unroll
+							for (int t = 1; t < BFC_EC_HIST; ++t) s.ecpos[t] = zz.ecpos[t - 1];
+						}
+						s.clean = b == cob ? zz.clean + 1 : 0;
+						if (has_c) {
+							s.n_absent = zz.n_absent + (int)(c >> 3 & 1);
+							if (b != cb) { // the path changes this base: remember it (forward coordinates)
+								if (n_edits >= P.edit_cap) { rvl = EC_OVERFLOW; job_done = true; break; }
+								const int f = dir ? n - 1 - zz.i : zz.i;
+								edits[n_edits] = make_uint2((uint32_t)zz.edit, (uint32_t)f << 3 | (uint32_t)(dir ? 3 - b : b));
+								s.edit = n_edits++;
+							}
+						}
+						bfc_kmer_append(k, s.x, b);
+						if (in_place) { z = s; top_valid = true; }
+						else {
+							uint32_t id;
+							if (heap_n < n_init) id = heapk[heap_n] & 0xfff;
+							else id = (uint32_t)n_init++;
+							pool[id] = s;
+							heapk[heap_n++] = (uint32_t)s.tot_pen << 12 | id;
+							heapk_up(heapk, heap_n);
+						}
+					}
+				} else { // past the end of the read with 0 or >= 2 extensions: the path ends here (correct.c:360-372)
+					const int fin = z.tot_pen + (n_added == 0 ? P.w_absent * (P.max_end_ext - (z.i - n)) : 0);
+					if (fin < best_pen) best_pen = fin, best_edit = z.edit, best_absent = z.n_absent, have_best = true;
+					if (++n_paths == BFC_MAX_PATHS) job_done = true;
+				}
+				break;
+			}
+			default: yield = true; break;
+			}
+			if (job_done) {
+				if (rvl == EC_OVERFLOW) P.overflow[atomicAdd(P.ctr, 1ULL)] = (uint32_t)jid;
+				else {
+					int rv = rvl;
+					if (n_paths > 0) { // buf_backtrack (correct.c:232-247): only the changed bases need recording
+						uint32_t *ev = (uint32_t*)(P.pl + (uint64_t)(dir ? PL_E1V : PL_E0V) * P.pl_words);
+						const uint64_t s32 = P.pl_words * 2;
+						for (int e = best_edit; e >= 0;) {
+							const uint2 ed = edits[e];
+							const uint64_t pos = (uint64_t)(o + (int64_t)(ed.y >> 3) + PL_PAD);
+							const uint32_t bit = 1u << (pos & 31), b = ed.y & 7;
+							uint32_t *w = ev + (pos >> 5);
+							atomicOr(w, bit);
+							if (b & 1) atomicOr(w + s32, bit);
+							if (b & 2) atomicOr(w + 2 * s32, bit);
+							e = (int)ed.x;
+						}
+						rv = best_absent;
+					}
+					P.res[jid] = make_int2(rv, max_heap);
+				}
+				pc = PC_NEWJOB;
+			}
+		}
+		if (pc == PC_EXIT) break;
+		// ---------------- convergent part: every lane that is still searching has exactly one lookup to do
+		{
+			uint64_t x[4] = { z.x[0], z.x[1], z.x[2], z.x[3] };
+			bfc_kmer_append(k, x, req_b);
+			res = tab_kmer_occ(P.tab, x);
+			++n_lookups;
+		}
+	}
+	block_add(P.ctr + 1, n_lookups);
+}
+
+// ------------------------------------------------------------------ K6c: merge + rewrite, one read per warp
+
+__global__ void __launch_bounds__(256) k_ec_merge(EcParams P)
+{
+	const int lane = threadIdx.x & 31;
+	const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+	for (int64_t r = warp; r < P.n_reads; r += n_warps) {
+		const uint64_t ob0 = P.off[r];
+		const int64_t o = (int64_t)(ob0 - P.base0);
+		const int n = (int)(P.off[r + 1] - ob0 - 1), k = P.k;
+		const ReadDesc d = P.desc[r];
+		uint32_t ec_code = (uint32_t)d.code, brute = d.brute >= 0, n_absent = 0, mh = 0;
+		int2 r0 = make_int2(0, 0), r1 = r0;
+		if (ec_code == 0) {
+			r0 = P.res[2 * r], r1 = P.res[2 * r + 1];
+			const int bad = r0.x < 0 ? r0.x : r1.x < 0 ? r1.x : 0; // the reference stops at the first failing direction
+			if (bad < 0) ec_code = bad == -2 ? 4 : bad == -3 ? 5 : 1;
+		}
+		uint32_t n_ec = 0, n_ec_high = 0;
+		if (ec_code == 0) {
+			uint8_t *seq = P.seq + ob0;
+			uint8_t *qual = P.qual && n > 0 && P.qual[ob0] != 0xFF ? P.qual + ob0 : 0;
+			const int bp = d.brute >= 0 ? d.brute >> 2 : -1, bb = d.brute & 3;
+			const int lim0 = d.start0 + k, lim1 = n - d.start1 - k; // masked: i < lim0 (forward), i >= lim1 (reverse), correct.c:378-379
+			mh = (uint32_t)(r0.y > r1.y ? r0.y : r1.y), n_absent = (uint32_t)(r0.x + r1.x);
+			for (int i = lane; i < n; i += 32) {
+				const int ff = __ldg(P.fl + o + i);
+				const int ob = FL_OB(ff), cur = i == bp ? bb : ob, q = (ff & FL_Q) != 0;
+				int f = cur, g = cur;
+				if (bit1(plane(P, PL_E0V), o + i)) f = bit1(plane(P, PL_E0L), o + i) | bit1(plane(P, PL_E0H), o + i) << 1;
+				if (bit1(plane(P, PL_E1V), o + i)) g = bit1(plane(P, PL_E1L), o + i) | bit1(plane(P, PL_E1H), o + i) << 1;
+				if (i < lim0) f = 4;
+				if (i >= lim1) g = 4;
+				int nb; // correct.c:443-450
+				if (f == g) nb = f > 3 ? cur : f;
+				else if (g > 3) nb = f;
+				else if (f > 3) nb = g;
+				else nb = ob;
+				const bool diff = nb != ob;
+				n_ec += diff, n_ec_high += diff && q;
+				seq[i] = (uint8_t)((diff ? "acgtn" : "ACGTN")[nb]);
+				if (qual) qual[i] = (uint8_t)(diff ? 34 + ob : (q ? '?' : '+'));
+			}
+			for (int s = 16; s > 0; s >>= 1) {
+				n_ec += __shfl_down_sync(0xffffffffu, n_ec, s);
+				n_ec_high += __shfl_down_sync(0xffffffffu, n_ec_high, s);
+			}
+		}
+		if (lane == 0) { // correct.c:552-553
+			P.aux[2 * r] = (n_ec & 0x3fff) << 18 | (n_ec_high & 0x3fff) << 4 | brute << 3 | ec_code;
+			P.aux[2 * r + 1] = (n_absent & 0x3fffff) << 10 | 0u << 8 | (mh & 0xff);
+		}
+	}
 }
 
 // ------------------------------------------------------------------ host side
@@ -490,7 +707,13 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 static uint64_t batch_bytes_limit()
 {
 	const char *e = getenv("BFC_B200_EC_BATCH");
-	return e && atoll(e) >= 4096 ? (uint64_t)atoll(e) : 1ULL << 27;
+	return e && atoll(e) >= 4096 ? (uint64_t)atoll(e) : 1ULL << 28;
+}
+
+static int edit_cap0()
+{
+	const char *e = getenv("BFC_B200_EC_EDITS");
+	return e && atoi(e) >= 4 ? atoi(e) : 192;
 }
 
 extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int mode, bfcg_batch_t *batch,
@@ -516,34 +739,36 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 	}
 	const uint64_t limit = batch_bytes_limit();
 	const int threads = 128;
-	const int64_t max_slots = (int64_t)rt.sm_count * 1024;
+	const int64_t max_slots = (int64_t)rt.sm_count * 4 * threads; // persistent: what is resident at 4 CTAs per SM
 	const int heap_cap = opt->max_heap + 6; // the search never holds more than max_heap + 4 states
-	const int stack_cap0 = 512;
+	const int edit_cap = edit_cap0();
 
 	BfcgTimer timer(stats);
 	for (int64_t r0 = 0; r0 < n;) {
 		int64_t r1 = r0 + 1;
-		while (r1 < n && h_off[r1 + 1] - h_off[r0] <= limit) ++r1;
+		while (r1 < n && h_off[r1 + 1] - h_off[r0] <= limit && r1 - r0 < (1LL << 30)) ++r1;
 		const int64_t nr = r1 - r0;
 		const uint64_t b0 = h_off[r0], nb = h_off[r1] - b0;
 		const uint64_t n_rec = enum_padded(nb);
-		const int64_t slots = std::min<int64_t>(max_slots, (nr + threads - 1) / threads * threads);
-		size_t tot = 0, o_seq = 0, o_qual = 0, o_off = 0, o_aux = 0, o_fb, o_p0, o_p1, o_y0, o_y1, o_occ, o_heap, o_stack, o_ovf, o_ctr;
+		const uint64_t pl_words = (n_rec + PL_PAD) / 64 + 4;
+		const int64_t slots = std::min<int64_t>(max_slots, (2 * nr + threads - 1) / threads * threads);
+		size_t tot = 0, o_seq = 0, o_qual = 0, o_off = 0, o_aux = 0, o_pl, o_fl, o_y0, o_y1, o_desc, o_res, o_pool, o_heapk, o_edits, o_ovf, o_ctr;
 		if (host) {
 			o_seq = tot; tot = align_up(tot + nb, 256);
 			o_qual = tot; tot = align_up(tot + nb, 256);
 			o_off = tot; tot = align_up(tot + (nr + 1) * 8, 256);
 			o_aux = tot; tot = align_up(tot + nr * 8, 256);
 		}
-		o_fb = tot; tot = align_up(tot + nb, 256);
-		o_p0 = tot; tot = align_up(tot + nb, 256);
-		o_p1 = tot; tot = align_up(tot + nb, 256);
+		o_pl = tot; tot = align_up(tot + (size_t)PL_N * pl_words * 8, 256);
+		o_fl = tot; tot = align_up(tot + n_rec * 2, 256);
 		o_y0 = tot; tot = align_up(tot + n_rec * 8, 256);
 		o_y1 = tot; tot = align_up(tot + n_rec * 8, 256);
-		o_occ = tot; tot = align_up(tot + n_rec * 2, 256);
-		o_heap = tot; tot = align_up(tot + (size_t)slots * heap_cap * sizeof(HeapEnt), 256);
-		o_stack = tot; tot = align_up(tot + (size_t)slots * stack_cap0 * sizeof(StackEnt), 256);
-		o_ovf = tot; tot = align_up(tot + nr * 4, 256);
+		o_desc = tot; tot = align_up(tot + nr * sizeof(ReadDesc), 256);
+		o_res = tot; tot = align_up(tot + 2 * nr * sizeof(int2), 256);
+		o_pool = tot; tot = align_up(tot + (size_t)slots * heap_cap * sizeof(EcState), 256);
+		o_heapk = tot; tot = align_up(tot + (size_t)slots * heap_cap * 4, 256);
+		o_edits = tot; tot = align_up(tot + (size_t)slots * edit_cap * sizeof(uint2), 256);
+		o_ovf = tot; tot = align_up(tot + 2 * nr * 4, 256);
 		o_ctr = tot; tot += 256;
 		uint8_t *a = (uint8_t*)bfcg_arena(tot);
 		if (!a) return BFCG_ERR_NOMEM;
@@ -565,54 +790,70 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 			P.aux = aux + 2 * r0;
 			P.base0 = b0;
 		}
-		P.fb = a + o_fb, P.p0 = a + o_p0, P.p1 = a + o_p1;
-		P.occ16 = (const uint16_t*)(a + o_occ);
-		P.n_reads = nr;
+		P.pl = (const uint64_t*)(a + o_pl), P.pl_words = pl_words;
+		P.fl = (const uint16_t*)(a + o_fl);
+		P.desc = (ReadDesc*)(a + o_desc), P.res = (int2*)(a + o_res);
+		P.n_reads = nr, P.n_jobs = 2 * nr;
 		P.tab = tab_view(ch);
 		P.k = opt->k, P.q = opt->q, P.min_cov = opt->min_cov, P.win_multi_ec = opt->win_multi_ec, P.max_end_ext = opt->max_end_ext;
 		P.w_ec = opt->w_ec, P.w_ec_high = opt->w_ec_high, P.w_absent = opt->w_absent, P.w_absent_high = opt->w_absent_high;
 		P.max_path_diff = opt->max_path_diff, P.max_heap = opt->max_heap, P.mode = mode;
-		P.heap = (HeapEnt*)(a + o_heap), P.stack = (StackEnt*)(a + o_stack);
-		P.heap_cap = heap_cap, P.stack_cap = stack_cap0;
+		P.pool = (EcState*)(a + o_pool), P.heapk = (uint32_t*)(a + o_heapk), P.edits = (uint2*)(a + o_edits);
+		P.heap_cap = heap_cap, P.edit_cap = edit_cap;
 		P.overflow = (uint32_t*)(a + o_ovf), P.ctr = (unsigned long long*)(a + o_ctr);
 		BFCG_CUDA(cudaMemsetAsync(P.ctr, 0, 64, rt.stream));
+		BFCG_CUDA(cudaMemsetAsync(a + o_pl, 0, (size_t)PL_N * pl_words * 8, rt.stream));
 
+		const uint8_t *w_seq = host ? a + o_seq : batch->seq + b0;
+		const uint8_t *w_qual = host ? (batch->qual ? a + o_qual : 0) : (batch->qual ? batch->qual + b0 : 0);
 		EnumParams ep;
 		memset(&ep, 0, sizeof(ep));
-		ep.seq = (host ? a + o_seq : batch->seq + b0), ep.qual = 0; // the quality flag of a record is not used here
+		ep.seq = w_seq, ep.qual = 0; // the quality flag of a record is not used here
 		ep.len = nb, ep.emit_from = 0, ep.k = opt->k, ep.q = opt->q;
 		ep.rec_y0 = (unsigned long long*)(a + o_y0), ep.rec_y1 = (unsigned long long*)(a + o_y1);
 		{ KTime kt(KT_ENUM); k_enum<<<(unsigned)(n_rec / ENUM_SEG), ENUM_THREADS, 0, rt.stream>>>(ep); }
 		BFCG_LAUNCH_CHECK();
-		{ KTime kt(KT_EC_LOOKUP); k_ec_lookup<<<(unsigned)(n_rec / ENUM_SEG), ENUM_THREADS, 0, rt.stream>>>(P.tab, ep.rec_y0, ep.rec_y1, (uint16_t*)(a + o_occ), nb, P.ctr); }
+		LookupParams lp;
+		lp.tab = P.tab, lp.rec_y0 = ep.rec_y0, lp.rec_y1 = ep.rec_y1, lp.seq = w_seq, lp.qual = w_qual, lp.n_pos = nb;
+		lp.pl = (uint64_t*)(a + o_pl), lp.pl_words = pl_words, lp.q = opt->q, lp.min_cov = opt->min_cov, lp.ctr = P.ctr;
+		{ KTime kt(KT_EC_LOOKUP); k_ec_lookup<<<(unsigned)(n_rec / ENUM_SEG), ENUM_THREADS, 0, rt.stream>>>(lp); }
 		BFCG_LAUNCH_CHECK();
-		{ KTime kt(KT_CORRECT); k_ec_read<<<(unsigned)(slots / threads), threads, 0, rt.stream>>>(P); }
+		{
+			KTime kt(KT_EC_SETUP);
+			k_ec_cov<<<(unsigned)(n_rec / 256), 256, 0, rt.stream>>>(P, n_rec, (uint16_t*)(a + o_fl), (uint64_t*)(a + o_pl));
+			k_ec_setup<<<(unsigned)((nr + 127) / 128), 128, 0, rt.stream>>>(P);
+		}
+		BFCG_LAUNCH_CHECK();
+		++rt.n_launches;
+		{ KTime kt(KT_CORRECT); k_ec_search<<<(unsigned)(slots / threads), threads, 0, rt.stream>>>(P); }
 		BFCG_LAUNCH_CHECK();
 		unsigned long long c[2];
 		BFCG_CUDA(cudaMemcpyAsync(c, P.ctr, sizeof(c), cudaMemcpyDeviceToHost, rt.stream));
 		BFCG_CUDA(cudaStreamSynchronize(rt.stream));
-		// reads whose search outgrew the stack: same kernel, fewer threads, larger stacks
+		// jobs whose edit list outgrew the scratch: same kernel, fewer threads, larger lists
 		uint32_t *redo = 0;
-		StackEnt *big = 0;
-		for (int cap = stack_cap0 * 16; c[0] > 0; cap *= 16) {
+		uint2 *big = 0;
+		for (int cap = edit_cap * 16; c[0] > 0; cap *= 16) {
 			const uint64_t n_redo = c[0];
 			if (stats) stats->n_redo += n_redo;
-			if (cap > (1 << 25)) { cudaFree(redo); cudaFree(big); return bfcg_fail(__func__, "search stack overflow beyond 2^25 entries", cudaSuccess), BFCG_ERR_OVERFLOW; }
-			const int64_t rs = std::min<int64_t>(std::min<int64_t>(slots, (int64_t)((n_redo + 31) / 32 * 32)), std::max<int64_t>(32, (int64_t)((8ULL << 30) / ((uint64_t)cap * sizeof(StackEnt))) / 32 * 32));
+			if (cap > (1 << 26)) { cudaFree(redo); cudaFree(big); return bfcg_fail(__func__, "search edit list overflow beyond 2^26 entries", cudaSuccess), BFCG_ERR_OVERFLOW; }
+			const int64_t rs = std::min<int64_t>(std::min<int64_t>(slots, (int64_t)((n_redo + 31) / 32 * 32)), std::max<int64_t>(32, (int64_t)((4ULL << 30) / ((uint64_t)cap * sizeof(uint2))) / 32 * 32));
 			cudaFree(redo); cudaFree(big);
 			redo = 0, big = 0;
 			BFCG_CUDA(cudaMalloc(&redo, n_redo * 4));
-			BFCG_CUDA(cudaMalloc(&big, (size_t)rs * cap * sizeof(StackEnt)));
+			BFCG_CUDA(cudaMalloc(&big, (size_t)rs * cap * sizeof(uint2)));
 			BFCG_CUDA(cudaMemcpyAsync(redo, P.overflow, n_redo * 4, cudaMemcpyDeviceToDevice, rt.stream));
 			BFCG_CUDA(cudaMemsetAsync(P.ctr, 0, 8, rt.stream));
 			EcParams Q = P;
-			Q.redo = redo, Q.n_reads = (int64_t)n_redo, Q.stack = big, Q.stack_cap = cap;
-			{ KTime kt(KT_CORRECT_REDO); k_ec_read<<<(unsigned)(rs / 32), 32, 0, rt.stream>>>(Q); }
+			Q.redo = redo, Q.n_jobs = (int64_t)n_redo, Q.edits = big, Q.edit_cap = cap;
+			{ KTime kt(KT_CORRECT_REDO); k_ec_search<<<(unsigned)(rs / 32), 32, 0, rt.stream>>>(Q); }
 			BFCG_LAUNCH_CHECK();
 			BFCG_CUDA(cudaMemcpyAsync(c, P.ctr, sizeof(c), cudaMemcpyDeviceToHost, rt.stream));
 			BFCG_CUDA(cudaStreamSynchronize(rt.stream));
 		}
 		cudaFree(redo); cudaFree(big);
+		{ KTime kt(KT_EC_MERGE); k_ec_merge<<<(unsigned)std::min<int64_t>((nr + 7) / 8, (int64_t)rt.sm_count * 16), 256, 0, rt.stream>>>(P); }
+		BFCG_LAUNCH_CHECK();
 		if (stats) stats->n_lookups += c[1];
 		if (host) {
 			BFCG_CUDA(cudaMemcpyAsync(batch->seq + b0, a + o_seq, nb, cudaMemcpyDeviceToHost, rt.stream));
