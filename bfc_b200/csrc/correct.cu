@@ -410,107 +410,26 @@ __global__ void __launch_bounds__(128, 4) k_ec_search(EcParams P)
 	for (int t = 0; t < BFC_EC_HIST_HIGH; ++t) z.ecpos_high[t] = -1;
 
 	for (;;) {
-		// ---------------- divergent part: run this thread's state machine up to its next lookup
+		// ---------------- stage 0: take the lookup result in (correct.c:299 / :320)
+		if (pc == PC_OWN_DONE) {
+			osf = (res >= 0 && (res & 0xff) >= P.min_cov ? FL_SOL : 0) | ((res & 0xff) >= P.min_cov + 1 ? FL_A : 0) |
+			      (res >= 0 && (res >> 8 & 0xff) >= P.min_cov ? FL_H : 0);
+			pc = PC_AFTER_OWN;
+		} else if (pc == PC_ALT_DONE) { // correct.c:320-333
+			if (res >= 0 && (res & 0xff) >= P.min_cov) {
+				const uint32_t ec = has_c && cb < 4 ? 1u : 0u;
+				cand |= (1u | ec << 1 | (ec && (ff & FL_Q) ? 4u : 0u) | ((res >> 8 & 0xff) < P.min_cov ? 16u : 0u)) << (8 * cur_alt);
+				++other_ext;
+			}
+			pc = PC_ALT_NEXT;
+		}
+		// ---------------- the step pipeline: stages in the order a search step runs through them, so that the
+		// lanes of a warp stay together; the loop repeats only after a memoised lookup, a jump, a finished
+		// path or a new job
 		bool yield = false;
-		while (!yield) {
+		do {
 			bool job_done = false;
-			switch (pc) {
-			case PC_NEWJOB: {
-				job += n_slots;
-				if (job >= P.n_jobs) { pc = PC_EXIT; yield = true; break; }
-				jid = P.redo ? (int)P.redo[job] : (int)job;
-				const int r = jid >> 1;
-				const ReadDesc d = P.desc[r];
-				if (d.start0 < 0) break; // nothing to search for this read
-				dir = jid & 1;
-				const uint64_t ob = P.off[r];
-				o = (int64_t)(ob - P.base0);
-				n = (int)(P.off[r + 1] - ob - 1);
-				bp = d.brute >= 0 ? d.brute >> 2 : -1, bb = d.brute & 3;
-				// the reverse-complement k-mer hashes like the forward one only for odd k (kmer.h:81)
-				memo_dir = dir == 0 || (k & 1) != 0;
-				const int start = dir ? d.start1 : d.start0;
-				heap_n = n_init = n_edits = 0, max_heap = 0, n_fail = 0, n_paths = 0, rvl = -1;
-				best_pen = INT_MAX, best_edit = -1, best_absent = 0, have_best = false;
-				// seed: the k-1 bases before position z.i (correct.c:260-267); [start, start+k) is a k-mer of ACGT
-				z.i = start + k - 1;
-				z.tot_pen = 0, z.edit = -1, z.n_absent = 0;
-#pragma unroll
-				for (int t = 0; t < BFC_EC_HIST; ++t) z.ecpos[t] = -1;
-#pragma unroll
-				for (int t = 0; t < BFC_EC_HIST_HIGH; ++t) z.ecpos_high[t] = -1;
-				if (start < 0 || z.i >= n) { rvl = -1; job_done = true; break; } // the reference asserts
-				extract_kmer(P, o, n, dir, z.i - 1, k - 1, bp, bb, z.x);
-				z.clean = k - 1;
-				if (bp >= 0) { // bases after the rescue edit are the original ones
-					const int ib = dir ? n - 1 - bp : bp; // search position of the edit
-					if (ib >= start && ib <= z.i - 1) z.clean = z.i - 1 - ib;
-				}
-				top_valid = true;
-				pc = PC_POP;
-				break;
-			}
-			case PC_POP: {
-				const int hs = heap_n + (top_valid ? 1 : 0);
-				max_heap = max_heap > 255 ? 255 : max_heap > hs ? max_heap : hs; // correct.c:276
-				if (hs == 0) { rvl = -2; job_done = true; break; }
-				if (top_valid) top_valid = false;
-				else { // ks_heapdown-based pop (correct.c:281-283); the freed slot id parks behind the live keys
-					const uint32_t key = heapk[0];
-					--heap_n;
-					heapk[0] = heapk[heap_n];
-					heapk[heap_n] = key;
-					if (heap_n > 1) heapk_down(heapk, heap_n);
-					z = pool[key & 0xfff];
-				}
-				if (have_best && z.tot_pen > best_pen + P.max_path_diff) { job_done = true; break; } // correct.c:288
-				if (z.i - n > P.max_end_ext) { // correct.c:289, 366-372
-					if (z.tot_pen < best_pen) best_pen = z.tot_pen, best_edit = z.edit, best_absent = z.n_absent, have_best = true;
-					if (++n_paths == BFC_MAX_PATHS) job_done = true;
-					break; // next pop
-				}
-				pc = PC_STEP;
-				break;
-			}
-			case PC_STEP: {
-				has_c = z.i < n;
-				cand = 0, other_ext = 0, osf = 0, cb = cob = -1, ff = 0;
-				if (has_c) {
-					const int f = dir ? n - 1 - z.i : z.i;
-					ff = __ldg(P.fl + o + f);
-					const int ob = FL_OB(ff), cur = f == bp ? bb : ob;
-					cb = dir ? comp_b(cur) : cur, cob = dir ? comp_b(ob) : ob;
-					if (cb < 4) {
-						if (memo_dir && z.clean >= k - 1 && cb == cob) { // the read's own k-mer: K5 fetched it
-							if (heap_n == 0) { // a lone state: step over every decision-free base at once
-								int run;
-								if (!dir) { const uint64_t w = ~bits64(plane(P, PL_J0), o + f); run = w ? __ffsll((long long)w) - 1 : 64; }
-								else { const uint64_t w = ~bits64(plane(P, PL_J1), o + f - 63); run = w ? __clzll((long long)w) : 64; }
-								if (bp >= 0) { // the rescued base is not the original one: stop in front of it
-									const int ib = dir ? n - 1 - bp : bp;
-									if (ib >= z.i && ib < z.i + run) run = ib - z.i;
-								}
-								if (run > 0) {
-									max_heap = max_heap > 1 ? max_heap : 1;
-									z.i += run, z.clean += run;
-									extract_kmer(P, o, n, dir, z.i - 1, k - 1, -1, 0, z.x);
-									break; // PC_STEP again at the new position
-								}
-							}
-							osf = __ldg(P.fl + o + (dir ? f + k - 1 : f));
-							pc = PC_AFTER_OWN;
-						} else { req_b = cb; pc = PC_OWN_DONE; yield = true; }
-					} else pc = PC_AFTER_OWN;
-				} else pc = PC_AFTER_OWN;
-				break;
-			}
-			case PC_OWN_DONE: { // os = res (correct.c:299)
-				osf = (res >= 0 && (res & 0xff) >= P.min_cov ? FL_SOL : 0) | ((res & 0xff) >= P.min_cov + 1 ? FL_A : 0) |
-				      (res >= 0 && (res >> 8 & 0xff) >= P.min_cov ? FL_H : 0);
-				pc = PC_AFTER_OWN;
-				break;
-			}
-			case PC_AFTER_OWN: {
+			if (pc == PC_AFTER_OWN) {
 				fixed = z.i > n; // correct.c:295 with end == n
 				if (has_c && cb < 4) {
 					if ((ff & FL_Q) && (osf & FL_A) && (ff & FL_LC)) fixed = true; // correct.c:299-301
@@ -528,31 +447,20 @@ __global__ void __launch_bounds__(128, 4) k_ec_search(EcParams P)
 					if (allowed) alt_mask = has_c && cb < 4 ? 0xF & ~(1 << cb) : 0xF;
 				}
 				pc = PC_ALT_NEXT;
-				break;
 			}
-			case PC_ALT_NEXT: {
+			if (pc == PC_ALT_NEXT) {
 				if (alt_mask) {
 					cur_alt = __ffs(alt_mask) - 1;
 					alt_mask &= alt_mask - 1;
 					req_b = cur_alt; pc = PC_ALT_DONE; yield = true;
 				} else pc = PC_FINISH;
-				break;
 			}
-			case PC_ALT_DONE: { // correct.c:320-333
-				if (res >= 0 && (res & 0xff) >= P.min_cov) {
-					const uint32_t ec = has_c && cb < 4 ? 1u : 0u;
-					cand |= (1u | ec << 1 | (ec && (ff & FL_Q) ? 4u : 0u) | ((res >> 8 & 0xff) < P.min_cov ? 16u : 0u)) << (8 * cur_alt);
-					++other_ext;
-				}
-				pc = PC_ALT_NEXT;
-				break;
-			}
-			case PC_FINISH: {
+			if (pc == PC_FINISH) {
 				const int n_added = (int)((cand & 1) + (cand >> 8 & 1) + (cand >> 16 & 1) + (cand >> 24 & 1));
 				pc = PC_POP;
 				if (!fixed && other_ext == 0) ++n_fail;
-				if (n_fail > n * 2) { rvl = -3; job_done = true; break; } // correct.c:342-347
-				if (has_c || n_added == 1) {
+				if (n_fail > n * 2) { rvl = -3; job_done = true; } // correct.c:342-347
+				else if (has_c || n_added == 1) {
 					uint32_t push = cand;
 					if (n_added > 1 && heap_n > P.max_heap) { // keep only the cheapest extension, first on ties (correct.c:349-355)
 						int min = INT_MAX, min_b = -1;
@@ -564,34 +472,56 @@ __global__ void __launch_bounds__(128, 4) k_ec_search(EcParams P)
 							}
 						push = cand & (0xffu << (8 * min_b));
 					}
-					const bool in_place = heap_n == 0 && (push & 0x01010101u) != 0 && ((push & 0x01010101u) & ((push & 0x01010101u) - 1)) == 0;
-					const EcState zz = z;
-#pragma unroll
-					for (int b = 0; b < 4; ++b) { // buf_update (correct.c:198-230), in base order
+					const uint32_t pm = push & 0x01010101u;
+					if (heap_n == 0 && pm != 0 && (pm & (pm - 1)) == 0) {
+						// a single successor and nothing else alive: it replaces z in registers (buf_update, correct.c:198-230)
+						const int b = (__ffs(pm) - 1) >> 3;
 						const uint32_t c = push >> (8 * b) & 0xff;
-						if (!(c & 1)) continue;
-						EcState s = zz;
-						s.i = zz.i + 1;
-						s.tot_pen = zz.tot_pen + cand_weight(P, c);
-						if (c & 4) s.ecpos_high[0] = zz.i, s.ecpos_high[1] = zz.ecpos_high[0];
-						if (c & 2) {
-							s.ecpos[0] = zz.i;
-#pragma unroll
-							for (int t = 1; t < BFC_EC_HIST; ++t) s.ecpos[t] = zz.ecpos[t - 1];
-						}
-						s.clean = b == cob ? zz.clean + 1 : 0;
-						if (has_c) {
-							s.n_absent = zz.n_absent + (int)(c >> 3 & 1);
-							if (b != cb) { // the path changes this base: remember it (forward coordinates)
-								if (n_edits >= P.edit_cap) { rvl = EC_OVERFLOW; job_done = true; break; }
-								const int f = dir ? n - 1 - zz.i : zz.i;
-								edits[n_edits] = make_uint2((uint32_t)zz.edit, (uint32_t)f << 3 | (uint32_t)(dir ? 3 - b : b));
-								s.edit = n_edits++;
+						const int zi = z.i;
+						if (has_c && b != cb) { // the path changes this base: remember it (forward coordinates)
+							if (n_edits >= P.edit_cap) { rvl = EC_OVERFLOW; job_done = true; }
+							else {
+								const int f = dir ? n - 1 - zi : zi;
+								edits[n_edits] = make_uint2((uint32_t)z.edit, (uint32_t)f << 3 | (uint32_t)(dir ? 3 - b : b));
+								z.edit = n_edits++;
 							}
 						}
-						bfc_kmer_append(k, s.x, b);
-						if (in_place) { z = s; top_valid = true; }
-						else {
+						z.i = zi + 1;
+						z.tot_pen += cand_weight(P, c);
+						if (c & 4) z.ecpos_high[1] = z.ecpos_high[0], z.ecpos_high[0] = zi;
+						if (c & 2) {
+#pragma unroll
+							for (int t = BFC_EC_HIST - 1; t > 0; --t) z.ecpos[t] = z.ecpos[t - 1];
+							z.ecpos[0] = zi;
+						}
+						z.clean = b == cob ? z.clean + 1 : 0;
+						if (has_c) z.n_absent += (int)(c >> 3 & 1);
+						bfc_kmer_append(k, z.x, b);
+						top_valid = true;
+					} else {
+						for (int b = 0; b < 4 && !job_done; ++b) { // buf_update (correct.c:198-230), in base order
+							const uint32_t c = push >> (8 * b) & 0xff;
+							if (!(c & 1)) continue;
+							EcState s = z;
+							s.i = z.i + 1;
+							s.tot_pen = z.tot_pen + cand_weight(P, c);
+							if (c & 4) s.ecpos_high[0] = z.i, s.ecpos_high[1] = z.ecpos_high[0];
+							if (c & 2) {
+								s.ecpos[0] = z.i;
+#pragma unroll
+								for (int t = 1; t < BFC_EC_HIST; ++t) s.ecpos[t] = z.ecpos[t - 1];
+							}
+							s.clean = b == cob ? z.clean + 1 : 0;
+							if (has_c) {
+								s.n_absent = z.n_absent + (int)(c >> 3 & 1);
+								if (b != cb) {
+									if (n_edits >= P.edit_cap) { rvl = EC_OVERFLOW; job_done = true; break; }
+									const int f = dir ? n - 1 - z.i : z.i;
+									edits[n_edits] = make_uint2((uint32_t)z.edit, (uint32_t)f << 3 | (uint32_t)(dir ? 3 - b : b));
+									s.edit = n_edits++;
+								}
+							}
+							bfc_kmer_append(k, s.x, b);
 							uint32_t id;
 							if (heap_n < n_init) id = heapk[heap_n] & 0xfff;
 							else id = (uint32_t)n_init++;
@@ -605,9 +535,27 @@ __global__ void __launch_bounds__(128, 4) k_ec_search(EcParams P)
 					if (fin < best_pen) best_pen = fin, best_edit = z.edit, best_absent = z.n_absent, have_best = true;
 					if (++n_paths == BFC_MAX_PATHS) job_done = true;
 				}
-				break;
 			}
-			default: yield = true; break;
+			if (pc == PC_POP && !job_done) {
+				const int hs = heap_n + (top_valid ? 1 : 0);
+				max_heap = max_heap > 255 ? 255 : max_heap > hs ? max_heap : hs; // correct.c:276
+				if (hs == 0) { rvl = -2; job_done = true; }
+				else {
+					if (top_valid) top_valid = false;
+					else { // ks_heapdown-based pop (correct.c:281-283); the freed slot id parks behind the live keys
+						const uint32_t key = heapk[0];
+						--heap_n;
+						heapk[0] = heapk[heap_n];
+						heapk[heap_n] = key;
+						if (heap_n > 1) heapk_down(heapk, heap_n);
+						z = pool[key & 0xfff];
+					}
+					if (have_best && z.tot_pen > best_pen + P.max_path_diff) job_done = true; // correct.c:288
+					else if (z.i - n > P.max_end_ext) { // correct.c:289, 366-372; then the next pop
+						if (z.tot_pen < best_pen) best_pen = z.tot_pen, best_edit = z.edit, best_absent = z.n_absent, have_best = true;
+						if (++n_paths == BFC_MAX_PATHS) job_done = true;
+					} else pc = PC_STEP;
+				}
 			}
 			if (job_done) {
 				if (rvl == EC_OVERFLOW) P.overflow[atomicAdd(P.ctr, 1ULL)] = (uint32_t)jid;
@@ -632,7 +580,76 @@ __global__ void __launch_bounds__(128, 4) k_ec_search(EcParams P)
 				}
 				pc = PC_NEWJOB;
 			}
-		}
+			if (pc == PC_NEWJOB) {
+				job += n_slots;
+				if (job >= P.n_jobs) { pc = PC_EXIT; yield = true; }
+				else {
+					jid = P.redo ? (int)P.redo[job] : (int)job;
+					const int r = jid >> 1;
+					const ReadDesc d = P.desc[r];
+					if (d.start0 >= 0) { // else: nothing to search for this read
+						dir = jid & 1;
+						const uint64_t ob = P.off[r];
+						o = (int64_t)(ob - P.base0);
+						n = (int)(P.off[r + 1] - ob - 1);
+						bp = d.brute >= 0 ? d.brute >> 2 : -1, bb = d.brute & 3;
+						// the reverse-complement k-mer hashes like the forward one only for odd k (kmer.h:81)
+						memo_dir = dir == 0 || (k & 1) != 0;
+						const int start = dir ? d.start1 : d.start0;
+						heap_n = n_init = n_edits = 0, max_heap = 0, n_fail = 0, n_paths = 0, rvl = -1;
+						best_pen = INT_MAX, best_edit = -1, best_absent = 0, have_best = false;
+						// seed: the k-1 bases before position z.i (correct.c:260-267); [start, start+k) is a k-mer of ACGT
+						z.i = start + k - 1;
+						z.tot_pen = 0, z.edit = -1, z.n_absent = 0;
+#pragma unroll
+						for (int t = 0; t < BFC_EC_HIST; ++t) z.ecpos[t] = -1;
+#pragma unroll
+						for (int t = 0; t < BFC_EC_HIST_HIGH; ++t) z.ecpos_high[t] = -1;
+						if (start < 0 || z.i >= n) { P.res[jid] = make_int2(-1, 0); } // the reference asserts
+						else {
+							extract_kmer(P, o, n, dir, z.i - 1, k - 1, bp, bb, z.x);
+							z.clean = k - 1;
+							if (bp >= 0) { // bases after the rescue edit are the original ones
+								const int ib = dir ? n - 1 - bp : bp; // search position of the edit
+								if (ib >= start && ib <= z.i - 1) z.clean = z.i - 1 - ib;
+							}
+							top_valid = true;
+							pc = PC_POP;
+						}
+					}
+				}
+			}
+			if (pc == PC_STEP) {
+				has_c = z.i < n;
+				cand = 0, other_ext = 0, osf = 0, cb = cob = -1, ff = 0;
+				pc = PC_AFTER_OWN;
+				if (has_c) {
+					const int f = dir ? n - 1 - z.i : z.i;
+					ff = __ldg(P.fl + o + f);
+					const int ob = FL_OB(ff), cur = f == bp ? bb : ob;
+					cb = dir ? comp_b(cur) : cur, cob = dir ? comp_b(ob) : ob;
+					if (cb < 4) {
+						if (memo_dir && z.clean >= k - 1 && cb == cob) { // the read's own k-mer: K5 fetched it
+							int run = 0;
+							if (heap_n == 0) { // a lone state: step over every decision-free base at once
+								if (!dir) { const uint64_t w = ~bits64(plane(P, PL_J0), o + f); run = w ? __ffsll((long long)w) - 1 : 64; }
+								else { const uint64_t w = ~bits64(plane(P, PL_J1), o + f - 63); run = w ? __clzll((long long)w) : 64; }
+								if (bp >= 0) { // the rescued base is not the original one: stop in front of it
+									const int ib = dir ? n - 1 - bp : bp;
+									if (ib >= z.i && ib < z.i + run) run = ib - z.i;
+								}
+							}
+							if (run > 0) {
+								max_heap = max_heap > 1 ? max_heap : 1;
+								z.i += run, z.clean += run;
+								extract_kmer(P, o, n, dir, z.i - 1, k - 1, -1, 0, z.x);
+								pc = PC_STEP; // again, at the new position
+							} else osf = __ldg(P.fl + o + (dir ? f + k - 1 : f));
+						} else { req_b = cb; pc = PC_OWN_DONE; yield = true; }
+					}
+				}
+			}
+		} while (!yield);
 		if (pc == PC_EXIT) break;
 		// ---------------- convergent part: every lane that is still searching has exactly one lookup to do
 		{
