@@ -85,6 +85,7 @@ struct EcParams {
 	uint64_t pl_words;
 	const uint16_t *fl;          // per window position
 	ReadDesc *desc;
+	int4 *jobs;                  // per job: (window offset of the read, length, search start or -1, rescue edit or -1)
 	int2 *res;                   // per job: (return value of bfc_ec1dir, max_heap)
 	TabView tab;
 	int k, q, min_cov, win_multi_ec, max_end_ext;
@@ -329,6 +330,8 @@ __global__ void __launch_bounds__(128) k_ec_setup(EcParams P)
 			}
 		}
 		P.desc[r] = d;
+		P.jobs[2 * r] = make_int4((int)o, n, d.start0, d.brute);
+		P.jobs[2 * r + 1] = make_int4((int)o, n, d.start0 < 0 ? -1 : d.start1, d.brute);
 	}
 	block_add(P.ctr + 1, n_lookups);
 }
@@ -341,34 +344,45 @@ enum { PC_NEWJOB = 0, PC_POP, PC_STEP, PC_OWN_DONE, PC_AFTER_OWN, PC_ALT_NEXT, P
 
 __device__ __forceinline__ uint32_t hk_pen(uint32_t key) { return key >> 12; }
 
+// The key heap of a thread: keys 0..HK_SMEM-1 in shared memory (interleaved by thread, conflict-free),
+// the rest in the thread's global scratch.  Heaps hold a handful of states almost always.
+#define HK_SMEM 8
+#define EC_THREADS 128
+struct KeyHeap {
+	uint32_t *sm;   // &s_hk[0][threadIdx.x]
+	uint32_t *gl;   // global scratch of heap_cap keys
+	__device__ __forceinline__ uint32_t get(int j) const { return j < HK_SMEM ? sm[j * EC_THREADS] : gl[j]; }
+	__device__ __forceinline__ void set(int j, uint32_t v) const { if (j < HK_SMEM) sm[j * EC_THREADS] = v; else gl[j] = v; }
+};
+
 // klib heap with "less" = larger tot_pen: root = smallest penalty (correct.c:179, ksort.h:125-146)
-__device__ __forceinline__ void heapk_down(uint32_t *l, int n)
+__device__ __forceinline__ void heapk_down(const KeyHeap &l, int n)
 {
 	int i = 0, c;
-	const uint32_t tmp = l[0];
+	const uint32_t tmp = l.get(0);
 	while ((c = 2 * i + 1) < n) {
-		uint32_t vc = l[c];
+		uint32_t vc = l.get(c);
 		if (c != n - 1) {
-			const uint32_t vr = l[c + 1];
+			const uint32_t vr = l.get(c + 1);
 			if (hk_pen(vc) > hk_pen(vr)) ++c, vc = vr;
 		}
 		if (hk_pen(vc) > hk_pen(tmp)) break;
-		l[i] = vc; i = c;
+		l.set(i, vc); i = c;
 	}
-	l[i] = tmp;
+	l.set(i, tmp);
 }
 
-__device__ __forceinline__ void heapk_up(uint32_t *l, int n)
+__device__ __forceinline__ void heapk_up(const KeyHeap &l, int n)
 {
 	int c = n - 1;
-	const uint32_t tmp = l[c];
+	const uint32_t tmp = l.get(c);
 	while (c) {
 		const int par = (c - 1) >> 1;
-		const uint32_t vp = l[par];
+		const uint32_t vp = l.get(par);
 		if (hk_pen(tmp) > hk_pen(vp)) break;
-		l[c] = vp; c = par;
+		l.set(c, vp); c = par;
 	}
-	l[c] = tmp;
+	l.set(c, tmp);
 }
 
 // packed candidate of one step: bit 0 valid, 1 ec, 2 ec_high, 3 absent, 4 absent_high
@@ -377,11 +391,13 @@ __device__ __forceinline__ int cand_weight(const EcParams &P, uint32_t c)
 	return P.w_ec * (int)(c >> 1 & 1) + P.w_ec_high * (int)(c >> 2 & 1) + P.w_absent * (int)(c >> 3 & 1) + P.w_absent_high * (int)(c >> 4 & 1);
 }
 
-__global__ void __launch_bounds__(128, 4) k_ec_search(EcParams P)
+__global__ void __launch_bounds__(EC_THREADS, 4) k_ec_search(EcParams P)
 {
 	const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, n_slots = (int64_t)gridDim.x * blockDim.x;
 	EcState *const pool = P.pool + slot * P.heap_cap;
-	uint32_t *const heapk = P.heapk + slot * P.heap_cap;
+	__shared__ uint32_t s_hk[HK_SMEM][EC_THREADS];
+	KeyHeap heapk;
+	heapk.sm = &s_hk[0][threadIdx.x], heapk.gl = P.heapk + slot * P.heap_cap;
 	uint2 *const edits = P.edits + slot * P.edit_cap;
 	const int k = P.k;
 
@@ -394,6 +410,7 @@ __global__ void __launch_bounds__(128, 4) k_ec_search(EcParams P)
 	int heap_n = 0, n_init = 0, n_edits = 0, max_heap = 0, n_fail = 0, n_paths = 0, rvl = -1;
 	int best_pen = INT_MAX, best_edit = -1, best_absent = 0;
 	bool top_valid = false, have_best = false;
+	int z_id = -1; // pool slot of a successor that is still only in registers (its key is in the heap)
 	// step context
 	int cb = -1, cob = -1, ff = 0, osf = 0, alt_mask = 0, other_ext = 0, cur_alt = 0;
 	uint32_t cand = 0; // 4 x 8 bits, one per base
@@ -473,8 +490,9 @@ __global__ void __launch_bounds__(128, 4) k_ec_search(EcParams P)
 						push = cand & (0xffu << (8 * min_b));
 					}
 					const uint32_t pm = push & 0x01010101u;
-					if (heap_n == 0 && pm != 0 && (pm & (pm - 1)) == 0) {
-						// a single successor and nothing else alive: it replaces z in registers (buf_update, correct.c:198-230)
+					if (pm != 0 && (pm & (pm - 1)) == 0) {
+						// a single successor replaces z in registers (buf_update, correct.c:198-230); with other states alive
+						// its KEY goes through the heap like any other, the state is stored only if another one pops first
 						const int b = (__ffs(pm) - 1) >> 3;
 						const uint32_t c = push >> (8 * b) & 0xff;
 						const int zi = z.i;
@@ -497,7 +515,15 @@ __global__ void __launch_bounds__(128, 4) k_ec_search(EcParams P)
 						z.clean = b == cob ? z.clean + 1 : 0;
 						if (has_c) z.n_absent += (int)(c >> 3 & 1);
 						bfc_kmer_append(k, z.x, b);
-						top_valid = true;
+						if (heap_n == 0) top_valid = true;
+						else if (!job_done) {
+							uint32_t id;
+							if (heap_n < n_init) id = heapk.get(heap_n) & 0xfff;
+							else id = (uint32_t)n_init++;
+							heapk.set(heap_n++, (uint32_t)z.tot_pen << 12 | id);
+							heapk_up(heapk, heap_n);
+							z_id = (int)id;
+						}
 					} else {
 						for (int b = 0; b < 4 && !job_done; ++b) { // buf_update (correct.c:198-230), in base order
 							const uint32_t c = push >> (8 * b) & 0xff;
@@ -523,10 +549,10 @@ __global__ void __launch_bounds__(128, 4) k_ec_search(EcParams P)
 							}
 							bfc_kmer_append(k, s.x, b);
 							uint32_t id;
-							if (heap_n < n_init) id = heapk[heap_n] & 0xfff;
+							if (heap_n < n_init) id = heapk.get(heap_n) & 0xfff;
 							else id = (uint32_t)n_init++;
 							pool[id] = s;
-							heapk[heap_n++] = (uint32_t)s.tot_pen << 12 | id;
+							heapk.set(heap_n++, (uint32_t)s.tot_pen << 12 | id);
 							heapk_up(heapk, heap_n);
 						}
 					}
@@ -543,12 +569,16 @@ __global__ void __launch_bounds__(128, 4) k_ec_search(EcParams P)
 				else {
 					if (top_valid) top_valid = false;
 					else { // ks_heapdown-based pop (correct.c:281-283); the freed slot id parks behind the live keys
-						const uint32_t key = heapk[0];
+						const uint32_t key = heapk.get(0);
 						--heap_n;
-						heapk[0] = heapk[heap_n];
-						heapk[heap_n] = key;
+						heapk.set(0, heapk.get(heap_n));
+						heapk.set(heap_n, key);
 						if (heap_n > 1) heapk_down(heapk, heap_n);
-						z = pool[key & 0xfff];
+						if ((int)(key & 0xfff) != z_id) {
+							if (z_id >= 0) pool[z_id] = z; // the register state lost the pop: now it needs its slot
+							z = pool[key & 0xfff];
+						}
+						z_id = -1;
 					}
 					if (have_best && z.tot_pen > best_pen + P.max_path_diff) job_done = true; // correct.c:288
 					else if (z.i - n > P.max_end_ext) { // correct.c:289, 366-372; then the next pop
@@ -585,18 +615,16 @@ __global__ void __launch_bounds__(128, 4) k_ec_search(EcParams P)
 				if (job >= P.n_jobs) { pc = PC_EXIT; yield = true; }
 				else {
 					jid = P.redo ? (int)P.redo[job] : (int)job;
-					const int r = jid >> 1;
-					const ReadDesc d = P.desc[r];
-					if (d.start0 >= 0) { // else: nothing to search for this read
+					const int4 jr = P.jobs[jid];
+					if (jr.z >= 0) { // else: nothing to search for this read
 						dir = jid & 1;
-						const uint64_t ob = P.off[r];
-						o = (int64_t)(ob - P.base0);
-						n = (int)(P.off[r + 1] - ob - 1);
-						bp = d.brute >= 0 ? d.brute >> 2 : -1, bb = d.brute & 3;
+						o = (int64_t)(uint32_t)jr.x;
+						n = jr.y;
+						bp = jr.w >= 0 ? jr.w >> 2 : -1, bb = jr.w & 3;
 						// the reverse-complement k-mer hashes like the forward one only for odd k (kmer.h:81)
 						memo_dir = dir == 0 || (k & 1) != 0;
-						const int start = dir ? d.start1 : d.start0;
-						heap_n = n_init = n_edits = 0, max_heap = 0, n_fail = 0, n_paths = 0, rvl = -1;
+						const int start = jr.z;
+						heap_n = n_init = n_edits = 0, max_heap = 0, n_fail = 0, n_paths = 0, rvl = -1, z_id = -1;
 						best_pen = INT_MAX, best_edit = -1, best_absent = 0, have_best = false;
 						// seed: the k-1 bases before position z.i (correct.c:260-267); [start, start+k) is a k-mer of ACGT
 						z.i = start + k - 1;
@@ -755,7 +783,7 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 		h_off = off_copy.data();
 	}
 	const uint64_t limit = batch_bytes_limit();
-	const int threads = 128;
+	const int threads = EC_THREADS;
 	const int64_t max_slots = (int64_t)rt.sm_count * 4 * threads; // persistent: what is resident at 4 CTAs per SM
 	const int heap_cap = opt->max_heap + 6; // the search never holds more than max_heap + 4 states
 	const int edit_cap = edit_cap0();
@@ -769,7 +797,7 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 		const uint64_t n_rec = enum_padded(nb);
 		const uint64_t pl_words = (n_rec + PL_PAD) / 64 + 4;
 		const int64_t slots = std::min<int64_t>(max_slots, (2 * nr + threads - 1) / threads * threads);
-		size_t tot = 0, o_seq = 0, o_qual = 0, o_off = 0, o_aux = 0, o_pl, o_fl, o_y0, o_y1, o_desc, o_res, o_pool, o_heapk, o_edits, o_ovf, o_ctr;
+		size_t tot = 0, o_seq = 0, o_qual = 0, o_off = 0, o_aux = 0, o_pl, o_fl, o_y0, o_y1, o_desc, o_jobs, o_res, o_pool, o_heapk, o_edits, o_ovf, o_ctr;
 		if (host) {
 			o_seq = tot; tot = align_up(tot + nb, 256);
 			o_qual = tot; tot = align_up(tot + nb, 256);
@@ -781,6 +809,7 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 		o_y0 = tot; tot = align_up(tot + n_rec * 8, 256);
 		o_y1 = tot; tot = align_up(tot + n_rec * 8, 256);
 		o_desc = tot; tot = align_up(tot + nr * sizeof(ReadDesc), 256);
+		o_jobs = tot; tot = align_up(tot + 2 * nr * sizeof(int4), 256);
 		o_res = tot; tot = align_up(tot + 2 * nr * sizeof(int2), 256);
 		o_pool = tot; tot = align_up(tot + (size_t)slots * heap_cap * sizeof(EcState), 256);
 		o_heapk = tot; tot = align_up(tot + (size_t)slots * heap_cap * 4, 256);
@@ -809,7 +838,7 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 		}
 		P.pl = (const uint64_t*)(a + o_pl), P.pl_words = pl_words;
 		P.fl = (const uint16_t*)(a + o_fl);
-		P.desc = (ReadDesc*)(a + o_desc), P.res = (int2*)(a + o_res);
+		P.desc = (ReadDesc*)(a + o_desc), P.jobs = (int4*)(a + o_jobs), P.res = (int2*)(a + o_res);
 		P.n_reads = nr, P.n_jobs = 2 * nr;
 		P.tab = tab_view(ch);
 		P.k = opt->k, P.q = opt->q, P.min_cov = opt->min_cov, P.win_multi_ec = opt->win_multi_ec, P.max_end_ext = opt->max_end_ext;
