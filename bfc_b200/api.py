@@ -115,6 +115,14 @@ def lib():
                                      C.POINTER(Stats)]
     L.bfcg_trim_batch.argtypes = [C.POINTER(Opt), C.POINTER(BF), C.POINTER(Batch), C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.POINTER(Stats)]
+    L.bfcg_enum_records.argtypes = [C.POINTER(Opt), C.POINTER(Batch), C.c_int, C.c_void_p, C.c_void_p, u64p]
+    L.bfcg_count_records.argtypes = [C.POINTER(Opt), C.POINTER(BF), C.POINTER(BF), C.c_void_p, C.c_uint64,
+                                     C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Stats)]
+    L.bfcg_bf_init_shard.restype = C.POINTER(BF)
+    L.bfcg_bf_init_shard.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.bfcg_ch_export_device.restype = C.c_uint64
+    L.bfcg_ch_export_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.bfcg_ch_import_device.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
     L.bfcg_dev_alloc.restype = C.c_void_p
     L.bfcg_dev_alloc.argtypes = [C.c_uint64]
     L.bfcg_dev_free.argtypes = [C.c_void_p]
@@ -145,7 +153,7 @@ def lib():
 
 
 KERNEL_NAMES = ["count_probe", "count_resolve", "conflict_sort", "count_replay", "correct", "correct_redo", "trim",
-                "tab_rehash", "tab_hist", "tab_apply", "enum", "ec_lookup", "ec_setup", "ec_merge"]
+                "tab_rehash", "tab_hist", "tab_apply", "enum", "ec_lookup", "ec_setup", "ec_merge", "bucket"]
 
 
 def kernel_times():

@@ -64,6 +64,27 @@ bfc_bf_t *bfc_bf_init(int n_shift, int n_hashes)
 	return b;
 }
 
+// one shard of a filter split over n_owners ranks by the top bits of the block index: n_shift stays the
+// GLOBAL one (the probe positions derive from it, bbf.c:27-33), the allocation is 1/n_owners of the bytes
+bfc_bf_t *bfcg_bf_init_shard(int n_shift, int n_hashes, int n_owners)
+{
+	int bits = 0;
+	while ((1 << bits) < n_owners) ++bits;
+	if (n_shift + BFC_BLK_SHIFT > 64 || n_shift < BFC_BLK_SHIFT || (1 << bits) != n_owners || n_shift - BFC_BLK_SHIFT < bits) return 0;
+	if (bfcg_rt_init() != BFCG_OK) return 0;
+	bfc_bf_t *b = (bfc_bf_t*)calloc(1, sizeof(bfc_bf_t));
+	b->n_shift = n_shift, b->n_hashes = n_hashes;
+	const size_t bytes = ((size_t)1 << (n_shift - 3)) >> bits;
+	if (cudaMalloc(&b->b, bytes) != cudaSuccess) {
+		bfcg_fail(__func__, "cudaMalloc(Bloom filter shard)", cudaErrorMemoryAllocation);
+		free(b);
+		return 0;
+	}
+	cudaMemsetAsync(b->b, 0, bytes, bfcg_rt().stream);
+	cudaStreamSynchronize(bfcg_rt().stream);
+	return b;
+}
+
 // reference bbf.c:19-23
 void bfc_bf_destroy(bfc_bf_t *b)
 {

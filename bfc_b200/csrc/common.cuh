@@ -42,7 +42,7 @@ struct BfcgRuntime {
 };
 
 enum { KT_COUNT_PROBE = 0, KT_COUNT_RESOLVE, KT_COUNT_SORT, KT_COUNT_REPLAY, KT_CORRECT, KT_CORRECT_REDO,
-       KT_TRIM, KT_TAB_REHASH, KT_TAB_HIST, KT_TAB_APPLY, KT_ENUM, KT_EC_LOOKUP, KT_EC_SETUP, KT_EC_MERGE, KT_N };
+       KT_TRIM, KT_TAB_REHASH, KT_TAB_HIST, KT_TAB_APPLY, KT_ENUM, KT_EC_LOOKUP, KT_EC_SETUP, KT_EC_MERGE, KT_BUCKET, KT_N };
 
 int  bfcg_kt_begin(int id);   // records a start event on the stream when timing is on; returns a span index or -1
 void bfcg_kt_end(int idx);
@@ -106,6 +106,7 @@ struct bfc_ch_s {
 struct BloomView {
 	uint32_t *w;      // 16 words per 64-byte block
 	int n_shift, n_hashes;
+	uint64_t blk_mask; // block index -> index inside this allocation (all ones unless the filter is one shard of N)
 };
 
 struct TabView {
@@ -119,7 +120,7 @@ struct TabView {
 static inline BloomView bloom_view(const bfc_bf_t *b)
 {
 	BloomView v;
-	v.w = (uint32_t*)b->b, v.n_shift = b->n_shift, v.n_hashes = b->n_hashes;
+	v.w = (uint32_t*)b->b, v.n_shift = b->n_shift, v.n_hashes = b->n_hashes, v.blk_mask = ~0ULL;
 	return v;
 }
 
@@ -165,6 +166,9 @@ __device__ __forceinline__ BloomProbe bloom_locate(uint64_t hash, int n_shift)
 	if ((p.h2 & 31) == 0) p.h2 = (p.h2 + 1) & BFC_BLK_MASK;
 	return p;
 }
+
+// the 16 words of a block inside this view's allocation
+__device__ __forceinline__ uint32_t *bloom_block(const BloomView &v, uint64_t blk) { return v.w + ((blk & v.blk_mask) << 4); }
 
 // number of probe bits set in the block at `w` (16 words); the reference's probe walk
 // (bbf.c:35-42 / 54-61): positions < 8 belong to the lock byte and do not count.

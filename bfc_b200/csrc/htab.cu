@@ -337,6 +337,40 @@ uint64_t bfcg_ch_export(const bfc_ch_t *ch, uint32_t *sub, uint64_t *key)
 	return n;
 }
 
+// all entries as (sub-table index, slot) pairs in DEVICE arrays, unsorted (multi-GPU table exchange)
+uint64_t bfcg_ch_export_device(const bfc_ch_t *ch, uint32_t *d_sub, uint64_t *d_key)
+{
+	if (bfcg_rt_init() != BFCG_OK) return 0;
+	BfcgRuntime &rt = bfcg_rt();
+	unsigned long long c[2] = {0, 0};
+	if (tab_read_counters(ch, c) != BFCG_OK) return 0;
+	if (d_sub == 0 || d_key == 0 || c[0] == 0) return c[0];
+	unsigned long long *cursor = ch->counters + 3;
+	cudaMemsetAsync(cursor, 0, 8, rt.stream);
+	k_tab_export<<<rt.sm_count * 8, 256, 0, rt.stream>>>(ch->slots, ch->rbits, tab_capacity(ch), d_sub, (unsigned long long*)d_key, cursor);
+	++rt.n_launches;
+	if (cudaStreamSynchronize(rt.stream) != cudaSuccess) { bfcg_fail(__func__, "kernel", cudaGetLastError()); return 0; }
+	return c[0];
+}
+
+// add n entries (none of them present yet) from DEVICE arrays
+int bfcg_ch_import_device(bfc_ch_t *ch, uint64_t n, const uint32_t *d_sub, const uint64_t *d_key)
+{
+	int r;
+	if ((r = bfcg_rt_init()) != BFCG_OK) return r;
+	BfcgRuntime &rt = bfcg_rt();
+	if (n == 0) return BFCG_OK;
+	if ((r = bfcg_tab_reserve(ch, n)) != BFCG_OK) return r;
+	unsigned long long *fail = ch->counters + 2, h_fail = 0;
+	BFCG_CUDA(cudaMemsetAsync(fail, 0, 8, rt.stream));
+	k_tab_put_raw<<<(unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)rt.sm_count * 32), 256, 0, rt.stream>>>(tab_view(ch), d_sub, (const unsigned long long*)d_key, n, fail);
+	BFCG_LAUNCH_CHECK();
+	BFCG_CUDA(cudaMemcpyAsync(&h_fail, fail, 8, cudaMemcpyDeviceToHost, rt.stream));
+	BFCG_CUDA(cudaStreamSynchronize(rt.stream));
+	if (h_fail) return bfcg_fail(__func__, "import found full regions", cudaSuccess);
+	return BFCG_OK;
+}
+
 // reference htab.c:129-149.  Same container: u32 k, u32 l_pre, then per sub-table
 // u32 n_buckets, u32 size, size raw u64 keys.  Key order inside a sub-table is
 // ascending here (khash slot order there); n_buckets is the smallest khash size that

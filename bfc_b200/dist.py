@@ -1,0 +1,233 @@
+"""Multi-GPU count phase: one process per GPU, k-mers sharded by Bloom-block prefix.
+
+Every ordering constraint of the count phase is local to one 64-byte Bloom block
+(reference bbf.c:25-45, count.c:54-70), so rank r of N owns the blocks whose index has
+the top log2(N) bits equal to r -- a contiguous 1/N of the first filter (and of bf_high
+in trim mode) -- and the table entries of exactly those k-mers.
+
+The reads are consumed in GLOBAL chunks; rank r holds the r-th piece of every chunk.
+Per chunk:
+    1. enumerate the k-mers of the local piece and bucket them by owner   (bfcg_enum_records)
+    2. all-to-all of the 16-byte records over NVLink                      (torch.distributed / NCCL)
+       -- the receiver gets the pieces concatenated in rank order = the global read order
+    3. the Bloom -> table cascade over the received records, in order     (bfcg_count_records)
+so the result is that of the reference's `-t1` run on the whole input, bit for bit.
+After the last chunk the table shards (or the bf_high shards) are all-gathered: every
+rank ends with the complete table and corrects its own reads with no communication.
+
+The protocol is written against a small backend interface so that the same driver runs
+on the CUDA library (CudaBackend, below) and, in the CPU tests, on the oracle with the
+gloo backend (tests/test_dist_cpu.py).  torch is plumbing here: device buffers for the
+exchange and the collectives; every byte of compute is in libbfc_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def owner_bits(world: int) -> int:
+    b = world.bit_length() - 1
+    if world < 1 or (1 << b) != world or world > 8:
+        raise ValueError("the number of ranks must be 1, 2, 4 or 8")
+    return b
+
+
+def piece_bounds(chunk_lo: int, chunk_hi: int, rank: int, world: int):
+    """Reads [lo, hi) of the global chunk [chunk_lo, chunk_hi) that rank `rank` holds: contiguous, in rank order."""
+    n = chunk_hi - chunk_lo
+    return chunk_lo + n * rank // world, chunk_lo + n * (rank + 1) // world
+
+
+class ShardedCount:
+    """The count phase of one rank.  `backend` supplies the compute and the buffers."""
+
+    def __init__(self, backend, rank: int, world: int, group=None):
+        owner_bits(world)
+        self.be, self.rank, self.world, self.group = backend, rank, world, group
+        self.sent_records = 0
+        self.recv_records = 0
+
+    # -- collectives (world == 1 short-circuits so a single process needs no process group)
+    def _all_gather_counts(self, counts):
+        t = torch.tensor(counts, dtype=torch.int64, device=self.be.device)
+        if self.world == 1:
+            return t.view(1, -1).cpu()
+        out = torch.empty(self.world * self.world, dtype=torch.int64, device=self.be.device)
+        dist.all_gather_into_tensor(out, t, group=self.group)
+        return out.view(self.world, self.world).cpu()
+
+    def _all_to_all(self, src, in_splits, out_splits):
+        out = self.be.empty(int(sum(out_splits)), torch.int64)
+        if self.world == 1:
+            out.copy_(src[:out.numel()])
+            return out
+        dist.all_to_all_single(out, src[:int(sum(in_splits))], list(out_splits), list(in_splits), group=self.group)
+        return out
+
+    def count_piece(self, piece):
+        """Count this rank's piece of the current global chunk (every rank must call this once per chunk)."""
+        y0, y1, counts = self.be.enum_records(piece, self.world)
+        m = self._all_gather_counts(counts)              # m[src][dst]
+        in_splits = [int(v) for v in m[self.rank]]
+        out_splits = [int(m[src][self.rank]) for src in range(self.world)]
+        r0 = self._all_to_all(y0, in_splits, out_splits)
+        r1 = self._all_to_all(y1, in_splits, out_splits)
+        self.sent_records += sum(in_splits) - in_splits[self.rank]
+        self.recv_records += sum(out_splits)
+        self.be.count_records(r0, r1, int(sum(out_splits)), self.world)
+
+    def gather(self):
+        """Replicate the result on every rank: the complete table (normal mode) or bf_high (trim mode)."""
+        if self.be.filter_mode:
+            shard = self.be.bf_high_shard()
+            if self.world == 1:
+                full = shard
+            else:
+                full = self.be.empty(shard.numel() * self.world, torch.uint8)
+                dist.all_gather_into_tensor(full, shard, group=self.group)
+            self.be.set_bf_high_full(full)
+            return
+        sub, key = self.be.export_table()
+        n = int(sub.numel())
+        if self.world == 1:
+            self.be.import_table([(sub, key)])
+            return
+        sizes = torch.empty(self.world, dtype=torch.int64, device=self.be.device)
+        dist.all_gather_into_tensor(sizes, torch.tensor([n], dtype=torch.int64, device=self.be.device), group=self.group)
+        sizes = [int(v) for v in sizes.cpu()]
+        cap = max(max(sizes), 1)
+        psub, pkey = self.be.empty(cap, torch.int32), self.be.empty(cap, torch.int64)
+        psub[:n].copy_(sub)
+        pkey[:n].copy_(key)
+        gsub, gkey = self.be.empty(cap * self.world, torch.int32), self.be.empty(cap * self.world, torch.int64)
+        dist.all_gather_into_tensor(gsub, psub, group=self.group)
+        dist.all_gather_into_tensor(gkey, pkey, group=self.group)
+        self.be.import_table([(gsub[r * cap:r * cap + sizes[r]], gkey[r * cap:r * cap + sizes[r]]) for r in range(self.world)])
+
+
+class CudaBackend:
+    """The C ABI of libbfc_b200.so (include/bfc_b200.h) behind the ShardedCount backend interface."""
+
+    def __init__(self, opt, world: int, device_index: int = 0):
+        from . import api
+        self.api, self.L, self.opt, self.world = api, api.lib(), opt, world
+        self.filter_mode = bool(opt.filter_mode)
+        self.device = torch.device("cuda", device_index)
+        L = self.L
+        self.stats = api.Stats()
+        self.bf = L.bfcg_bf_init_shard(opt.bf_shift, opt.n_hashes, world)
+        self.bf_high = L.bfcg_bf_init_shard(opt.bf_shift, opt.n_hashes, world) if self.filter_mode else None
+        self.ch = None if self.filter_mode else L.bfc_ch_init(opt.k, opt.l_pre)
+        if not self.bf or (self.filter_mode and not self.bf_high) or (not self.filter_mode and not self.ch):
+            raise api.BfcError("allocation failed: " + L.bfcg_last_error().decode())
+        self.full_ch = None          # complete table after gather()
+        self.full_bf_high = None     # complete bf_high (torch tensor keeps the memory) after gather()
+        self._bf_high_view = None
+        self._buf = {}
+
+    def empty(self, n, dtype):
+        return torch.empty(max(int(n), 0), dtype=dtype, device=self.device)
+
+    def _scratch(self, name, n):
+        t = self._buf.get(name)
+        if t is None or t.numel() < n:
+            t = self._buf[name] = torch.empty(int(n), dtype=torch.int64, device=self.device)
+        return t
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise self.api.BfcError(f"{what} failed ({rc}): {self.L.bfcg_last_error().decode()}")
+
+    def enum_records(self, batch, world):
+        """batch: api.Batch (host or device pointers).  Returns (y0, y1, counts) bucketed by owner."""
+        n = int(batch.n_bytes)
+        y0, y1 = self._scratch("y0", n), self._scratch("y1", n)
+        counts = (C.c_uint64 * 8)()
+        torch.cuda.current_stream(self.device).synchronize()
+        self._check(self.L.bfcg_enum_records(C.byref(self.opt), C.byref(batch), world, C.c_void_p(y0.data_ptr()),
+                                             C.c_void_p(y1.data_ptr()), counts), "bfcg_enum_records")
+        return y0, y1, [int(counts[i]) for i in range(world)]
+
+    def count_records(self, y0, y1, n, world):
+        torch.cuda.current_stream(self.device).synchronize()
+        self._check(self.L.bfcg_count_records(C.byref(self.opt), self.bf, self.bf_high, self.ch, n,
+                                              C.c_void_p(y0.data_ptr()), C.c_void_p(y1.data_ptr()), world,
+                                              C.byref(self.stats)), "bfcg_count_records")
+
+    def shard_bytes(self) -> int:
+        return (1 << (self.opt.bf_shift - 3)) // self.world
+
+    def _shard_tensor(self, bf):
+        t = torch.empty(self.shard_bytes(), dtype=torch.uint8, device=self.device)
+        cudart = C.CDLL("libcudart.so.12")
+        torch.cuda.current_stream(self.device).synchronize()
+        rc = cudart.cudaMemcpy(C.c_void_p(t.data_ptr()), C.c_void_p(bf.contents.b), C.c_size_t(t.numel()), 3)
+        if rc != 0:
+            raise self.api.BfcError(f"cudaMemcpy failed: {rc}")
+        return t
+
+    def bf_shard(self):
+        return self._shard_tensor(self.bf)
+
+    def bf_high_shard(self):
+        return self._shard_tensor(self.bf_high)
+
+    def set_bf_high_full(self, full):
+        torch.cuda.current_stream(self.device).synchronize()
+        self.full_bf_high = full
+        self._bf_high_view = self.api.BF(self.opt.bf_shift, self.opt.n_hashes, full.data_ptr())
+
+    def bf_high_full(self):
+        """bfc_bf_t* over the gathered filter (for bfcg_trim_batch)."""
+        return C.pointer(self._bf_high_view)
+
+    def export_table(self):
+        n = int(self.L.bfcg_ch_export_device(self.ch, None, None))
+        sub, key = self.empty(n, torch.int32), self.empty(n, torch.int64)
+        if n:
+            got = int(self.L.bfcg_ch_export_device(self.ch, C.c_void_p(sub.data_ptr()), C.c_void_p(key.data_ptr())))
+            if got != n:
+                raise self.api.BfcError("bfcg_ch_export_device failed: " + self.L.bfcg_last_error().decode())
+        return sub, key
+
+    def import_table(self, parts):
+        L = self.L
+        total = sum(int(s.numel()) for s, _ in parts)
+        if self.world == 1:
+            self.full_ch = self.ch   # a single rank already holds everything
+            return
+        full = L.bfc_ch_init(self.opt.k, self.opt.l_pre)
+        if not full:
+            raise self.api.BfcError("bfc_ch_init failed: " + L.bfcg_last_error().decode())
+        self._check(L.bfcg_ch_reserve(full, total), "bfcg_ch_reserve")
+        torch.cuda.current_stream(self.device).synchronize()
+        for sub, key in parts:
+            if sub.numel():
+                self._check(L.bfcg_ch_import_device(full, int(sub.numel()), C.c_void_p(sub.data_ptr()),
+                                                    C.c_void_p(key.data_ptr())), "bfcg_ch_import_device")
+        L.bfc_ch_destroy(self.ch)    # the shard is not needed any more
+        self.ch = None
+        self.full_ch = full
+
+    def release_first_filter(self):
+        """The first filter never outlives the count phase (reference count.c:155)."""
+        if self.bf:
+            self.L.bfc_bf_destroy(self.bf)
+            self.bf = None
+
+    def close(self):
+        L = self.L
+        self.release_first_filter()
+        if self.bf_high:
+            L.bfc_bf_destroy(self.bf_high)
+            self.bf_high = None
+        if self.full_ch and self.full_ch != self.ch:
+            L.bfc_ch_destroy(self.full_ch)
+        if self.ch:
+            L.bfc_ch_destroy(self.ch)
+        self.ch = self.full_ch = None
+        self._buf.clear()

@@ -63,7 +63,7 @@ const char *bfcg_last_error(void);
 /* per-kernel device time accumulated since the last call (needs bfcg_set_timing(1)); indices:
  * 0 count_probe 1 count_resolve 2 conflict sort 3 count_replay 4 correct (search) 5 correct redo 6 trim
  * 7 table rehash 8 table hist 9 table deferred-apply 10 k-mer enumeration 11 correct: batched lookups
- * 12 correct: coverage flags + per-read setup 13 correct: merge + rewrite.
+ * 12 correct: coverage flags + per-read setup 13 correct: merge + rewrite 14 sharded count: owner bucketing.
  * Returns the number of valid entries. */
 int  bfcg_kernel_times(double *ms, uint64_t *launches, int n);
 /* CUDA events on the engine's stream: record into slot 0..7, elapsed ms between two slots */
@@ -88,6 +88,26 @@ int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int mode,
  * bytes (as worker_ec's memmove does). */
 int bfcg_trim_batch(const bfc_opt_t *opt, const bfc_bf_t *bf_high, const bfcg_batch_t *batch,
                     uint8_t *keep, int32_t *tstart, int32_t *tend, bfcg_stats_t *stats);
+
+/* sharded counting: one rank of N (N = 1, 2, 4, 8), one process per GPU -----------
+ * The owner of a k-mer is given by the top log2(N) bits of its Bloom block index (bbf.c:27-28), so rank r
+ * holds blocks [r, r+1) * 2^(b-9) / N of the first filter (and of bf_high) and the table entries of exactly
+ * those k-mers.  Records are 16 bytes: y0 | is_high << 63 and y1 (the two words of bfc_kmer_hash).
+ *
+ * bfcg_enum_records: enumerate the k-mers of a batch (count.c:72-89) and bucket them by owner, stream order
+ * kept inside a bucket.  d_y0 / d_y1: device arrays with room for batch->n_bytes records; counts[n_owners]
+ * (host) receives the bucket sizes; bucket o starts at counts[0] + ... + counts[o-1].
+ * bfcg_count_records: the Bloom -> table cascade (count.c:54-70) over records in stream order (what the
+ * all-to-all delivers: the pieces of the ranks concatenated in rank order), against this rank's shard. */
+int bfcg_enum_records(const bfc_opt_t *opt, const bfcg_batch_t *batch, int n_owners,
+                      uint64_t *d_y0, uint64_t *d_y1, uint64_t *counts);
+int bfcg_count_records(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, bfc_ch_t *ch, uint64_t n_rec,
+                       const uint64_t *d_y0, const uint64_t *d_y1, int n_owners, bfcg_stats_t *stats);
+bfc_bf_t *bfcg_bf_init_shard(int n_shift, int n_hashes, int n_owners);   /* 2^(n_shift-3) / n_owners bytes */
+/* table exchange: entries as (sub-table index, key50<<14 | val14) in DEVICE arrays, unsorted; returns n
+ * (pass NULLs to get n); import adds entries that are not present yet (shards are disjoint) */
+uint64_t bfcg_ch_export_device(const bfc_ch_t *ch, uint32_t *d_sub, uint64_t *d_key);
+int      bfcg_ch_import_device(bfc_ch_t *ch, uint64_t n, const uint32_t *d_sub, const uint64_t *d_key);
 
 /* device memory helpers for callers that keep batches resident in HBM -------------- */
 void *bfcg_dev_alloc(uint64_t bytes);

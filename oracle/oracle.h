@@ -77,6 +77,12 @@ typedef struct {
 void orc_count_batch(const orc_opt_t *opt, orc_bf_t *bf, orc_bf_t *bf_high, orc_ch_t *ch,
                      const orc_batch_t *batch, uint64_t stats[2]);
 
+/* the same cascade in two halves, for the sharded protocol tests: records = (y[0] | is_high << 63, y[1]) */
+uint64_t orc_enum_records(const orc_opt_t *opt, const orc_batch_t *batch, uint64_t *y0, uint64_t *y1);
+uint64_t orc_hash_from_y(int k, uint64_t y0, uint64_t y1);
+void orc_count_records(const orc_opt_t *opt, orc_bf_t *bf, orc_bf_t *bf_high, orc_ch_t *ch, uint64_t n,
+                       const uint64_t *y0, const uint64_t *y1, uint64_t stats[2]);
+
 /* ---- correct (oracle_correct.c; reference correct.c) ---- */
 typedef struct orc_ecbuf_s orc_ecbuf_t;
 orc_ecbuf_t *orc_ecbuf_new(const orc_opt_t *opt, const orc_ch_t *ch, int mode);

@@ -92,6 +92,11 @@ def lib():
     L.orc_kmer_hash.argtypes = [C.c_int, u64p, u64p]
     L.orc_count_batch.argtypes = [C.POINTER(Opt), C.POINTER(BF), C.POINTER(BF), C.c_void_p,
                                   C.POINTER(Batch), u64p]
+    L.orc_enum_records.restype = C.c_uint64
+    L.orc_enum_records.argtypes = [C.POINTER(Opt), C.POINTER(Batch), u64p, u64p]
+    L.orc_hash_from_y.restype = C.c_uint64
+    L.orc_hash_from_y.argtypes = [C.c_int, C.c_uint64, C.c_uint64]
+    L.orc_count_records.argtypes = [C.POINTER(Opt), C.POINTER(BF), C.POINTER(BF), C.c_void_p, C.c_uint64, u64p, u64p, u64p]
     L.orc_correct_batch.argtypes = [C.POINTER(Opt), C.c_void_p, C.c_int, C.c_int64, u64p, u8p, u8p,
                                     u32p, u64p]
     L.orc_max_streak.restype = C.c_uint64

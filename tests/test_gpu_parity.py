@@ -197,3 +197,55 @@ def test_cli_matches_reference_golden(bfc, tmp_path):
         assert np.array_equal(sub, c.sub) and np.array_equal(key, c.key)
         out = subprocess.run([exe] + args + ["-r", str(dump), str(fq)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True).stdout
         assert out == c.corrected
+
+
+@pytest.mark.parametrize("world,k,b,trim", [(4, 31, 22, False), (2, 33, 20, True), (8, 55, 24, False)])
+def test_sharded_count_kernels_emulated_on_one_gpu(bfc, monkeypatch, world, k, b, trim):
+    """The sharded count path (bfcg_enum_records -> bucket exchange -> bfcg_count_records on 1/N filters) with
+    the N ranks emulated one after the other on one GPU: the shards concatenate to the oracle's filter and the
+    union of the shard tables is the oracle's table."""
+    import ctypes as C
+    import torch
+    from bfc_b200.dist import CudaBackend, piece_bounds
+    monkeypatch.setenv("BFC_B200_SUBBATCH", str(1 << 17))
+    seq, qual, off = synth_batch(60000, 16000, 120, seed=k + world, repeat=0.2)
+    N = len(off) - 1
+    opt = bfc.make_opt(k=k, bf_shift=b, filter_mode=1 if trim else 0)
+    o = orc.OracleRun(orc.make_opt(k=k, bf_shift=b, filter_mode=1 if trim else 0))
+    ranks = [CudaBackend(opt, world) for _ in range(world)]
+    try:
+        o.count(seq, qual, off)
+        chunk = 5000
+        for lo in range(0, N, chunk):
+            hi = min(N, lo + chunk)
+            sent = []
+            for r in range(world):  # every rank enumerates and buckets its piece
+                p0, p1 = piece_bounds(lo, hi, r, world)
+                s, q, f = seq[int(off[p0]):int(off[p1])], qual[int(off[p0]):int(off[p1])], off[p0:p1 + 1] - off[p0]
+                y0, y1, counts = ranks[r].enum_records(bfc.api.host_batch(s, q, f), world)
+                starts = np.concatenate([[0], np.cumsum(counts)])
+                sent.append([(y0[int(starts[d]):int(starts[d + 1])].clone(), y1[int(starts[d]):int(starts[d + 1])].clone()) for d in range(world)])
+            for d in range(world):  # the all-to-all: destination d receives the pieces in source-rank order
+                r0 = torch.cat([sent[r][d][0] for r in range(world)])
+                r1 = torch.cat([sent[r][d][1] for r in range(world)])
+                ranks[d].count_records(r0, r1, int(r0.numel()), world)
+        bloom = np.concatenate([ranks[r].bf_shard().cpu().numpy() for r in range(world)])
+        assert np.array_equal(bloom, o.bloom_bytes())
+        assert sum(int(r.stats.n_kmers) for r in ranks) == int(o.stats[0])
+        assert sum(int(r.stats.n_pass) for r in ranks) == int(o.stats[1])
+        if trim:
+            high = np.concatenate([ranks[r].bf_high_shard().cpu().numpy() for r in range(world)])
+            assert np.array_equal(high, o.bloom_bytes(high=True))
+        else:
+            parts = [ranks[r].export_table() for r in range(world)]
+            ranks[0].import_table(parts)
+            L = bfc.lib()
+            n = int(L.bfcg_ch_export(ranks[0].full_ch, None, None))
+            sub, key = np.zeros(n, dtype=np.uint32), np.zeros(n, dtype=np.uint64)
+            L.bfcg_ch_export(ranks[0].full_ch, sub.ctypes.data_as(bfc.api.u32p), key.ctypes.data_as(bfc.api.u64p))
+            so, ko = o.table()
+            assert np.array_equal(sub, so) and np.array_equal(key, ko)
+    finally:
+        for r in ranks:
+            r.close()
+        o.close()
