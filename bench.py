@@ -12,10 +12,11 @@ A *step* is one complete job: empty filter/table -> count every read -> histogra
 correct every read.  `value` times K steps with the reads already resident in HBM
 (CUDA events on the engine's stream, max over ranks); `e2e` times the same job through
 the C ABI with HOST buffers (H2D of every batch and D2H of the corrected reads inside
-the timed region).  N > 1 (one process per GPU under torchrun): every rank counts the
-whole read set (the table is needed in full by every rank for correction, and the
-exact -t1 order semantics need no exchange that way), correction is partitioned over
-the ranks; total work is fixed => "strong".
+the timed region).  N > 1 (one process per GPU under torchrun): the k-mers are sharded
+by Bloom-block prefix -- every rank enumerates its pieces of the reads, one all-to-all
+per global chunk delivers the 16-byte records to their owners in global read order,
+the table shards are all-gathered and the correction is partitioned by reads
+(bfc_b200/dist.py); total work is fixed => "strong".
 """
 from __future__ import annotations
 
@@ -197,6 +198,7 @@ def main():
     ap.add_argument("--reads", type=int, default=int(os.environ.get("BFC_BENCH_READS", 100_000_000)))
     ap.add_argument("--k", type=int, default=33)
     ap.add_argument("--bf-shift", type=int, default=37)
+    ap.add_argument("--chunk-reads", type=int, default=4_000_000, help="N > 1: reads per global chunk (one all-to-all each)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -207,7 +209,7 @@ def main():
     config = {"workload": f"count+correct: {args.reads} x {READ_LEN} bp synthetic reads at {COVERAGE:.0f}x, k={args.k}, "
                           f"Bloom 2^{args.bf_shift} bits, H=4, min_cov=3 (BASELINE configs[2], `-s 3g`)",
               "reads": args.reads, "read_len": READ_LEN, "genome": genome_size(args.reads), "k": args.k,
-              "bf_shift": args.bf_shift, "parallelism": f"count replicated, correct partitioned x{world}" if world > 1 else "single GPU",
+              "bf_shift": args.bf_shift, "parallelism": f"k-mers sharded by Bloom-block prefix x{world} (all-to-all per chunk), table all-gathered, correction partitioned by reads" if world > 1 else "single GPU",
               "l2": "inputs (>= 30 GB) and filter/table (>= 32 GB) exceed the 126 MB L2; no flush needed"}
 
     if args.impl == "reference":
@@ -250,52 +252,117 @@ def main():
         return float(t.item())
 
     n = args.reads
-    data = DeviceData(L, api, n)
-    # this rank's share of the correction
-    r0, r1 = n * rank // world, n * (rank + 1) // world
-    nb_mine = (r1 - r0) * (READ_LEN + 1)
-    byte0 = r0 * (READ_LEN + 1)
-    w_seq, w_qual = L.bfcg_dev_alloc(max(1, nb_mine)), L.bfcg_dev_alloc(max(1, nb_mine))
-    d_aux = L.bfcg_dev_alloc(max(8, 8 * (r1 - r0)))
-    assert w_seq and w_qual and d_aux
     cudart = C.CDLL("libcudart.so.12")
-
     opt = bfc_b200.make_opt(k=args.k, bf_shift=args.bf_shift)
-    eng = bfc_b200.Engine(opt, timing=True)
-    count_b = data.batch(data.d_seq, data.d_qual, 0, n)
-    # the working copy holds reads [r0, r1) at offset 0: shift the base pointers so absolute offsets still apply
-    work_b = data.batch(w_seq - byte0, w_qual - byte0, r0, r1)
+    RB = READ_LEN + 1
 
-    def restore_working_copy():
-        cudart.cudaMemcpy(C.c_void_p(w_seq), C.c_void_p(data.d_seq + byte0), C.c_size_t(nb_mine), 3)
-        cudart.cudaMemcpy(C.c_void_p(w_qual), C.c_void_p(data.d_qual + byte0), C.c_size_t(nb_mine), 3)
+    if world == 1:
+        data = DeviceData(L, api, n)
+        r0, r1 = 0, n
+        nb_mine = n * RB
+        w_seq, w_qual = L.bfcg_dev_alloc(max(1, nb_mine)), L.bfcg_dev_alloc(max(1, nb_mine))
+        d_aux = L.bfcg_dev_alloc(max(8, 8 * n))
+        assert w_seq and w_qual and d_aux
+        eng = bfc_b200.Engine(opt, timing=True)
+        count_b = data.batch(data.d_seq, data.d_qual, 0, n)
+        work_b = data.batch(w_seq, w_qual, 0, n)
+        src_seq, src_qual, n_mine = data.d_seq, data.d_qual, n
+        pieces = [(0, n)]
 
-    def step():
-        eng.reset()
-        restore_working_copy()
-        eng.count_batch(count_b)
-        if r1 > r0:
+        def step():
+            eng.reset()
+            cudart.cudaMemcpy(C.c_void_p(w_seq), C.c_void_p(src_seq), C.c_size_t(nb_mine), 3)
+            cudart.cudaMemcpy(C.c_void_p(w_qual), C.c_void_p(src_qual), C.c_size_t(nb_mine), 3)
+            eng.count_batch(count_b)
             eng.correct_batch(work_b, d_aux)
+
+        def get_stats():
+            return eng.stats.as_dict()
+
+        def clear_stats():
+            eng.stats = api.Stats()
+    else:
+        # rank r holds the r-th piece of every global chunk (bfc_b200/dist.py): local reads = its pieces back to back
+        from bfc_b200.dist import CudaBackend, ShardedCount, piece_bounds
+        G = genome_size(n)
+        pieces = [piece_bounds(lo, min(n, lo + args.chunk_reads), rank, world) for lo in range(0, n, args.chunk_reads)]
+        n_mine = sum(p1 - p0 for p0, p1 in pieces)
+        nb_mine = n_mine * RB
+        d_gen = L.bfcg_dev_alloc(G)
+        src_seq, src_qual = L.bfcg_dev_alloc(max(1, nb_mine)), L.bfcg_dev_alloc(max(1, nb_mine))
+        w_seq, w_qual = L.bfcg_dev_alloc(max(1, nb_mine)), L.bfcg_dev_alloc(max(1, nb_mine))
+        d_off, d_off_tmp = L.bfcg_dev_alloc(8 * (n_mine + 1)), L.bfcg_dev_alloc(8 * (max(p1 - p0 for p0, p1 in pieces) + 1))
+        d_aux = L.bfcg_dev_alloc(max(8, 8 * n_mine))
+        assert d_gen and src_seq and src_qual and w_seq and w_qual and d_off and d_off_tmp and d_aux, L.bfcg_last_error()
+        assert L.bfcg_synth_genome(d_gen, G, SEED) == 0
+        loc = 0
+        piece_loc = []
+        for p0, p1 in pieces:
+            assert L.bfcg_synth_reads(d_gen, G, SEED, p0, p1 - p0, READ_LEN, ERR, N_RATE, src_seq + loc * RB, src_qual + loc * RB, d_off_tmp) == 0
+            piece_loc.append(loc)
+            loc += p1 - p0
+        h_off_local = (np.arange(n_mine + 1, dtype=np.uint64) * np.uint64(RB))
+        L.bfcg_h2d(d_off, h_off_local.ctypes.data, 8 * (n_mine + 1))
+        L.bfcg_dev_free(d_off_tmp)
+        be = CudaBackend(opt, world, local_rank)
+        L.bfcg_set_timing(1)
+        sc = ShardedCount(be, rank, world)
+
+        def dev_batch(seq_ptr, qual_ptr, first, count):
+            b = api.Batch()
+            b.n_reads, b.where, b.n_bytes = count, api.DEVICE, count * RB
+            b.off = C.cast(d_off, api.u64p)   # offsets relative to the pointers below
+            b.seq, b.qual = C.cast(seq_ptr + first * RB, api.u8p), C.cast(qual_ptr + first * RB, api.u8p)
+            return b
+
+        count_pieces = [dev_batch(src_seq, src_qual, piece_loc[i], p1 - p0) for i, (p0, p1) in enumerate(pieces)]
+        work_b = dev_batch(w_seq, w_qual, 0, n_mine)
+        r0, r1 = 0, n_mine
+
+        def step():
+            be.reset()
+            cudart.cudaMemcpy(C.c_void_p(w_seq), C.c_void_p(src_seq), C.c_size_t(nb_mine), 3)
+            cudart.cudaMemcpy(C.c_void_p(w_qual), C.c_void_p(src_qual), C.c_size_t(nb_mine), 3)
+            for b in count_pieces:
+                sc.count_piece(b)
+            sc.gather()
+            if n_mine:
+                be.correct_batch(work_b, d_aux)
+
+        def get_stats():
+            return be.stats.as_dict()
+
+        def clear_stats():
+            be.stats = api.Stats()
 
     for _ in range(args.warmup):
         step()
     barrier()
-    eng.stats = api.Stats()
+    clear_stats()
     api.kernel_times()
     clocks = ClockSampler(local_rank)
     clocks.start()
     L.bfcg_event_record(0)
     for _ in range(args.steps):
         step()
+    L.bfcg_sync()
     L.bfcg_event_record(1)
     L.bfcg_sync()
     ms = L.bfcg_event_elapsed_ms(0, 1)
     barrier()
     clk = clocks.stop()
     ms = max_over_ranks(ms)
-    st = eng.stats.as_dict()
+    st = get_stats()
     kt = api.kernel_times()
     value = n * args.steps / (ms / 1e3) / 1e6
+    if world > 1:  # whole-job counters for the roofline arithmetic and the stats block
+        import torch
+        keys = ["n_kmers", "n_pass", "n_pending", "n_conflict", "n_lookups", "n_redo", "n_launches"]
+        t = torch.tensor([st[k_] for k_ in keys], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        launches_rank0 = st["n_launches"]
+        st.update({k_: int(v) for k_, v in zip(keys, t.cpu())})
+        st["n_launches"] = launches_rank0
 
     # ---- roofline of the dominant kernel (algorithmic bytes: DESIGN.md "Kernels")
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -303,8 +370,8 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    count_bytes = 2 * data.nb * args.steps + 64 * st["n_kmers"] + 16 * st["n_pass"]
-    correct_bytes = 32 * st["n_lookups"] + 4 * nb_mine * args.steps
+    count_bytes = 2 * n * RB * args.steps + 64 * st["n_kmers"] + 16 * st["n_pass"]
+    correct_bytes = 32 * st["n_lookups"] + 4 * n * RB * args.steps
     kern = {}
     for name, alg in (("count_probe", count_bytes), ("correct", correct_bytes)):
         t_ms, launches = kt.get(name, (0.0, 0))
@@ -325,46 +392,59 @@ def main():
                 "algorithmic_bytes_per_launch": d["algorithmic_bytes"] / max(1, d["launches"]),
                 "kernels": kern}
 
-    # ---- end to end through the C ABI with host buffers (rank-local share of the reads for correction)
+    # ---- end to end through the C ABI with host buffers: this rank's reads start in pinned host memory, every
+    # count piece and the correction copy them to the device inside the timed region, the corrected reads and
+    # the per-read stats come back to host memory
     e2e = None
     if not args.no_e2e:
         e2e_steps = min(args.steps, 2)
         def pinned_u8(nbytes):  # pinned host memory (what a pipelined host would stage batches in)
             p = L.bfcg_host_alloc_pinned(max(1, nbytes))
             if not p:
-                return np.empty(nbytes, dtype=np.uint8)
-            return np.ctypeslib.as_array(C.cast(p, api.u8p), shape=(max(1, nbytes),))[:nbytes]
-        h_seq, h_qual = pinned_u8(data.nb), pinned_u8(data.nb)
-        h_off = np.empty(n + 1, dtype=np.uint64)
-        L.bfcg_d2h(h_seq.ctypes.data, data.d_seq, data.nb)
-        L.bfcg_d2h(h_qual.ctypes.data, data.d_qual, data.nb)
-        L.bfcg_d2h(h_off.ctypes.data, data.d_off, 8 * (n + 1))
-        p_seq, p_qual = L.bfcg_host_alloc_pinned(max(1, nb_mine)), L.bfcg_host_alloc_pinned(max(1, nb_mine))
-        p_aux = np.empty(2 * (r1 - r0), dtype=np.uint32)
-        ws = np.ctypeslib.as_array(C.cast(p_seq, api.u8p), shape=(max(1, nb_mine),))
-        wq = np.ctypeslib.as_array(C.cast(p_qual, api.u8p), shape=(max(1, nb_mine),))
-        off_mine = (h_off[r0:r1 + 1] - h_off[r0]).copy()
-        hb_count = api.host_batch(h_seq, h_qual, h_off)
-        hb_work = api.host_batch(ws, wq, off_mine)
+                raise SystemExit("bench.py: pinned host allocation failed: " + L.bfcg_last_error().decode())
+            return p, np.ctypeslib.as_array(C.cast(p, api.u8p), shape=(max(1, nbytes),))[:nbytes]
+        p_hs, h_seq = pinned_u8(nb_mine)
+        p_hq, h_qual = pinned_u8(nb_mine)
+        p_ws, ws = pinned_u8(nb_mine)
+        p_wq, wq = pinned_u8(nb_mine)
+        L.bfcg_d2h(h_seq.ctypes.data, src_seq, nb_mine)
+        L.bfcg_d2h(h_qual.ctypes.data, src_qual, nb_mine)
+        h_off = np.arange(n_mine + 1, dtype=np.uint64) * np.uint64(RB)
+        p_aux = np.empty(2 * max(1, n_mine), dtype=np.uint32)
+        hb_work = api.host_batch(ws, wq, h_off)
+        hb_pieces, loc = [], 0
+        for p0, p1 in pieces:
+            m = p1 - p0
+            hb_pieces.append(api.host_batch(h_seq[loc * RB:(loc + m) * RB], h_qual[loc * RB:(loc + m) * RB], h_off[:m + 1]))
+            loc += m
         tot = 0.0
         for it in range(1 + e2e_steps):
-            ws[:nb_mine] = h_seq[byte0:byte0 + nb_mine]
-            wq[:nb_mine] = h_qual[byte0:byte0 + nb_mine]
+            ws[:] = h_seq
+            wq[:] = h_qual
             barrier()
             t0 = time.perf_counter()
-            eng.reset()
-            eng.count_batch(hb_count)
-            if r1 > r0:
+            if world == 1:
+                eng.reset()
+                eng.count_batch(hb_pieces[0])
                 eng.correct_batch(hb_work, p_aux.ctypes.data)
+            else:
+                be.reset()
+                for hb in hb_pieces:
+                    sc.count_piece(hb)
+                sc.gather()
+                if n_mine:
+                    be.correct_batch(hb_work, p_aux.ctypes.data)
             L.bfcg_sync()
             dt = max_over_ranks(time.perf_counter() - t0)
             if it > 0:
                 tot += dt
         e2e = {"value": n * e2e_steps / tot / 1e6, "unit": "Mreads/s",
-               "h2d_bytes_per_step": int(2 * data.nb + 2 * nb_mine + 8 * (r1 - r0 + 1)),
-               "d2h_bytes_per_step": int(2 * nb_mine + 8 * (r1 - r0)),
-               "steps": e2e_steps, "note": "host buffers -> bfcg_count_batch / bfcg_correct_batch -> host buffers; wall clock, max over ranks"}
-        L.bfcg_host_free_pinned(p_seq); L.bfcg_host_free_pinned(p_qual)
+               "h2d_bytes_per_step": int(4 * n * RB + 8 * (n + world)),
+               "d2h_bytes_per_step": int(2 * n * RB + 8 * n),
+               "steps": e2e_steps, "note": "whole job, all ranks: pinned host buffers -> bfcg_count_batch (N>1: bfcg_enum_records + "
+               "all-to-all + bfcg_count_records) / bfcg_correct_batch -> host buffers; wall clock, max over ranks"}
+        for p_ in (p_hs, p_hq, p_ws, p_wq):
+            L.bfcg_host_free_pinned(p_)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -386,9 +466,12 @@ def main():
                 "stats": {"kmers_per_step": st["n_kmers"] // args.steps, "f_pass": st["n_pass"] / max(1, st["n_kmers"]),
                           "pending_frac": st["n_pending"] / max(1, st["n_kmers"]),
                           "conflict_frac": st["n_conflict"] / max(1, st["n_kmers"]),
-                          "lookups_per_read": st["n_lookups"] / max(1, (r1 - r0) * args.steps), "redo": st["n_redo"]}}
+                          "lookups_per_read": st["n_lookups"] / max(1, n * args.steps), "redo": st["n_redo"]}}
         print(json.dumps(line))
-    eng.close()
+    if world == 1:
+        eng.close()
+    else:
+        be.close()
     if dist is not None:
         dist.destroy_process_group()
 

@@ -213,6 +213,42 @@ class CudaBackend:
         self.ch = None
         self.full_ch = full
 
+    def reset(self):
+        """Empty shards and table (between bench steps)."""
+        L, opt = self.L, self.opt
+        if self.full_ch and self.full_ch != self.ch:
+            L.bfc_ch_destroy(self.full_ch)
+        if self.ch:
+            L.bfc_ch_destroy(self.ch)
+        self.full_ch = self.ch = None
+        for name in ("bf", "bf_high"):
+            if getattr(self, name):
+                L.bfc_bf_destroy(getattr(self, name))
+                setattr(self, name, None)
+        self.full_bf_high = self._bf_high_view = None
+        self.bf = L.bfcg_bf_init_shard(opt.bf_shift, opt.n_hashes, self.world)
+        self.bf_high = L.bfcg_bf_init_shard(opt.bf_shift, opt.n_hashes, self.world) if self.filter_mode else None
+        self.ch = None if self.filter_mode else L.bfc_ch_init(opt.k, opt.l_pre)
+        if not self.bf or (self.filter_mode and not self.bf_high) or (not self.filter_mode and not self.ch):
+            raise self.api.BfcError("allocation failed: " + L.bfcg_last_error().decode())
+
+    def mode(self) -> int:
+        """bfc_ch_hist of the gathered table (reference correct.c:633)."""
+        cnt = (C.c_uint64 * 256)()
+        high = (C.c_uint64 * 64)()
+        return int(self.L.bfc_ch_hist(self.full_ch, cnt, high))
+
+    def correct_batch(self, batch, aux_ptr, mode=None):
+        """bfc_ec1 on every read of `batch` against the gathered table."""
+        torch.cuda.current_stream(self.device).synchronize()
+        self._check(self.L.bfcg_correct_batch(C.byref(self.opt), self.full_ch, self.mode() if mode is None else mode,
+                                              C.byref(batch), aux_ptr, C.byref(self.stats)), "bfcg_correct_batch")
+
+    def trim_batch(self, batch, keep_ptr, ts_ptr, te_ptr):
+        torch.cuda.current_stream(self.device).synchronize()
+        self._check(self.L.bfcg_trim_batch(C.byref(self.opt), self.bf_high_full(), C.byref(batch), keep_ptr, ts_ptr, te_ptr,
+                                           C.byref(self.stats)), "bfcg_trim_batch")
+
     def release_first_filter(self):
         """The first filter never outlives the count phase (reference count.c:155)."""
         if self.bf:
