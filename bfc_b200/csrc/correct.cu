@@ -658,8 +658,12 @@ __global__ void __launch_bounds__(EC_THREADS, 4) k_ec_search(EcParams P)
 					cb = dir ? comp_b(cur) : cur, cob = dir ? comp_b(ob) : ob;
 					if (cb < 4) {
 						if (memo_dir && z.clean >= k - 1 && cb == cob) { // the read's own k-mer: K5 fetched it
+							// Step over every decision-free base at once.  Each such step pushes one successor with the
+							// same penalty, which is popped right back (ties keep rising in ks_heapup), so only z moves.
+							// With up to 3 OTHER states alive the push + pop leaves their heap order untouched, except
+							// that two states of equal penalty swap places each time (ksort.h:125-146 worked through).
 							int run = 0;
-							if (heap_n == 0) { // a lone state: step over every decision-free base at once
+							if (heap_n <= 3) {
 								if (!dir) { const uint64_t w = ~bits64(plane(P, PL_J0), o + f); run = w ? __ffsll((long long)w) - 1 : 64; }
 								else { const uint64_t w = ~bits64(plane(P, PL_J1), o + f - 63); run = w ? __clzll((long long)w) : 64; }
 								if (bp >= 0) { // the rescued base is not the original one: stop in front of it
@@ -668,7 +672,12 @@ __global__ void __launch_bounds__(EC_THREADS, 4) k_ec_search(EcParams P)
 								}
 							}
 							if (run > 0) {
-								max_heap = max_heap > 1 ? max_heap : 1;
+								const int hs = heap_n + 1;
+								max_heap = max_heap > 255 ? 255 : max_heap > hs ? max_heap : hs;
+								if (heap_n == 2 && (run & 1)) {
+									const uint32_t k0 = heapk.get(0), k1 = heapk.get(1);
+									if (hk_pen(k0) == hk_pen(k1)) heapk.set(0, k1), heapk.set(1, k0);
+								}
 								z.i += run, z.clean += run;
 								extract_kmer(P, o, n, dir, z.i - 1, k - 1, -1, 0, z.x);
 								pc = PC_STEP; // again, at the new position
