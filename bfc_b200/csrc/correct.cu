@@ -440,11 +440,12 @@ __global__ void __launch_bounds__(EC_THREADS, 4) k_ec_search(EcParams P)
 			}
 			pc = PC_ALT_NEXT;
 		}
-		// ---------------- the step pipeline: stages in the order a search step runs through them, so that the
-		// lanes of a warp stay together; the loop repeats only after a memoised lookup, a jump, a finished
-		// path or a new job
+		// ---------------- the step pipeline: ONE pass per round through the stages in the order a search step
+		// runs through them, every lane executing the stages its state is due for, so the lanes of a warp stay
+		// together whatever each of them is doing.  A lane that ends the pass without a lookup request (its
+		// k-mer was memoised, a path ended, a new job started) just sits out this round's lookup.
 		bool yield = false;
-		do {
+		{
 			bool job_done = false;
 			if (pc == PC_AFTER_OWN) {
 				fixed = z.i > n; // correct.c:295 with end == n
@@ -647,7 +648,7 @@ __global__ void __launch_bounds__(EC_THREADS, 4) k_ec_search(EcParams P)
 					}
 				}
 			}
-			if (pc == PC_STEP) {
+			while (pc == PC_STEP) { // repeats only after a jump
 				has_c = z.i < n;
 				cand = 0, other_ext = 0, osf = 0, cb = cob = -1, ff = 0;
 				pc = PC_AFTER_OWN;
@@ -686,10 +687,10 @@ __global__ void __launch_bounds__(EC_THREADS, 4) k_ec_search(EcParams P)
 					}
 				}
 			}
-		} while (!yield);
+		}
 		if (pc == PC_EXIT) break;
-		// ---------------- convergent part: every lane that is still searching has exactly one lookup to do
-		{
+		// ---------------- the one lookup site of the loop
+		if (yield) {
 			uint64_t x[4] = { z.x[0], z.x[1], z.x[2], z.x[3] };
 			bfc_kmer_append(k, x, req_b);
 			res = tab_kmer_occ(P.tab, x);
