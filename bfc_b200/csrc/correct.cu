@@ -348,6 +348,9 @@ __device__ __forceinline__ uint32_t hk_pen(uint32_t key) { return key >> 12; }
 // the rest in the thread's global scratch.  Heaps hold a handful of states almost always.
 #define HK_SMEM 8
 #define EC_THREADS 128
+#ifndef EC_CTAS_PER_SM
+#define EC_CTAS_PER_SM 6   // 80 registers per thread (measured best: 5 CTAs x 96 regs and 8 x 64 are slower)
+#endif
 struct KeyHeap {
 	uint32_t *sm;   // &s_hk[0][threadIdx.x]
 	uint32_t *gl;   // global scratch of heap_cap keys
@@ -391,7 +394,7 @@ __device__ __forceinline__ int cand_weight(const EcParams &P, uint32_t c)
 	return P.w_ec * (int)(c >> 1 & 1) + P.w_ec_high * (int)(c >> 2 & 1) + P.w_absent * (int)(c >> 3 & 1) + P.w_absent_high * (int)(c >> 4 & 1);
 }
 
-__global__ void __launch_bounds__(EC_THREADS, 4) k_ec_search(EcParams P)
+__global__ void __launch_bounds__(EC_THREADS, EC_CTAS_PER_SM) k_ec_search(EcParams P)
 {
 	const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, n_slots = (int64_t)gridDim.x * blockDim.x;
 	EcState *const pool = P.pool + slot * P.heap_cap;
@@ -757,6 +760,25 @@ __global__ void __launch_bounds__(256) k_ec_merge(EcParams P)
 
 // ------------------------------------------------------------------ host side
 
+// window starts of a device batch: out[0] = number of entries, then (read index, byte offset) pairs, the last one = the end
+__global__ void k_ec_cuts(const uint64_t *off, int64_t n, uint64_t limit, uint64_t cap, unsigned long long *out)
+{
+	uint64_t m = 0;
+	for (int64_t r0 = 0; r0 < n && m + 1 < cap;) {
+		// largest r1 in (r0, n] with off[r1] - off[r0] <= limit, at least r0 + 1, at most r0 + 2^30
+		int64_t lo = r0 + 1, hi = n < r0 + (1LL << 30) ? n : r0 + (1LL << 30);
+		const uint64_t b0 = off[r0];
+		while (lo < hi) {
+			const int64_t mid = lo + (hi - lo + 1) / 2;
+			if (off[mid] - b0 <= limit) lo = mid; else hi = mid - 1;
+		}
+		out[1 + 2 * m] = (unsigned long long)r0, out[2 + 2 * m] = b0, ++m;
+		r0 = lo;
+		if (r0 >= n) { out[1 + 2 * m] = (unsigned long long)n, out[2 + 2 * m] = off[n], ++m; }
+	}
+	out[0] = m;
+}
+
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 static uint64_t batch_bytes_limit()
@@ -783,27 +805,42 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 	const bool host = batch->where == BFCG_HOST;
 	const int64_t n = batch->n_reads;
 
-	// read offsets on the host (needed to cut launches at read boundaries)
-	std::vector<uint64_t> off_copy;
-	const uint64_t *h_off = batch->off;
-	if (!host) {
-		off_copy.resize(n + 1);
-		BFCG_CUDA(cudaMemcpyAsync(off_copy.data(), batch->off, (n + 1) * 8, cudaMemcpyDeviceToHost, rt.stream));
-		BFCG_CUDA(cudaStreamSynchronize(rt.stream));
-		h_off = off_copy.data();
-	}
 	const uint64_t limit = batch_bytes_limit();
+	// windows of at most `limit` bytes / 2^30 reads, cut at read boundaries; for a device batch the cuts are
+	// found on the device (one thread, a binary search per window) so the offsets never travel to the host
+	std::vector<uint64_t> cut_r, cut_b; // read index / byte offset of every window start, plus the end
+	if (host) {
+		for (int64_t r0 = 0; r0 < n;) {
+			int64_t r1 = r0 + 1;
+			while (r1 < n && batch->off[r1 + 1] - batch->off[r0] <= limit && r1 - r0 < (1LL << 30)) ++r1;
+			cut_r.push_back(r0), cut_b.push_back(batch->off[r0]);
+			r0 = r1;
+		}
+		cut_r.push_back(n), cut_b.push_back(batch->off[n]);
+	} else {
+		const uint64_t cap = batch->n_bytes / limit * 2 + (uint64_t)(n >> 30) + 8;
+		unsigned long long *d_cuts = (unsigned long long*)bfcg_arena((2 * cap + 1) * 8);
+		if (!d_cuts) return BFCG_ERR_NOMEM;
+		k_ec_cuts<<<1, 1, 0, rt.stream>>>(batch->off, n, limit, cap, d_cuts);
+		BFCG_LAUNCH_CHECK();
+		std::vector<unsigned long long> h(2 * cap + 1);
+		BFCG_CUDA(cudaMemcpyAsync(h.data(), d_cuts, (2 * cap + 1) * 8, cudaMemcpyDeviceToHost, rt.stream));
+		BFCG_CUDA(cudaStreamSynchronize(rt.stream));
+		if (h[0] == 0 || h[0] > cap) return bfcg_fail(__func__, "window cut search failed", cudaSuccess);
+		for (uint64_t i = 0; i < h[0]; ++i) cut_r.push_back(h[1 + 2 * i]), cut_b.push_back(h[2 + 2 * i]);
+	}
 	const int threads = EC_THREADS;
-	const int64_t max_slots = (int64_t)rt.sm_count * 4 * threads; // persistent: what is resident at 4 CTAs per SM
+	int ctas = EC_CTAS_PER_SM;
+	{ const char *e = getenv("BFC_B200_EC_CTAS"); if (e && atoi(e) >= 1 && atoi(e) <= EC_CTAS_PER_SM) ctas = atoi(e); }
+	const int64_t max_slots = (int64_t)rt.sm_count * ctas * threads; // persistent threads: exactly what is resident
 	const int heap_cap = opt->max_heap + 6; // the search never holds more than max_heap + 4 states
 	const int edit_cap = edit_cap0();
 
 	BfcgTimer timer(stats);
-	for (int64_t r0 = 0; r0 < n;) {
-		int64_t r1 = r0 + 1;
-		while (r1 < n && h_off[r1 + 1] - h_off[r0] <= limit && r1 - r0 < (1LL << 30)) ++r1;
+	for (size_t w = 0; w + 1 < cut_r.size(); ++w) {
+		const int64_t r0 = (int64_t)cut_r[w], r1 = (int64_t)cut_r[w + 1];
 		const int64_t nr = r1 - r0;
-		const uint64_t b0 = h_off[r0], nb = h_off[r1] - b0;
+		const uint64_t b0 = cut_b[w], nb = cut_b[w + 1] - b0;
 		const uint64_t n_rec = enum_padded(nb);
 		const uint64_t pl_words = (n_rec + PL_PAD) / 64 + 4;
 		const int64_t slots = std::min<int64_t>(max_slots, (2 * nr + threads - 1) / threads * threads);
@@ -834,7 +871,7 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 		std::vector<uint64_t> rel;
 		if (host) {
 			rel.resize(nr + 1);
-			for (int64_t i = 0; i <= nr; ++i) rel[i] = h_off[r0 + i] - b0;
+			for (int64_t i = 0; i <= nr; ++i) rel[i] = batch->off[r0 + i] - b0;
 			BFCG_CUDA(cudaMemcpyAsync(a + o_seq, batch->seq + b0, nb, cudaMemcpyHostToDevice, rt.stream));
 			if (batch->qual) BFCG_CUDA(cudaMemcpyAsync(a + o_qual, batch->qual + b0, nb, cudaMemcpyHostToDevice, rt.stream));
 			BFCG_CUDA(cudaMemcpyAsync(a + o_off, rel.data(), (nr + 1) * 8, cudaMemcpyHostToDevice, rt.stream));
@@ -917,7 +954,6 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 			BFCG_CUDA(cudaMemcpyAsync(aux + 2 * r0, a + o_aux, nr * 8, cudaMemcpyDeviceToHost, rt.stream));
 			BFCG_CUDA(cudaStreamSynchronize(rt.stream));
 		}
-		r0 = r1;
 	}
 	timer.stop();
 	BFCG_CUDA(cudaStreamSynchronize(rt.stream));
