@@ -153,14 +153,15 @@ def lib():
 
 
 KERNEL_NAMES = ["count_probe", "count_resolve", "conflict_sort", "count_replay", "correct", "correct_redo", "trim",
-                "tab_rehash", "tab_hist", "tab_apply", "enum", "ec_lookup", "ec_setup", "ec_merge", "bucket"]
+                "tab_rehash", "tab_hist", "tab_apply", "enum", "ec_lookup", "ec_setup", "ec_merge", "bucket",
+                "count_part", "count_bounds", "enum_lin"]
 
 
 def kernel_times():
     """{kernel: (ms, launches)} of device time accumulated since the last call (timing must be on)."""
-    ms = (C.c_double * 16)()
-    n = (C.c_uint64 * 16)()
-    k = lib().bfcg_kernel_times(ms, n, 16)
+    ms = (C.c_double * 24)()
+    n = (C.c_uint64 * 24)()
+    k = lib().bfcg_kernel_times(ms, n, 24)
     return {KERNEL_NAMES[i]: (ms[i], int(n[i])) for i in range(min(k, len(KERNEL_NAMES)))}
 
 

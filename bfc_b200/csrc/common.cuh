@@ -36,13 +36,17 @@ struct BfcgRuntime {
 	struct Span { int id; cudaEvent_t a, b; };
 	std::vector<Span> spans;
 	std::vector<cudaEvent_t> ev_pool;
-	double kt_ms[16];
-	uint64_t kt_n[16];
+	double kt_ms[24];
+	uint64_t kt_n[24];
 	cudaEvent_t user_ev[8];
+	// host <-> device copies of host batches run on their own streams so that they overlap the kernels
+	cudaStream_t copy_in, copy_out;
+	cudaEvent_t ev_in[2], ev_free[2], ev_done[2], ev_out[2];
 };
 
 enum { KT_COUNT_PROBE = 0, KT_COUNT_RESOLVE, KT_COUNT_SORT, KT_COUNT_REPLAY, KT_CORRECT, KT_CORRECT_REDO,
-       KT_TRIM, KT_TAB_REHASH, KT_TAB_HIST, KT_TAB_APPLY, KT_ENUM, KT_EC_LOOKUP, KT_EC_SETUP, KT_EC_MERGE, KT_BUCKET, KT_N };
+       KT_TRIM, KT_TAB_REHASH, KT_TAB_HIST, KT_TAB_APPLY, KT_ENUM, KT_EC_LOOKUP, KT_EC_SETUP, KT_EC_MERGE, KT_BUCKET,
+       KT_COUNT_PART, KT_COUNT_BOUNDS, KT_ENUM_LIN, KT_N };
 
 int  bfcg_kt_begin(int id);   // records a start event on the stream when timing is on; returns a span index or -1
 void bfcg_kt_end(int idx);
@@ -95,10 +99,13 @@ struct BfcgTimer { // accumulates device time of the enclosed stream work into s
 struct bfc_ch_s {
 	int k, l_pre;             // l_pre after the adjustment of reference htab.c:24-26
 	int rbits;                // log2(slots per region); capacity = 2^(l_pre + rbits) slots
+	int rot;                  // region of sub-table s = s rotated right by rot inside l_pre bits (tab_region)
 	unsigned long long *slots;
 	unsigned long long *counters; // device, 8 words: [0] n_entries, [1] n_deferred, [2] rehash failures
 	unsigned long long *deferred; // device: 2 words per deferred insert (y0 | is_high<<63, y1)
 	uint64_t def_cap;
+	uint64_t prev_new;        // distinct keys added by the previous count window (growth estimate of the next one)
+	int have_prev;
 };
 
 // ------------------------------------------------------------------ device views
@@ -114,7 +121,7 @@ struct TabView {
 	unsigned long long *counters;
 	unsigned long long *deferred;
 	unsigned long long def_cap;
-	int k, l_pre, rbits;
+	int k, l_pre, rbits, rot;
 };
 
 static inline BloomView bloom_view(const bfc_bf_t *b)
@@ -128,14 +135,22 @@ static inline TabView tab_view(const bfc_ch_s *c)
 {
 	TabView v;
 	v.slots = c->slots, v.counters = c->counters, v.deferred = c->deferred, v.def_cap = c->def_cap;
-	v.k = c->k, v.l_pre = c->l_pre, v.rbits = c->rbits;
+	v.k = c->k, v.l_pre = c->l_pre, v.rbits = c->rbits, v.rot = c->rot;
 	return v;
 }
 
 // table growth policy (htab.cu): make room for `extra` more distinct keys at load <= 1/2
 int bfcg_tab_reserve(bfc_ch_s *ch, uint64_t extra);
+// place the sub-tables so that k-mers of neighbouring Bloom blocks (2^x blocks) sit in neighbouring regions
+int bfcg_tab_align_to_filter(bfc_ch_s *ch, int x);
 // re-apply inserts that found their region full (after growing); htab.cu
 int bfcg_tab_drain_deferred(bfc_ch_s *ch);
+
+// the partitioned count path (count_part.cu); count.cu dispatches to it when it applies
+bool bfcg_count_part_usable(const bfc_opt_t *opt, const bfc_bf_t *bf, int owner_bits);
+int bfcg_count_part_batch(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, bfc_ch_t *ch, const bfcg_batch_t *batch, bfcg_stats_t *stats);
+int bfcg_count_part_records(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, bfc_ch_t *ch, uint64_t n_rec,
+                            const uint64_t *d_y0, const uint64_t *d_y1, int owner_bits, bfcg_stats_t *stats);
 
 #ifdef __CUDACC__
 
@@ -146,6 +161,14 @@ __device__ __forceinline__ int base_code(uint8_t ch)
 {
 	const uint32_t u = ch & 0xDFu; // fold case
 	return u == 'A' ? 0 : u == 'C' ? 1 : u == 'G' ? 2 : u == 'T' ? 3 : 4;
+}
+
+// the 64-bit Bloom hash of a record (y0, y1): inverse of the last two lines of
+// bfc_kmer_hash (kmer.h:85-86): h1 = y1, h0 = y0 - y1
+__device__ __forceinline__ uint64_t hash_from_y(int k, uint64_t y0, uint64_t y1)
+{
+	const uint64_t m = (1ULL << k) - 1, h0 = (y0 - y1) & m;
+	return ((h0 ^ y1) << k) | y0;
 }
 
 // ------------------------------------------------------------------ Bloom probes
@@ -218,6 +241,18 @@ __device__ __forceinline__ void tab_subkey(int k, int l_pre, uint64_t y0, uint64
 	}
 }
 
+// Where sub-table `sub` lives: its index rotated right by t.rot inside l_pre bits.  With rot = (number of Bloom
+// block-index bits that are also sub-table bits) the low y0 bits a count partition fixes become the TOP bits of
+// the region index, so one partition's upserts fall into one contiguous stretch of the table (count_part.cu).
+__host__ __device__ __forceinline__ uint32_t tab_region(int l_pre, int rot, uint32_t sub)
+{
+	return rot ? ((sub >> rot) | (sub << (l_pre - rot))) & ((1u << l_pre) - 1) : sub;
+}
+__host__ __device__ __forceinline__ uint32_t tab_region_inv(int l_pre, int rot, uint32_t reg)
+{
+	return rot ? ((reg << rot) | (reg >> (l_pre - rot))) & ((1u << l_pre) - 1) : reg;
+}
+
 __device__ __forceinline__ uint64_t tab_mix(uint64_t key)
 {
 	key ^= key >> 29;
@@ -237,7 +272,7 @@ __device__ __forceinline__ int tab_upsert(const TabView &t, uint64_t y0, uint64_
 	uint32_t sub; uint64_t key;
 	tab_subkey(t.k, t.l_pre, y0, y1, sub, key);
 	const uint64_t R = 1ULL << t.rbits;
-	unsigned long long *reg = t.slots + ((uint64_t)sub << t.rbits);
+	unsigned long long *reg = t.slots + ((uint64_t)tab_region(t.l_pre, t.rot, sub) << t.rbits);
 	uint64_t h = tab_mix(key) & (R - 1) & ~3ULL;
 	const unsigned long long fresh = key << 14 | (unsigned long long)(is_high ? 1 : 0) << 8 | 1ULL;
 	for (uint64_t n = 0; n < R; n += 4, h = (h + 4) & (R - 1)) {
@@ -278,7 +313,7 @@ __device__ __forceinline__ int tab_upsert(const TabView &t, uint64_t y0, uint64_
 __device__ __forceinline__ bool tab_put_raw(const TabView &t, uint32_t sub, unsigned long long slot)
 {
 	const uint64_t R = 1ULL << t.rbits;
-	unsigned long long *reg = t.slots + ((uint64_t)sub << t.rbits);
+	unsigned long long *reg = t.slots + ((uint64_t)tab_region(t.l_pre, t.rot, sub) << t.rbits);
 	uint64_t h = tab_mix(slot >> 14) & (R - 1) & ~3ULL;
 	for (uint64_t n = 0; n < R; ++n) {
 		const uint64_t i = (h + n) & (R - 1);
@@ -293,7 +328,7 @@ __device__ __forceinline__ int tab_get(const TabView &t, uint64_t y0, uint64_t y
 	uint32_t sub; uint64_t key;
 	tab_subkey(t.k, t.l_pre, y0, y1, sub, key);
 	const uint64_t R = 1ULL << t.rbits;
-	const unsigned long long *reg = t.slots + ((uint64_t)sub << t.rbits);
+	const unsigned long long *reg = t.slots + ((uint64_t)tab_region(t.l_pre, t.rot, sub) << t.rbits);
 	uint64_t h = tab_mix(key) & (R - 1) & ~3ULL;
 	for (uint64_t n = 0; n < R; n += 4, h = (h + 4) & (R - 1)) {
 		const ulonglong2 v01 = __ldg((const ulonglong2*)(reg + h));

@@ -836,53 +836,80 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 	const int heap_cap = opt->max_heap + 6; // the search never holds more than max_heap + 4 states
 	const int edit_cap = edit_cap0();
 
-	BfcgTimer timer(stats);
+	// one arena for every window: two sets of in/out buffers for host batches (window w+1 is copied in and
+	// window w-1 copied out, on their own streams, while window w is searched) + one set of scratch
+	uint64_t nb_max = 0;
+	int64_t nr_max = 0;
 	for (size_t w = 0; w + 1 < cut_r.size(); ++w) {
+		nb_max = std::max<uint64_t>(nb_max, cut_b[w + 1] - cut_b[w]);
+		nr_max = std::max<int64_t>(nr_max, (int64_t)(cut_r[w + 1] - cut_r[w]));
+	}
+	const uint64_t n_rec_max = enum_padded(nb_max), pl_words_max = (n_rec_max + PL_PAD) / 64 + 4;
+	const int64_t slots_max = std::min<int64_t>(max_slots, (2 * nr_max + threads - 1) / threads * threads);
+	size_t tot = 0, o_seq[2] = {0, 0}, o_qual[2] = {0, 0}, o_off[2] = {0, 0}, o_aux[2] = {0, 0};
+	size_t o_pl, o_fl, o_y0, o_y1, o_desc, o_jobs, o_res, o_pool, o_heapk, o_edits, o_ovf, o_ctr;
+	if (host)
+		for (int b = 0; b < 2; ++b) {
+			o_seq[b] = tot; tot = align_up(tot + nb_max, 256);
+			o_qual[b] = tot; tot = align_up(tot + nb_max, 256);
+			o_off[b] = tot; tot = align_up(tot + (nr_max + 1) * 8, 256);
+			o_aux[b] = tot; tot = align_up(tot + nr_max * 8, 256);
+		}
+	o_pl = tot; tot = align_up(tot + (size_t)PL_N * pl_words_max * 8, 256);
+	o_fl = tot; tot = align_up(tot + n_rec_max * 2, 256);
+	o_y0 = tot; tot = align_up(tot + n_rec_max * 8, 256);
+	o_y1 = tot; tot = align_up(tot + n_rec_max * 8, 256);
+	o_desc = tot; tot = align_up(tot + nr_max * sizeof(ReadDesc), 256);
+	o_jobs = tot; tot = align_up(tot + 2 * nr_max * sizeof(int4), 256);
+	o_res = tot; tot = align_up(tot + 2 * nr_max * sizeof(int2), 256);
+	o_pool = tot; tot = align_up(tot + (size_t)slots_max * heap_cap * sizeof(EcState), 256);
+	o_heapk = tot; tot = align_up(tot + (size_t)slots_max * heap_cap * 4, 256);
+	o_edits = tot; tot = align_up(tot + (size_t)slots_max * edit_cap * sizeof(uint2), 256);
+	o_ovf = tot; tot = align_up(tot + 2 * nr_max * 4, 256);
+	o_ctr = tot; tot += 256;
+	uint8_t *a = (uint8_t*)bfcg_arena(tot);
+	if (!a) return BFCG_ERR_NOMEM;
+
+	const size_t n_win = cut_r.size() - 1;
+	auto issue_copy_in = [&](size_t w) -> cudaError_t {
+		const int64_t r0 = (int64_t)cut_r[w], nr = (int64_t)cut_r[w + 1] - r0;
+		const uint64_t b0 = cut_b[w], nb = cut_b[w + 1] - b0;
+		const int b = (int)(w & 1);
+		cudaError_t ce;
+		if (w >= 2 && (ce = cudaStreamWaitEvent(rt.copy_in, rt.ev_out[b], 0)) != cudaSuccess) return ce; // buffer b was read out
+		if ((ce = cudaMemcpyAsync(a + o_seq[b], batch->seq + b0, nb, cudaMemcpyHostToDevice, rt.copy_in)) != cudaSuccess) return ce;
+		if (batch->qual && (ce = cudaMemcpyAsync(a + o_qual[b], batch->qual + b0, nb, cudaMemcpyHostToDevice, rt.copy_in)) != cudaSuccess) return ce;
+		if ((ce = cudaMemcpyAsync(a + o_off[b], batch->off + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, rt.copy_in)) != cudaSuccess) return ce;
+		return cudaEventRecord(rt.ev_in[b], rt.copy_in);
+	};
+
+	BfcgTimer timer(stats);
+	if (host) {
+		BFCG_CUDA(cudaStreamSynchronize(rt.stream)); // earlier work on the engine's stream may still use the arena
+		BFCG_CUDA(issue_copy_in(0));
+	}
+	int rc = BFCG_OK;
+	for (size_t w = 0; w < n_win; ++w) {
 		const int64_t r0 = (int64_t)cut_r[w], r1 = (int64_t)cut_r[w + 1];
 		const int64_t nr = r1 - r0;
 		const uint64_t b0 = cut_b[w], nb = cut_b[w + 1] - b0;
 		const uint64_t n_rec = enum_padded(nb);
 		const uint64_t pl_words = (n_rec + PL_PAD) / 64 + 4;
 		const int64_t slots = std::min<int64_t>(max_slots, (2 * nr + threads - 1) / threads * threads);
-		size_t tot = 0, o_seq = 0, o_qual = 0, o_off = 0, o_aux = 0, o_pl, o_fl, o_y0, o_y1, o_desc, o_jobs, o_res, o_pool, o_heapk, o_edits, o_ovf, o_ctr;
-		if (host) {
-			o_seq = tot; tot = align_up(tot + nb, 256);
-			o_qual = tot; tot = align_up(tot + nb, 256);
-			o_off = tot; tot = align_up(tot + (nr + 1) * 8, 256);
-			o_aux = tot; tot = align_up(tot + nr * 8, 256);
-		}
-		o_pl = tot; tot = align_up(tot + (size_t)PL_N * pl_words * 8, 256);
-		o_fl = tot; tot = align_up(tot + n_rec * 2, 256);
-		o_y0 = tot; tot = align_up(tot + n_rec * 8, 256);
-		o_y1 = tot; tot = align_up(tot + n_rec * 8, 256);
-		o_desc = tot; tot = align_up(tot + nr * sizeof(ReadDesc), 256);
-		o_jobs = tot; tot = align_up(tot + 2 * nr * sizeof(int4), 256);
-		o_res = tot; tot = align_up(tot + 2 * nr * sizeof(int2), 256);
-		o_pool = tot; tot = align_up(tot + (size_t)slots * heap_cap * sizeof(EcState), 256);
-		o_heapk = tot; tot = align_up(tot + (size_t)slots * heap_cap * 4, 256);
-		o_edits = tot; tot = align_up(tot + (size_t)slots * edit_cap * sizeof(uint2), 256);
-		o_ovf = tot; tot = align_up(tot + 2 * nr * 4, 256);
-		o_ctr = tot; tot += 256;
-		uint8_t *a = (uint8_t*)bfcg_arena(tot);
-		if (!a) return BFCG_ERR_NOMEM;
+		const int ib = (int)(w & 1);
 
 		EcParams P;
 		memset(&P, 0, sizeof(P));
-		std::vector<uint64_t> rel;
-		if (host) {
-			rel.resize(nr + 1);
-			for (int64_t i = 0; i <= nr; ++i) rel[i] = batch->off[r0 + i] - b0;
-			BFCG_CUDA(cudaMemcpyAsync(a + o_seq, batch->seq + b0, nb, cudaMemcpyHostToDevice, rt.stream));
-			if (batch->qual) BFCG_CUDA(cudaMemcpyAsync(a + o_qual, batch->qual + b0, nb, cudaMemcpyHostToDevice, rt.stream));
-			BFCG_CUDA(cudaMemcpyAsync(a + o_off, rel.data(), (nr + 1) * 8, cudaMemcpyHostToDevice, rt.stream));
-			P.off = (const uint64_t*)(a + o_off), P.seq = a + o_seq, P.qual = batch->qual ? a + o_qual : 0;
-			P.aux = (uint32_t*)(a + o_aux);
-			P.base0 = 0;
-		} else { // device batch: offsets are absolute, the window starts at b0
+		if (host) { // offsets stay absolute (as in a device batch): the staged window starts at stream offset b0
+			const cudaError_t ce = cudaStreamWaitEvent(rt.stream, rt.ev_in[ib], 0);
+			if (ce != cudaSuccess) { rc = bfcg_fail(__func__, "staging copy", ce); break; }
+			P.off = (const uint64_t*)(a + o_off[ib]), P.seq = a + o_seq[ib] - b0, P.qual = batch->qual ? a + o_qual[ib] - b0 : 0;
+			P.aux = (uint32_t*)(a + o_aux[ib]);
+		} else {
 			P.off = batch->off + r0, P.seq = batch->seq, P.qual = batch->qual;
 			P.aux = aux + 2 * r0;
-			P.base0 = b0;
 		}
+		P.base0 = b0;
 		P.pl = (const uint64_t*)(a + o_pl), P.pl_words = pl_words;
 		P.fl = (const uint16_t*)(a + o_fl);
 		P.desc = (ReadDesc*)(a + o_desc), P.jobs = (int4*)(a + o_jobs), P.res = (int2*)(a + o_res);
@@ -897,8 +924,8 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 		BFCG_CUDA(cudaMemsetAsync(P.ctr, 0, 64, rt.stream));
 		BFCG_CUDA(cudaMemsetAsync(a + o_pl, 0, (size_t)PL_N * pl_words * 8, rt.stream));
 
-		const uint8_t *w_seq = host ? a + o_seq : batch->seq + b0;
-		const uint8_t *w_qual = host ? (batch->qual ? a + o_qual : 0) : (batch->qual ? batch->qual + b0 : 0);
+		const uint8_t *w_seq = host ? a + o_seq[ib] : batch->seq + b0;
+		const uint8_t *w_qual = host ? (batch->qual ? a + o_qual[ib] : 0) : (batch->qual ? batch->qual + b0 : 0);
 		EnumParams ep;
 		memset(&ep, 0, sizeof(ep));
 		ep.seq = w_seq, ep.qual = 0; // the quality flag of a record is not used here
@@ -920,6 +947,10 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 		++rt.n_launches;
 		{ KTime kt(KT_CORRECT); k_ec_search<<<(unsigned)(slots / threads), threads, 0, rt.stream>>>(P); }
 		BFCG_LAUNCH_CHECK();
+		if (host && w + 1 < n_win) { // the next window travels while this one is searched (issued after the launches:
+			const cudaError_t ce = issue_copy_in(w + 1); // a copy from pageable memory blocks the host, not the GPU)
+			if (ce != cudaSuccess) { rc = bfcg_fail(__func__, "staging copy", ce); break; }
+		}
 		unsigned long long c[2];
 		BFCG_CUDA(cudaMemcpyAsync(c, P.ctr, sizeof(c), cudaMemcpyDeviceToHost, rt.stream));
 		BFCG_CUDA(cudaStreamSynchronize(rt.stream));
@@ -948,13 +979,18 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 		{ KTime kt(KT_EC_MERGE); k_ec_merge<<<(unsigned)std::min<int64_t>((nr + 7) / 8, (int64_t)rt.sm_count * 16), 256, 0, rt.stream>>>(P); }
 		BFCG_LAUNCH_CHECK();
 		if (stats) stats->n_lookups += c[1];
-		if (host) {
-			BFCG_CUDA(cudaMemcpyAsync(batch->seq + b0, a + o_seq, nb, cudaMemcpyDeviceToHost, rt.stream));
-			if (batch->qual) BFCG_CUDA(cudaMemcpyAsync(batch->qual + b0, a + o_qual, nb, cudaMemcpyDeviceToHost, rt.stream));
-			BFCG_CUDA(cudaMemcpyAsync(aux + 2 * r0, a + o_aux, nr * 8, cudaMemcpyDeviceToHost, rt.stream));
-			BFCG_CUDA(cudaStreamSynchronize(rt.stream));
+		if (host) { // the corrected window leaves on the copy-out stream while the next one is searched
+			cudaError_t ce = cudaEventRecord(rt.ev_done[ib], rt.stream);
+			if (ce == cudaSuccess) ce = cudaStreamWaitEvent(rt.copy_out, rt.ev_done[ib], 0);
+			if (ce == cudaSuccess) ce = cudaMemcpyAsync(batch->seq + b0, a + o_seq[ib], nb, cudaMemcpyDeviceToHost, rt.copy_out);
+			if (ce == cudaSuccess && batch->qual) ce = cudaMemcpyAsync(batch->qual + b0, a + o_qual[ib], nb, cudaMemcpyDeviceToHost, rt.copy_out);
+			if (ce == cudaSuccess) ce = cudaMemcpyAsync(aux + 2 * r0, a + o_aux[ib], nr * 8, cudaMemcpyDeviceToHost, rt.copy_out);
+			if (ce == cudaSuccess) ce = cudaEventRecord(rt.ev_out[ib], rt.copy_out);
+			if (ce != cudaSuccess) { rc = bfcg_fail(__func__, "copy out", ce); break; }
 		}
 	}
+	if (host) { cudaStreamSynchronize(rt.copy_in); cudaStreamSynchronize(rt.copy_out); }
+	if (rc != BFCG_OK) { cudaStreamSynchronize(rt.stream); return rc; }
 	timer.stop();
 	BFCG_CUDA(cudaStreamSynchronize(rt.stream));
 	return BFCG_OK;

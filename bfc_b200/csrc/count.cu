@@ -41,13 +41,6 @@ struct CountParams {
 	int linear;                  // records are in stream order (received from other ranks); else k_enum's blocked order
 };
 
-__device__ __forceinline__ uint64_t hash_from_y(int k, uint64_t y0, uint64_t y1)
-{
-	// inverse of the last two lines of bfc_kmer_hash (kmer.h:85-86): h1 = y1, h0 = y0 - y1
-	const uint64_t m = (1ULL << k) - 1, h0 = (y0 - y1) & m;
-	return ((h0 ^ y1) << k) | y0;
-}
-
 __global__ void __launch_bounds__(256) k_count_probe(CountParams p)
 {
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -266,6 +259,7 @@ extern "C" int bfcg_count_batch(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf
 	if (!batch || !count_args_ok(opt, bf, bf_high, ch))
 		return bfcg_fail(__func__, "invalid arguments", cudaSuccess), BFCG_ERR_ARG;
 	if (batch->n_bytes == 0) return BFCG_OK;
+	if (bfcg_count_part_usable(opt, bf, 0)) return bfcg_count_part_batch(opt, bf, bf_high, ch, batch, stats);
 
 	const uint64_t sub = sub_batch_positions(opt);
 	const uint64_t halo = opt->k - 1;
@@ -483,6 +477,7 @@ extern "C" int bfcg_count_records(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *
 	if (!count_args_ok(opt, bf, bf_high, ch) || owner_bits < 0 || bf->n_shift - BFC_BLK_SHIFT < owner_bits || (n_rec && (!d_y0 || !d_y1)))
 		return bfcg_fail(__func__, "invalid arguments", cudaSuccess), BFCG_ERR_ARG;
 	if (n_rec == 0) return BFCG_OK;
+	if (bfcg_count_part_usable(opt, bf, owner_bits)) return bfcg_count_part_records(opt, bf, bf_high, ch, n_rec, d_y0, d_y1, owner_bits, stats);
 	const uint64_t sub = std::min<uint64_t>(sub_batch_positions(opt), 1ULL << 31);
 	const uint64_t rec_max = std::min<uint64_t>(sub, n_rec);
 	CountScratch sc;

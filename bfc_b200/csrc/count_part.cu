@@ -1,0 +1,450 @@
+// count_part.cu -- the count phase as a PARTITIONED pass: the Bloom -> table cascade of
+// bfc_kmer_insert (reference count.c:54-70) over the k-mers of worker_count (count.c:72-89)
+// with the sequential (-t1) semantics, arranged so that every random access lands in
+// shared memory or in a small window of L2 instead of HBM.
+//
+// Every ordering constraint of the cascade is local to one 64-byte Bloom block
+// (bbf.c:35-44: occurrence t passes iff occurrences < t of the same block set all its
+// bits).  A window of up to 2^30 stream positions is therefore processed as
+//
+//   K0' k_enum_lin     canonical k-mer hash of every stream position, from bit planes of
+//                      the window staged in shared memory (no rolling state, no warm-up):
+//                      16-byte records (y0 | is_high << 63, y1) in STREAM order
+//   K1' radix sort     stable partition of the records by the top bits of their Bloom
+//                      block index (cub onesweep over bits [10, x) of y0): partition =
+//                      1024 consecutive blocks = 64 KB of the filter
+//   K2' k_part_bounds  first / last record of every partition
+//   K3' k_count_part   one CTA per partition: the 64 KB slice of the filter is loaded into
+//                      shared memory, the partition's records are replayed in stream order
+//                      256 at a time -- records whose bits are all set pass (order-free);
+//                      the others take turns per block, earliest first (shared-memory
+//                      atomicMin claim), each applying the reference's test-then-set -- and
+//                      the slice is written back once.  Passing occurrences upsert the
+//                      table (or set bf_high in trim mode) straight from the CTA.
+//
+// HBM traffic per window: records 16 B written + 104 B through the sort + 16 B read, the
+// filter once in and once out (sequential), the table through L2.  Requires the block
+// index to be a bit field of y0 (n_shift - 9 <= k); otherwise count.cu's probe/resolve/
+// replay path (random access, same results) is used.
+#include "common.cuh"
+#include <cub/device/device_radix_sort.cuh>
+#include <algorithm>
+#include <functional>
+
+#define EL_THREADS 256
+#define EL_ITERS   32
+#define EL_SEG     (EL_THREADS * EL_ITERS)       // stream positions per CTA
+#define EL_LEAD    64                            // plane bits in front of the segment (>= k - 1)
+#define EL_WORDS   ((EL_SEG + EL_LEAD) / 32 + 2)
+
+#define CP_SLOG2   10                            // log2(Bloom blocks per partition): 64 KB slices
+#define CP_BLOCKS  (1 << CP_SLOG2)
+#define CP_THREADS 256
+#define CP_BLK_BYTES 64                           // one Bloom block (bbf.h: 512 bits)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline uint64_t el_padded(uint64_t n_positions) { return (n_positions + EL_SEG - 1) / EL_SEG * EL_SEG; }
+
+// ------------------------------------------------------------------ K0': enumeration in stream order
+
+struct EnumLinParams {
+	const uint8_t *seq, *qual;   // stream window (device); qual may be 0 (= every base has high quality)
+	uint64_t len;                // bytes in the window
+	uint64_t emit_from;          // records are emitted for window positions >= emit_from
+	int k, q;
+	unsigned long long *rec_y0, *rec_y1;
+};
+
+// 64 plane bits starting at bit index `bit`
+__device__ __forceinline__ uint64_t win64(const uint32_t *pl, uint32_t bit)
+{
+	const uint32_t w = bit >> 5, r = bit & 31;
+	const uint32_t a = pl[w], b = pl[w + 1], c = pl[w + 2];
+	return (uint64_t)__funnelshift_r(b, c, r) << 32 | __funnelshift_r(a, b, r);
+}
+
+// What worker_count does per base (count.c:76-88): map the character (bseq.c:9-26), restart on
+// a non-ACGT one, and once k bases are in, hash the canonical k-mer (kmer.h:79-88) with
+// is_high = all k bases have Q >= q.  Instead of rolling, the k-mer ending at a position is cut
+// out of the base bit planes of the segment (the same construction as correct.cu's extract_kmer).
+__global__ void __launch_bounds__(EL_THREADS) k_enum_lin(EnumLinParams p)
+{
+	__shared__ uint32_t s_pl[4][EL_WORDS]; // B0, B1 (base code bits), NB (not ACGT / outside), Q (Q >= q)
+	const int64_t seg0 = (int64_t)p.emit_from + (int64_t)blockIdx.x * EL_SEG;
+	const unsigned lane = threadIdx.x & 31;
+	if (threadIdx.x < 8) s_pl[threadIdx.x & 3][EL_WORDS - 1 - (threadIdx.x >> 2)] = 0;
+	for (int i = threadIdx.x; i < EL_SEG + EL_LEAD; i += EL_THREADS) { // whole warps in or out
+		const int64_t pos = seg0 - EL_LEAD + i;
+		uint32_t c = 4, q = 0;
+		if (pos >= 0 && (uint64_t)pos < p.len) {
+			c = base_code(__ldg(p.seq + pos));
+			q = c < 4 && (p.qual == 0 || (int)__ldg(p.qual + pos) - 33 >= p.q);
+		}
+		const uint32_t b0 = __ballot_sync(0xffffffffu, c & 1), b1 = __ballot_sync(0xffffffffu, c & 2);
+		const uint32_t nb = __ballot_sync(0xffffffffu, c > 3), bq = __ballot_sync(0xffffffffu, q);
+		if (lane == 0) s_pl[0][i >> 5] = b0, s_pl[1][i >> 5] = b1, s_pl[2][i >> 5] = nb, s_pl[3][i >> 5] = bq;
+	}
+	__syncthreads();
+	const int k = p.k;
+	const uint64_t kmask = (1ULL << k) - 1;
+	unsigned long long *o0 = p.rec_y0 + (uint64_t)blockIdx.x * EL_SEG + threadIdx.x;
+	unsigned long long *o1 = p.rec_y1 + (uint64_t)blockIdx.x * EL_SEG + threadIdx.x;
+#pragma unroll 4
+	for (int j = 0; j < EL_ITERS; ++j) {
+		const uint32_t pp = (uint32_t)(j * EL_THREADS + threadIdx.x);   // position inside the segment
+		const uint32_t bit = pp + EL_LEAD - (uint32_t)(k - 1);          // oldest base of the k-mer ending at pp
+		// a position where no k-mer ends still gets a record (y1 = ~0); its y0 is spread so that the
+		// partitions stay balanced
+		uint64_t y[2] = { ((uint64_t)(seg0 + pp) * 0x9E3779B97F4A7C15ULL) >> 1, ~0ULL };
+		if ((win64(s_pl[2], bit) & kmask) == 0) {
+			const uint64_t w0 = win64(s_pl[0], bit) & kmask, w1 = win64(s_pl[1], bit) & kmask;
+			const uint64_t qw = win64(s_pl[3], bit) & kmask;
+			const uint64_t x[4] = { __brevll(w0) >> (64 - k), __brevll(w1) >> (64 - k), ~w0 & kmask, ~w1 & kmask };
+			bfc_kmer_hash(k, x, y);
+			y[0] |= (unsigned long long)(qw == kmask) << 63;
+		}
+		o0[j * EL_THREADS] = y[0];
+		o1[j * EL_THREADS] = y[1];
+	}
+}
+
+// ------------------------------------------------------------------ K2': partition bounds
+
+__global__ void __launch_bounds__(256) k_part_bounds(const unsigned long long *y0, uint64_t n, uint32_t pmask, uint32_t *start, uint32_t *end)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t p = (uint32_t)(__ldg(y0 + i) >> CP_SLOG2) & pmask;
+	if (i == 0 || ((uint32_t)(__ldg(y0 + i - 1) >> CP_SLOG2) & pmask) != p) start[p] = (uint32_t)i;
+	if (i + 1 == n || ((uint32_t)(__ldg(y0 + i + 1) >> CP_SLOG2) & pmask) != p) end[p] = (uint32_t)(i + 1);
+}
+
+// ------------------------------------------------------------------ K3': one CTA per partition
+
+struct PartParams {
+	const unsigned long long *y0, *y1; // records, stably partitioned
+	const uint32_t *start, *end;       // record range per partition; 0 = a single partition [0, n_rec)
+	uint64_t n_rec;
+	uint32_t blocks_per_part;          // Bloom blocks per partition (power of two, <= CP_BLOCKS)
+	int k;
+	BloomView bf, bf_high;             // bf_high.w == 0 in normal mode
+	TabView tab;                       // tab.slots == 0 in trim mode
+	unsigned long long *ctr;           // [1] n_kmers [2] n_pass [3] occurrences that had to wait for an earlier one
+};
+
+__global__ void __launch_bounds__(CP_THREADS, 3) k_count_part(PartParams p)
+{
+	extern __shared__ __align__(16) uint32_t s_w[];  // the partition's slice of the filter: blocks_per_part x 16 words
+	__shared__ uint32_t s_claim[CP_BLOCKS];          // per block: lowest thread with a pending occurrence this round
+	const uint32_t part = blockIdx.x, nb = p.blocks_per_part, tid = threadIdx.x;
+	uint64_t beg = 0, end = p.n_rec;
+	if (p.start) beg = __ldg(p.start + part), end = __ldg(p.end + part);
+	if (beg >= end) return; // nothing for this slice in this window
+	uint4 *const g4 = (uint4*)(p.bf.w + ((uint64_t)part * nb << 4));
+	uint4 *const s4 = (uint4*)s_w;
+	for (uint32_t i = tid; i < nb * 4; i += CP_THREADS) s4[i] = __ldcs(g4 + i);
+	for (uint32_t i = tid; i < nb; i += CP_THREADS) s_claim[i] = ~0u;
+	const int H = p.bf.n_hashes;
+	unsigned long long n_k = 0, n_pass = 0, n_new = 0, n_wait = 0;
+	unsigned long long y0f = 0, y1 = ~0ULL;
+	if (beg + tid < end) y1 = __ldg(p.y1 + beg + tid), y0f = __ldg(p.y0 + beg + tid);
+	__syncthreads();
+	for (uint64_t base = beg; base < end; base += CP_THREADS) {
+		const unsigned long long c0f = y0f, c1 = y1;
+		{ // next round's records are in flight while this round is replayed
+			const uint64_t ni = base + CP_THREADS + tid;
+			y1 = ~0ULL;
+			if (ni < end) y1 = __ldg(p.y1 + ni), y0f = __ldg(p.y0 + ni);
+		}
+		const bool valid = c1 != ~0ULL;
+		const uint64_t c0 = c0f & ~(1ULL << 63);
+		bool pass = false, pend = false, waited = false;
+		BloomProbe pr;
+		pr.blk = 0, pr.h1 = pr.h2 = 0;
+		uint32_t lb = 0;
+		if (valid) {
+			pr = bloom_locate(hash_from_y(p.k, c0, c1), p.bf.n_shift);
+			lb = (uint32_t)pr.blk & (nb - 1);
+			// all bits already set: passes whatever the order, and writes nothing
+			pass = bloom_count_set<false>(s_w + (lb << 4), pr, H) == H;
+			pend = !pass;
+		}
+		// the others take turns per block in stream order (= thread order inside the round)
+		while (__syncthreads_or(pend)) {
+			if (pend) atomicMin(&s_claim[lb], tid);
+			__syncthreads();
+			const bool win = pend && s_claim[lb] == tid;
+			if (win) { // reference bbf.c:35-42: test-then-set each probe; the only writer of this block now
+				uint32_t *w = s_w + (lb << 4);
+				int z = pr.h1, done = 0, cnt = 0;
+				while (done < H) {
+					if (z >= 8) {
+						const uint32_t bit = 1u << (z & 31), v = w[z >> 5];
+						cnt += (v & bit) != 0;
+						w[z >> 5] = v | bit;
+						++done;
+					}
+					z = (z + pr.h2) & BFC_BLK_MASK;
+				}
+				pass = cnt == H; // reference count.c:60
+				pend = false;
+			} else if (pend) waited = true;
+			__syncthreads();
+			if (win) s_claim[lb] = ~0u;
+		}
+		if (pass) {
+			if (p.tab.slots) n_new += tab_upsert(p.tab, c0, c1, (int)(c0f >> 63)) == 1;
+			else {
+				const BloomProbe ph = bloom_locate(hash_from_y(p.k, c0, c1), p.bf_high.n_shift);
+				bloom_set_atomic(bloom_block(p.bf_high, ph.blk), ph, p.bf_high.n_hashes);
+			}
+		}
+		n_k += valid, n_pass += pass, n_wait += waited;
+	}
+	__syncthreads();
+	for (uint32_t i = tid; i < nb * 4; i += CP_THREADS) __stcs(g4 + i, s4[i]);
+	block_add(p.ctr + 1, n_k);
+	block_add(p.ctr + 2, n_pass);
+	block_add(p.ctr + 3, n_wait);
+	if (p.tab.slots) block_add(p.tab.counters, n_new);
+}
+
+// ------------------------------------------------------------------ host side
+
+struct PartGeom {
+	int x;              // log2(Bloom blocks this rank holds)
+	int pbits;          // log2(partitions)
+	uint32_t n_parts, blocks_per_part;
+};
+
+static PartGeom part_geom(const bfc_bf_t *bf, int owner_bits)
+{
+	PartGeom g;
+	g.x = bf->n_shift - BFC_BLK_SHIFT - owner_bits;
+	g.pbits = g.x > CP_SLOG2 ? g.x - CP_SLOG2 : 0;
+	g.n_parts = 1u << g.pbits;
+	g.blocks_per_part = 1u << (g.x < CP_SLOG2 ? g.x : CP_SLOG2);
+	return g;
+}
+
+bool bfcg_count_part_usable(const bfc_opt_t *opt, const bfc_bf_t *bf, int owner_bits)
+{
+	const char *e = getenv("BFC_B200_COUNT");
+	if (e && strcmp(e, "probe") == 0) return false;
+	const int x = bf->n_shift - BFC_BLK_SHIFT;
+	// the block index (bbf.c:27-28) must be a bit field of y0, and the partition index must fit the sort
+	return x <= opt->k && x - owner_bits >= 0 && x - owner_bits - CP_SLOG2 <= 30;
+}
+
+struct PartScratch {
+	unsigned long long *s_y0, *s_y1; // sorted records
+	uint8_t *tmp;
+	size_t tmp_bytes;
+	uint32_t *bounds;                // start[n_parts], end[n_parts]
+	unsigned long long *ctr;
+	static size_t sort_temp(uint64_t n, int pbits)
+	{
+		size_t t = 0;
+		if (pbits > 0)
+			cub::DeviceRadixSort::SortPairs((void*)0, t, (const unsigned long long*)0, (unsigned long long*)0,
+			                                (const unsigned long long*)0, (unsigned long long*)0, (int64_t)n, CP_SLOG2, CP_SLOG2 + pbits, bfcg_rt().stream);
+		return t;
+	}
+	static size_t bytes(uint64_t n, const PartGeom &g)
+	{
+		return 2 * align_up(n * 8, 256) + align_up(sort_temp(n, g.pbits), 256) + align_up((size_t)g.n_parts * 8, 256) + 256;
+	}
+	void carve(uint8_t *a, uint64_t n, const PartGeom &g)
+	{
+		size_t o = 0;
+		s_y0 = (unsigned long long*)(a + o); o += align_up(n * 8, 256);
+		s_y1 = (unsigned long long*)(a + o); o += align_up(n * 8, 256);
+		tmp_bytes = sort_temp(n, g.pbits);
+		tmp = a + o; o += align_up(tmp_bytes, 256);
+		bounds = (uint32_t*)(a + o); o += align_up((size_t)g.n_parts * 8, 256);
+		ctr = (unsigned long long*)(a + o);
+	}
+};
+
+// K1'-K3' over n records in stream order (in_y0 / in_y1, device)
+static int count_part_window(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, bfc_ch_t *ch, const PartGeom &g, uint64_t blk_mask,
+                             const unsigned long long *in_y0, const unsigned long long *in_y1, uint64_t n, PartScratch &sc, bfcg_stats_t *stats,
+                             const std::function<int()> *launched = 0)
+{
+	BfcgRuntime &rt = bfcg_rt();
+	int r;
+	unsigned long long before = 0;
+	if (ch) {
+		// room for the keys this window can add, at load <= 1/2: at most every second occurrence is new unless the
+		// filter misfires; after the first window the previous one's growth is the estimate.  A region that fills up
+		// anyway parks its inserts (tab_upsert) and the load is put right after the window.
+		before = bfc_ch_count(ch);
+		uint64_t extra = n / 2;
+		if (ch->have_prev) extra = std::min<uint64_t>(extra, std::max<uint64_t>(2 * ch->prev_new, n / 16));
+		if ((r = bfcg_tab_reserve(ch, std::max<uint64_t>(extra, 1024))) != BFCG_OK) return r;
+	}
+	PartParams p;
+	memset(&p, 0, sizeof(p));
+	p.k = opt->k, p.n_rec = n, p.blocks_per_part = g.blocks_per_part;
+	p.bf = bloom_view(bf), p.bf.blk_mask = blk_mask;
+	if (bf_high) p.bf_high = bloom_view(bf_high), p.bf_high.blk_mask = blk_mask;
+	if (ch) p.tab = tab_view(ch);
+	p.ctr = sc.ctr;
+	p.y0 = in_y0, p.y1 = in_y1;
+	if (g.pbits > 0) {
+		size_t tb = sc.tmp_bytes;
+		cudaError_t se;
+		{
+			KTime kt(KT_COUNT_SORT);
+			se = cub::DeviceRadixSort::SortPairs(sc.tmp, tb, in_y0, sc.s_y0, in_y1, sc.s_y1, (int64_t)n, CP_SLOG2, CP_SLOG2 + g.pbits, rt.stream);
+		}
+		BFCG_CUDA(se);
+		rt.n_launches += 1 + (g.pbits + 7) / 8; // histogram + one onesweep pass per 8 bits
+		uint32_t *start = sc.bounds, *end = sc.bounds + g.n_parts;
+		BFCG_CUDA(cudaMemsetAsync(sc.bounds, 0, (size_t)g.n_parts * 8, rt.stream));
+		{ KTime kt(KT_COUNT_BOUNDS); k_part_bounds<<<(unsigned)((n + 255) / 256), 256, 0, rt.stream>>>(sc.s_y0, n, g.n_parts - 1, start, end); }
+		BFCG_LAUNCH_CHECK();
+		p.y0 = sc.s_y0, p.y1 = sc.s_y1, p.start = start, p.end = end;
+	}
+	BFCG_CUDA(cudaMemsetAsync(p.ctr, 0, 64, rt.stream));
+	const size_t smem = (size_t)g.blocks_per_part * CP_BLK_BYTES;
+	{ KTime kt(KT_COUNT_PART); k_count_part<<<g.n_parts, CP_THREADS, smem, rt.stream>>>(p); }
+	BFCG_LAUNCH_CHECK();
+	if (launched && (r = (*launched)()) != BFCG_OK) return r; // host work that should overlap the kernels just enqueued
+	unsigned long long c[4];
+	BFCG_CUDA(cudaMemcpyAsync(c, p.ctr, sizeof(c), cudaMemcpyDeviceToHost, rt.stream));
+	BFCG_CUDA(cudaStreamSynchronize(rt.stream));
+	if (ch) {
+		if ((r = bfcg_tab_drain_deferred(ch)) != BFCG_OK) return r;
+		ch->prev_new = bfc_ch_count(ch) - before, ch->have_prev = 1;
+		if ((r = bfcg_tab_reserve(ch, 0)) != BFCG_OK) return r;
+	}
+	if (stats) {
+		stats->n_kmers += c[1], stats->n_pass += c[2];
+		stats->n_pending += c[1] - c[2], stats->n_conflict += c[3];
+	}
+	return BFCG_OK;
+}
+
+static int part_kernel_setup()
+{
+	static bool done = false;
+	if (!done) {
+		BFCG_CUDA(cudaFuncSetAttribute(k_count_part, cudaFuncAttributeMaxDynamicSharedMemorySize, CP_BLOCKS * CP_BLK_BYTES));
+		done = true;
+	}
+	return BFCG_OK;
+}
+
+// stream positions per window: as many as the free memory takes, at most 2^30
+static uint64_t window_positions(uint64_t n_positions, bool host, const PartGeom &g)
+{
+	const char *e = getenv("BFC_B200_COUNT_WINDOW");
+	uint64_t P = 1ULL << 30;
+	if (e && atoll(e) >= EL_SEG) P = el_padded((uint64_t)atoll(e));
+	else {
+		size_t fr = 0, tot = 0;
+		cudaMemGetInfo(&fr, &tot);
+		const double avail = 0.55 * (double)(fr + bfcg_rt().arena_bytes);
+		while (P > (1ULL << 22) && (double)(P * (host ? 36 : 32)) + (double)PartScratch::sort_temp(P, g.pbits) > avail) P >>= 1;
+	}
+	return std::min(P, el_padded(n_positions));
+}
+
+int bfcg_count_part_batch(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, bfc_ch_t *ch, const bfcg_batch_t *batch, bfcg_stats_t *stats)
+{
+	BfcgRuntime &rt = bfcg_rt();
+	int r;
+	if ((r = part_kernel_setup()) != BFCG_OK) return r;
+	const PartGeom g = part_geom(bf, 0);
+	if (ch && (r = bfcg_tab_align_to_filter(ch, bf->n_shift - BFC_BLK_SHIFT)) != BFCG_OK) return r;
+	const bool host = batch->where == BFCG_HOST;
+	const uint64_t nbytes = batch->n_bytes, halo = opt->k - 1;
+	const uint64_t P = window_positions(nbytes, host, g);
+	const uint64_t W = align_up(P + halo, 256);
+	PartScratch sc;
+	size_t o_stage[2][2] = {{0, 0}, {0, 0}}, o_y0, o_y1, o_sc, tot = 0;
+	if (host)
+		for (int b = 0; b < 2; ++b)
+			for (int j = 0; j < 2; ++j) { o_stage[b][j] = tot; tot += W; }
+	o_y0 = tot; tot += align_up(P * 8, 256);
+	o_y1 = tot; tot += align_up(P * 8, 256);
+	o_sc = tot; tot += PartScratch::bytes(P, g);
+	uint8_t *a = (uint8_t*)bfcg_arena(tot);
+	if (!a) return BFCG_ERR_NOMEM;
+	sc.carve(a + o_sc, P, g);
+	unsigned long long *rec_y0 = (unsigned long long*)(a + o_y0), *rec_y1 = (unsigned long long*)(a + o_y1);
+
+	const uint64_t n_win = (nbytes + P - 1) / P;
+	// host batches: the copy of window i+1 runs on its own stream while window i is counted
+	auto issue_copy = [&](uint64_t wi) -> cudaError_t {
+		const uint64_t s = wi * P, e = std::min(nbytes, s + P), w0 = s >= halo ? s - halo : 0;
+		const int b = (int)(wi & 1);
+		cudaError_t ce;
+		if (wi >= 2 && (ce = cudaStreamWaitEvent(rt.copy_in, rt.ev_free[b], 0)) != cudaSuccess) return ce;
+		if ((ce = cudaMemcpyAsync(a + o_stage[b][0], batch->seq + w0, e - w0, cudaMemcpyHostToDevice, rt.copy_in)) != cudaSuccess) return ce;
+		if (batch->qual && (ce = cudaMemcpyAsync(a + o_stage[b][1], batch->qual + w0, e - w0, cudaMemcpyHostToDevice, rt.copy_in)) != cudaSuccess) return ce;
+		return cudaEventRecord(rt.ev_in[b], rt.copy_in);
+	};
+	BfcgTimer timer(stats);
+	r = BFCG_OK;
+	if (host) {
+		BFCG_CUDA(cudaStreamSynchronize(rt.stream)); // the arena may still be in use by earlier work on the engine's stream
+		BFCG_CUDA(issue_copy(0));
+	}
+	for (uint64_t wi = 0; wi < n_win && r == BFCG_OK; ++wi) {
+		const uint64_t s = wi * P, e = std::min(nbytes, s + P), w0 = s >= halo ? s - halo : 0;
+		const int b = (int)(wi & 1);
+		EnumLinParams ep;
+		memset(&ep, 0, sizeof(ep));
+		ep.k = opt->k, ep.q = opt->q, ep.rec_y0 = rec_y0, ep.rec_y1 = rec_y1;
+		ep.len = e - w0, ep.emit_from = s - w0;
+		if (host) {
+			const cudaError_t ce = cudaStreamWaitEvent(rt.stream, rt.ev_in[b], 0);
+			if (ce != cudaSuccess) { r = bfcg_fail(__func__, "staging copy", ce); break; }
+			ep.seq = a + o_stage[b][0], ep.qual = batch->qual ? a + o_stage[b][1] : 0;
+		} else ep.seq = batch->seq + w0, ep.qual = batch->qual ? batch->qual + w0 : 0;
+		const uint64_t n_rec = el_padded(e - s);
+		{ KTime kt(KT_ENUM_LIN); k_enum_lin<<<(unsigned)(n_rec / EL_SEG), EL_THREADS, 0, rt.stream>>>(ep); }
+		++rt.n_launches;
+		{ const cudaError_t le = cudaGetLastError(); if (le != cudaSuccess) { r = bfcg_fail(__func__, "kernel launch", le); break; } }
+		if (host) cudaEventRecord(rt.ev_free[b], rt.stream);
+		// the next window travels while this one is counted (issued after this window's launches: a copy from
+		// pageable memory blocks the host, and should not hold the kernels back)
+		const std::function<int()> next_copy = [&]() -> int {
+			if (!host || wi + 1 >= n_win) return BFCG_OK;
+			const cudaError_t ce = issue_copy(wi + 1);
+			return ce == cudaSuccess ? BFCG_OK : bfcg_fail("bfcg_count_part_batch", "staging copy", ce);
+		};
+		r = count_part_window(opt, bf, bf_high, ch, g, ~0ULL, rec_y0, rec_y1, n_rec, sc, stats, &next_copy);
+	}
+	if (host) cudaStreamSynchronize(rt.copy_in);
+	if (r != BFCG_OK) { cudaStreamSynchronize(rt.stream); return r; }
+	timer.stop();
+	BFCG_CUDA(cudaStreamSynchronize(rt.stream));
+	return BFCG_OK;
+}
+
+int bfcg_count_part_records(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, bfc_ch_t *ch, uint64_t n_rec,
+                            const uint64_t *d_y0, const uint64_t *d_y1, int owner_bits, bfcg_stats_t *stats)
+{
+	BfcgRuntime &rt = bfcg_rt();
+	int r;
+	if ((r = part_kernel_setup()) != BFCG_OK) return r;
+	const PartGeom g = part_geom(bf, owner_bits);
+	if (ch && (r = bfcg_tab_align_to_filter(ch, bf->n_shift - BFC_BLK_SHIFT)) != BFCG_OK) return r;
+	const uint64_t P = std::min<uint64_t>(window_positions(n_rec, false, g), n_rec);
+	PartScratch sc;
+	uint8_t *a = (uint8_t*)bfcg_arena(PartScratch::bytes(P, g));
+	if (!a) return BFCG_ERR_NOMEM;
+	sc.carve(a, P, g);
+	const uint64_t blk_mask = (1ULL << g.x) - 1; // this rank holds 1/n_owners of the blocks
+	BfcgTimer timer(stats);
+	for (uint64_t s = 0; s < n_rec; s += P) {
+		const uint64_t n = std::min(P, n_rec - s);
+		if ((r = count_part_window(opt, bf, bf_high, ch, g, blk_mask, (const unsigned long long*)d_y0 + s, (const unsigned long long*)d_y1 + s, n, sc, stats)) != BFCG_OK) return r;
+	}
+	timer.stop();
+	BFCG_CUDA(cudaStreamSynchronize(rt.stream));
+	return BFCG_OK;
+}

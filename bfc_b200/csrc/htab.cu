@@ -9,11 +9,11 @@ static const uint64_t TAB_DEF_CAP = 1 << 20; // parked inserts per kernel before
 
 // ------------------------------------------------------------------ kernels
 
-__global__ void k_tab_rehash(const unsigned long long *old_slots, int old_rbits, uint64_t old_n, TabView nt, unsigned long long *fail)
+__global__ void k_tab_rehash(const unsigned long long *old_slots, int old_rbits, int old_rot, uint64_t old_n, TabView nt, unsigned long long *fail)
 {
 	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < old_n; i += (uint64_t)gridDim.x * blockDim.x) {
 		const unsigned long long s = old_slots[i];
-		if (s && !tab_put_raw(nt, (uint32_t)(i >> old_rbits), s)) atomicAdd(fail, 1ULL);
+		if (s && !tab_put_raw(nt, tab_region_inv(nt.l_pre, old_rot, (uint32_t)(i >> old_rbits)), s)) atomicAdd(fail, 1ULL);
 	}
 }
 
@@ -72,14 +72,14 @@ __global__ void k_tab_hist(const unsigned long long *slots, uint64_t n, unsigned
 		if (s_h[i]) atomicAdd(hist + i, (unsigned long long)s_h[i]);
 }
 
-__global__ void k_tab_export(const unsigned long long *slots, int rbits, uint64_t n, uint32_t *sub, unsigned long long *key,
+__global__ void k_tab_export(const unsigned long long *slots, int rbits, int l_pre, int rot, uint64_t n, uint32_t *sub, unsigned long long *key,
                              unsigned long long *cursor)
 {
 	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
 		const unsigned long long s = __ldg(slots + i);
 		if (s) {
 			const unsigned long long at = atomicAdd(cursor, 1ULL);
-			sub[at] = (uint32_t)(i >> rbits);
+			sub[at] = tab_region_inv(l_pre, rot, (uint32_t)(i >> rbits));
 			key[at] = s;
 		}
 	}
@@ -97,8 +97,9 @@ static int tab_read_counters(const bfc_ch_s *ch, unsigned long long c[2])
 	return BFCG_OK;
 }
 
-static int tab_resize(bfc_ch_s *ch, int new_rbits)
+static int tab_resize(bfc_ch_s *ch, int new_rbits, int new_rot = -1)
 {
+	if (new_rot < 0) new_rot = ch->rot;
 	BfcgRuntime &rt = bfcg_rt();
 	unsigned long long *ns = 0, *fail = ch->counters + 2, h_fail = 0; // own scratch word: callers may hold the arena
 	const uint64_t new_cap = 1ULL << (ch->l_pre + new_rbits);
@@ -109,15 +110,27 @@ static int tab_resize(bfc_ch_s *ch, int new_rbits)
 	BFCG_CUDA(cudaMemsetAsync(ns, 0, new_cap * 8, rt.stream));
 	BFCG_CUDA(cudaMemsetAsync(fail, 0, 8, rt.stream));
 	TabView nt = tab_view(ch);
-	nt.slots = ns, nt.rbits = new_rbits;
-	{ KTime kt(KT_TAB_REHASH); k_tab_rehash<<<rt.sm_count * 8, 256, 0, rt.stream>>>(ch->slots, ch->rbits, tab_capacity(ch), nt, fail); }
+	nt.slots = ns, nt.rbits = new_rbits, nt.rot = new_rot;
+	{ KTime kt(KT_TAB_REHASH); k_tab_rehash<<<rt.sm_count * 8, 256, 0, rt.stream>>>(ch->slots, ch->rbits, ch->rot, tab_capacity(ch), nt, fail); }
 	BFCG_LAUNCH_CHECK();
 	BFCG_CUDA(cudaMemcpyAsync(&h_fail, fail, 8, cudaMemcpyDeviceToHost, rt.stream));
 	BFCG_CUDA(cudaStreamSynchronize(rt.stream));
 	if (h_fail) return bfcg_fail(__func__, "rehash lost keys", cudaSuccess);
 	cudaFree(ch->slots);
-	ch->slots = ns, ch->rbits = new_rbits;
+	ch->slots = ns, ch->rbits = new_rbits, ch->rot = new_rot;
 	return BFCG_OK;
+}
+
+// The low x bits of y0 are the Bloom block index (when x <= k); sub-table index bit j is y0 bit j + k - l_pre
+// (htab.c:45-58; for k <= 32 and l_pre > k it is y0 bit j - (l_pre - k)).  Rotating the sub-table index right by the
+// number of its bits that lie below y0 bit x makes them the top bits of the region index.
+int bfcg_tab_align_to_filter(bfc_ch_s *ch, int x)
+{
+	int rot = x - (ch->k - ch->l_pre);
+	if (x > ch->k || rot <= 0 || rot >= ch->l_pre) rot = 0;
+	if (rot == ch->rot) return BFCG_OK;
+	if (bfc_ch_count(ch) == 0) { ch->rot = rot; return BFCG_OK; }
+	return tab_resize(ch, ch->rbits, rot);
 }
 
 int bfcg_tab_reserve(bfc_ch_s *ch, uint64_t extra)
@@ -299,6 +312,7 @@ int bfcg_ch_clear(bfc_ch_t *ch)
 	BFCG_CUDA(cudaMemsetAsync(ch->slots, 0, tab_capacity(ch) * 8, rt.stream));
 	BFCG_CUDA(cudaMemsetAsync(ch->counters, 0, 16, rt.stream));
 	BFCG_CUDA(cudaStreamSynchronize(rt.stream));
+	ch->prev_new = 0, ch->have_prev = 0;
 	return BFCG_OK;
 }
 
@@ -321,7 +335,7 @@ uint64_t bfcg_ch_export(const bfc_ch_t *ch, uint32_t *sub, uint64_t *key)
 	unsigned long long *d_key = (unsigned long long*)a, *cursor = (unsigned long long*)(a + n * 8);
 	uint32_t *d_sub = (uint32_t*)(a + n * 8 + 256);
 	cudaMemsetAsync(cursor, 0, 8, rt.stream);
-	k_tab_export<<<rt.sm_count * 8, 256, 0, rt.stream>>>(ch->slots, ch->rbits, tab_capacity(ch), d_sub, d_key, cursor);
+	k_tab_export<<<rt.sm_count * 8, 256, 0, rt.stream>>>(ch->slots, ch->rbits, ch->l_pre, ch->rot, tab_capacity(ch), d_sub, d_key, cursor);
 	++rt.n_launches;
 	std::vector<uint32_t> hs(n);
 	std::vector<uint64_t> hk(n);
@@ -347,7 +361,7 @@ uint64_t bfcg_ch_export_device(const bfc_ch_t *ch, uint32_t *d_sub, uint64_t *d_
 	if (d_sub == 0 || d_key == 0 || c[0] == 0) return c[0];
 	unsigned long long *cursor = ch->counters + 3;
 	cudaMemsetAsync(cursor, 0, 8, rt.stream);
-	k_tab_export<<<rt.sm_count * 8, 256, 0, rt.stream>>>(ch->slots, ch->rbits, tab_capacity(ch), d_sub, (unsigned long long*)d_key, cursor);
+	k_tab_export<<<rt.sm_count * 8, 256, 0, rt.stream>>>(ch->slots, ch->rbits, ch->l_pre, ch->rot, tab_capacity(ch), d_sub, (unsigned long long*)d_key, cursor);
 	++rt.n_launches;
 	if (cudaStreamSynchronize(rt.stream) != cudaSuccess) { bfcg_fail(__func__, "kernel", cudaGetLastError()); return 0; }
 	return c[0];

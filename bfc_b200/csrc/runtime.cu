@@ -37,8 +37,16 @@ int bfcg_rt_init()
 	// random 32-byte sector gathers dominate: do not let L2 widen the DRAM fetch
 	cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
 	BFCG_CUDA(cudaStreamCreateWithFlags(&g_rt.stream, cudaStreamNonBlocking));
+	BFCG_CUDA(cudaStreamCreateWithFlags(&g_rt.copy_in, cudaStreamNonBlocking));
+	BFCG_CUDA(cudaStreamCreateWithFlags(&g_rt.copy_out, cudaStreamNonBlocking));
 	BFCG_CUDA(cudaEventCreate(&g_rt.ev0));
 	BFCG_CUDA(cudaEventCreate(&g_rt.ev1));
+	for (int i = 0; i < 2; ++i) {
+		BFCG_CUDA(cudaEventCreateWithFlags(&g_rt.ev_in[i], cudaEventDisableTiming));
+		BFCG_CUDA(cudaEventCreateWithFlags(&g_rt.ev_free[i], cudaEventDisableTiming));
+		BFCG_CUDA(cudaEventCreateWithFlags(&g_rt.ev_done[i], cudaEventDisableTiming));
+		BFCG_CUDA(cudaEventCreateWithFlags(&g_rt.ev_out[i], cudaEventDisableTiming));
+	}
 	g_rt.ready = true;
 	return BFCG_OK;
 }
@@ -82,8 +90,8 @@ static void kt_collect()
 void *bfcg_arena(size_t bytes)
 {
 	if (bytes <= g_rt.arena_bytes) return g_rt.arena;
-	if (g_rt.arena) { cudaStreamSynchronize(g_rt.stream); cudaFree(g_rt.arena); g_rt.arena = 0; g_rt.arena_bytes = 0; }
-	size_t want = bytes + (bytes >> 2);
+	if (g_rt.arena) { cudaDeviceSynchronize(); cudaFree(g_rt.arena); g_rt.arena = 0; g_rt.arena_bytes = 0; }
+	size_t want = bytes < ((size_t)1 << 30) ? bytes + (bytes >> 2) : bytes; // head-room only for small arenas
 	if (cudaMalloc(&g_rt.arena, want) != cudaSuccess) {
 		want = bytes;
 		cudaGetLastError();
@@ -140,7 +148,7 @@ void bfcg_set_timing(int on) { g_rt.timing = on != 0; }
 int bfcg_kernel_times(double *ms, uint64_t *launches, int n)
 {
 	kt_collect();
-	for (int i = 0; i < n && i < 16; ++i) ms[i] = g_rt.kt_ms[i], launches[i] = g_rt.kt_n[i];
+	for (int i = 0; i < n && i < KT_N; ++i) ms[i] = g_rt.kt_ms[i], launches[i] = g_rt.kt_n[i];
 	memset(g_rt.kt_ms, 0, sizeof(g_rt.kt_ms));
 	memset(g_rt.kt_n, 0, sizeof(g_rt.kt_n));
 	return KT_N;

@@ -38,8 +38,10 @@ def mark_noqual(recs, qual, off):
     return q
 
 
+@pytest.mark.parametrize("path", ["part", "probe"])
 @pytest.mark.parametrize("name", CASES)
-def test_golden_count_correct(bfc, name):
+def test_golden_count_correct(bfc, monkeypatch, name, path):
+    monkeypatch.setenv("BFC_B200_COUNT", path)  # both count paths (see test_oracle_random)
     c = Case(name)
     qual = mark_noqual(c.recs, c.qual, c.off)
     e = bfc.Engine(as_bfc_opt(bfc, c.opt()))
@@ -83,10 +85,16 @@ def synth_batch(G, N, L, seed, err=0.01, repeat=0.0):
     (33, 30, 300000, 60000, 150, 0.3, 1 << 18),  # several sub-batches, few conflicts
     (55, 24, 100000, 30000, 150, 0.3, 1 << 17),
     (63, 22, 50000, 12000, 151, 0.1, 50000),
+    (13, 24, 3000, 12000, 60, 0.0, None),        # block index wider than k: not a bit field of y0 => probe path either way
 ])
-def test_oracle_random(bfc, monkeypatch, k, b, G, N, L, repeat, sub):
+@pytest.mark.parametrize("path", ["part", "probe"])
+def test_oracle_random(bfc, monkeypatch, k, b, G, N, L, repeat, sub, path):
+    # both count paths: "part" = partitioned windows with the filter slices in shared memory (count_part.cu),
+    # "probe" = probe / resolve / replay against the filter in HBM (count.cu; also what k < n_shift - 9 uses)
+    monkeypatch.setenv("BFC_B200_COUNT", path)
     if sub:
         monkeypatch.setenv("BFC_B200_SUBBATCH", str(sub))
+        monkeypatch.setenv("BFC_B200_COUNT_WINDOW", str(sub))
     seq, qual, off = synth_batch(G, N, L, seed=k * 1000 + b, repeat=repeat)
     o = orc.OracleRun(orc.make_opt(k=k, bf_shift=b))
     e = bfc.Engine(bfc.make_opt(k=k, bf_shift=b))
@@ -208,6 +216,7 @@ def test_sharded_count_kernels_emulated_on_one_gpu(bfc, monkeypatch, world, k, b
     import torch
     from bfc_b200.dist import CudaBackend, piece_bounds
     monkeypatch.setenv("BFC_B200_SUBBATCH", str(1 << 17))
+    monkeypatch.setenv("BFC_B200_COUNT_WINDOW", str(1 << 17))
     seq, qual, off = synth_batch(60000, 16000, 120, seed=k + world, repeat=0.2)
     N = len(off) - 1
     opt = bfc.make_opt(k=k, bf_shift=b, filter_mode=1 if trim else 0)
@@ -249,3 +258,52 @@ def test_sharded_count_kernels_emulated_on_one_gpu(bfc, monkeypatch, world, k, b
         for r in ranks:
             r.close()
         o.close()
+
+
+@pytest.mark.parametrize("path", ["part", "probe"])
+def test_device_batches_and_many_windows(bfc, monkeypatch, path):
+    """What bench.py runs: batches resident in HBM (BFCG_DEVICE), and host batches cut into many count /
+    correct windows (the double-buffered copy streams cycle several times); both equal the oracle."""
+    import ctypes as C
+    monkeypatch.setenv("BFC_B200_COUNT", path)
+    monkeypatch.setenv("BFC_B200_EC_BATCH", "150000")
+    monkeypatch.setenv("BFC_B200_COUNT_WINDOW", "65536")
+    monkeypatch.setenv("BFC_B200_SUBBATCH", "65536")
+    api, L = bfc.api, bfc.lib()
+    seq, qual, off = synth_batch(40000, 12000, 150, seed=7, repeat=0.2)
+    n, nb = len(off) - 1, int(off[-1])
+    o = orc.OracleRun(orc.make_opt(k=33, bf_shift=26))
+    eh = bfc.Engine(bfc.make_opt(k=33, bf_shift=26))
+    ed = bfc.Engine(bfc.make_opt(k=33, bf_shift=26))
+    d_seq, d_qual, d_off, d_aux = L.bfcg_dev_alloc(nb), L.bfcg_dev_alloc(nb), L.bfcg_dev_alloc(8 * (n + 1)), L.bfcg_dev_alloc(8 * n)
+    try:
+        o.count(seq, qual, off)
+        so, qo, ao, _ = o.correct(seq, qual, off)
+        # host batches, many windows
+        eh.count(seq, qual, off)
+        assert np.array_equal(eh.bloom_bytes(), o.bloom_bytes())
+        sub_o, key_o = o.table()
+        sub_e, key_e = eh.table()
+        assert np.array_equal(sub_e, sub_o) and np.array_equal(key_e, key_o)
+        se, qe, ae = eh.correct(seq, qual, off)
+        assert np.array_equal(ae, ao) and np.array_equal(se, so) and np.array_equal(qe, qo)
+        # device batches
+        assert d_seq and d_qual and d_off and d_aux
+        assert L.bfcg_h2d(d_seq, seq.ctypes.data, nb) == 0 and L.bfcg_h2d(d_qual, qual.ctypes.data, nb) == 0
+        assert L.bfcg_h2d(d_off, off.ctypes.data, 8 * (n + 1)) == 0
+        b = api.Batch()
+        b.n_reads, b.n_bytes, b.where = n, nb, api.DEVICE
+        b.off, b.seq, b.qual = C.cast(d_off, api.u64p), C.cast(d_seq, api.u8p), C.cast(d_qual, api.u8p)
+        ed.count_batch(b)
+        assert np.array_equal(ed.bloom_bytes(), o.bloom_bytes())
+        sub_e, key_e = ed.table()
+        assert np.array_equal(sub_e, sub_o) and np.array_equal(key_e, key_o)
+        ed.correct_batch(b, d_aux)
+        sd, qd, ad = np.empty_like(seq), np.empty_like(qual), np.empty(2 * n, dtype=np.uint32)
+        assert L.bfcg_d2h(sd.ctypes.data, d_seq, nb) == 0 and L.bfcg_d2h(qd.ctypes.data, d_qual, nb) == 0
+        assert L.bfcg_d2h(ad.ctypes.data, d_aux, 8 * n) == 0
+        assert np.array_equal(ad, ao) and np.array_equal(sd, so) and np.array_equal(qd, qo)
+    finally:
+        for p in (d_seq, d_qual, d_off, d_aux):
+            L.bfcg_dev_free(p)
+        eh.close(); ed.close(); o.close()
