@@ -418,6 +418,7 @@ def main():
             hb_pieces.append(api.host_batch(h_seq[loc * RB:(loc + m) * RB], h_qual[loc * RB:(loc + m) * RB], h_off[:m + 1]))
             loc += m
         tot = 0.0
+        split = {"reset_s": 0.0, "count_s": 0.0, "correct_s": 0.0}
         for it in range(1 + e2e_steps):
             ws[:] = h_seq
             wq[:] = h_qual
@@ -425,8 +426,12 @@ def main():
             t0 = time.perf_counter()
             if world == 1:
                 eng.reset()
+                t1 = time.perf_counter()
                 eng.count_batch(hb_pieces[0])
+                t2 = time.perf_counter()
                 eng.correct_batch(hb_work, p_aux.ctypes.data)
+                if it > 0:
+                    split["reset_s"] += t1 - t0; split["count_s"] += t2 - t1; split["correct_s"] += time.perf_counter() - t2
             else:
                 be.reset()
                 for hb in hb_pieces:
@@ -441,7 +446,7 @@ def main():
         e2e = {"value": n * e2e_steps / tot / 1e6, "unit": "Mreads/s",
                "h2d_bytes_per_step": int(4 * n * RB + 8 * (n + world)),
                "d2h_bytes_per_step": int(2 * n * RB + 8 * n),
-               "steps": e2e_steps, "note": "whole job, all ranks: pinned host buffers -> bfcg_count_batch (N>1: bfcg_enum_records + "
+               "steps": e2e_steps, "split": {k_: v / e2e_steps for k_, v in split.items()} if world == 1 else None, "note": "whole job, all ranks: pinned host buffers -> bfcg_count_batch (N>1: bfcg_enum_records + "
                "all-to-all + bfcg_count_records) / bfcg_correct_batch -> host buffers; wall clock, max over ranks"}
         for p_ in (p_hs, p_hq, p_ws, p_wq):
             L.bfcg_host_free_pinned(p_)

@@ -154,7 +154,7 @@ def lib():
 
 KERNEL_NAMES = ["count_probe", "count_resolve", "conflict_sort", "count_replay", "correct", "correct_redo", "trim",
                 "tab_rehash", "tab_hist", "tab_apply", "enum", "ec_lookup", "ec_setup", "ec_merge", "bucket",
-                "count_part", "count_bounds", "enum_lin"]
+                "count_part", "count_bounds", "enum_lin", "ec_ext"]
 
 
 def kernel_times():

@@ -41,12 +41,12 @@ struct BfcgRuntime {
 	cudaEvent_t user_ev[8];
 	// host <-> device copies of host batches run on their own streams so that they overlap the kernels
 	cudaStream_t copy_in, copy_out;
-	cudaEvent_t ev_in[2], ev_free[2], ev_done[2], ev_out[2];
+	cudaEvent_t ev_in[3], ev_free[3], ev_done[3], ev_out[3];
 };
 
 enum { KT_COUNT_PROBE = 0, KT_COUNT_RESOLVE, KT_COUNT_SORT, KT_COUNT_REPLAY, KT_CORRECT, KT_CORRECT_REDO,
        KT_TRIM, KT_TAB_REHASH, KT_TAB_HIST, KT_TAB_APPLY, KT_ENUM, KT_EC_LOOKUP, KT_EC_SETUP, KT_EC_MERGE, KT_BUCKET,
-       KT_COUNT_PART, KT_COUNT_BOUNDS, KT_ENUM_LIN, KT_N };
+       KT_COUNT_PART, KT_COUNT_BOUNDS, KT_ENUM_LIN, KT_EC_EXT, KT_N };
 
 int  bfcg_kt_begin(int id);   // records a start event on the stream when timing is on; returns a span index or -1
 void bfcg_kt_end(int idx);

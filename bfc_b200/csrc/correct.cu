@@ -87,6 +87,7 @@ struct EcParams {
 	ReadDesc *desc;
 	int4 *jobs;                  // per job: (window offset of the read, length, search start or -1, rescue edit or -1)
 	int2 *res;                   // per job: (return value of bfc_ec1dir, max_heap)
+	uint64_t *ext;               // per job: the lookups past the end of the read (k_ec_ext), 0 = not available
 	TabView tab;
 	int k, q, min_cov, win_multi_ec, max_end_ext;
 	int w_ec, w_ec_high, w_absent, w_absent_high, max_path_diff, max_heap, mode;
@@ -97,7 +98,7 @@ struct EcParams {
 	const uint32_t *redo;        // when set: thread job list (job = read * 2 + dir); n_jobs = its length
 	int64_t n_jobs;
 	uint32_t *overflow;          // jobs whose edit list overflowed
-	unsigned long long *ctr;     // [0] n_overflow, [1] n_lookups
+	unsigned long long *ctr;     // [0] n_overflow, [1] n_lookups, [2] next job to hand out
 };
 
 __device__ __forceinline__ int comp_b(int b) { return b < 4 ? 3 - b : 4; }
@@ -336,6 +337,53 @@ __global__ void __launch_bounds__(128) k_ec_setup(EcParams P)
 	block_add(P.ctr + 1, n_lookups);
 }
 
+// ------------------------------------------------------------------ K6a': lookups past the end of the read
+
+#define EC_EXT_STEPS 7 // positions n .. n + 6 fit the 8 bytes of a memo; used when max_end_ext < 7
+
+// Past the end of the read (z.i >= n) bfc_ec1dir tries all four bases at every position (correct.c:318-333) and
+// goes on only while exactly one of them is solid (correct.c:358-372), for at most max_end_ext + 1 positions
+// (correct.c:289).  For a state whose last k-1 bases are the read's own, those lookups depend on nothing else in
+// the search: they are made here for every job at once -- all lanes in step, four independent probes per position --
+// and k_ec_search reads them back.  Byte s of the memo = position n + s: bits 0-3 "base b is solid"
+// (cnt >= min_cov), bits 4-7 "its high count is below min_cov"; bit 63 = memo present.
+__global__ void __launch_bounds__(256) k_ec_ext(EcParams P)
+{
+	const int64_t job = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned long long n_lookups = 0;
+	if (job < P.n_jobs) {
+		const int4 jr = P.jobs[job];
+		const int k = P.k, n = jr.y, dir = (int)(job & 1);
+		uint64_t memo = 0;
+		if (jr.z >= 0 && n >= k) {
+			uint64_t x[4];
+			extract_kmer(P, (int64_t)(uint32_t)jr.x, n, dir, n - 1, k - 1, -1, 0, x);
+			memo = 1ULL << 63;
+			for (int s = 0; s <= P.max_end_ext; ++s) {
+				uint32_t bits = 0;
+				int n_solid = 0, last = 0;
+#pragma unroll
+				for (int b = 0; b < 4; ++b) {
+					uint64_t y[4] = { x[0], x[1], x[2], x[3] };
+					bfc_kmer_append(k, y, b);
+					const int res = tab_kmer_occ(P.tab, y);
+					if (res >= 0 && (res & 0xff) >= P.min_cov) {
+						bits |= 1u << b;
+						if ((res >> 8 & 0xff) < P.min_cov) bits |= 16u << b;
+						++n_solid, last = b;
+					}
+				}
+				n_lookups += 4;
+				memo |= (uint64_t)bits << (8 * s);
+				if (n_solid != 1) break;
+				bfc_kmer_append(k, x, last);
+			}
+		}
+		P.ext[job] = memo;
+	}
+	block_add(P.ctr + 1, n_lookups);
+}
+
 // ------------------------------------------------------------------ K6b: the search
 
 enum { PC_NEWJOB = 0, PC_POP, PC_STEP, PC_OWN_DONE, PC_AFTER_OWN, PC_ALT_NEXT, PC_ALT_DONE, PC_FINISH, PC_EXIT };
@@ -396,7 +444,7 @@ __device__ __forceinline__ int cand_weight(const EcParams &P, uint32_t c)
 
 __global__ void __launch_bounds__(EC_THREADS, EC_CTAS_PER_SM) k_ec_search(EcParams P)
 {
-	const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, n_slots = (int64_t)gridDim.x * blockDim.x;
+	const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	EcState *const pool = P.pool + slot * P.heap_cap;
 	__shared__ uint32_t s_hk[HK_SMEM][EC_THREADS];
 	KeyHeap heapk;
@@ -405,9 +453,10 @@ __global__ void __launch_bounds__(EC_THREADS, EC_CTAS_PER_SM) k_ec_search(EcPara
 	const int k = P.k;
 
 	// job context
-	int64_t job = slot - n_slots, o = 0;
+	int64_t job = 0, o = 0;
 	int jid = 0, n = 0, dir = 0, bp = -1, bb = 0;
 	bool memo_dir = false;
+	uint64_t ext = 0;
 	// search context (reference bfc_ec1dir locals)
 	EcState z;
 	int heap_n = 0, n_init = 0, n_edits = 0, max_heap = 0, n_fail = 0, n_paths = 0, rvl = -1;
@@ -615,7 +664,14 @@ __global__ void __launch_bounds__(EC_THREADS, EC_CTAS_PER_SM) k_ec_search(EcPara
 				pc = PC_NEWJOB;
 			}
 			if (pc == PC_NEWJOB) {
-				job += n_slots;
+				// jobs are handed out dynamically (their lengths vary by orders of magnitude): the lanes that arrive
+				// here together take consecutive jobs with one atomic
+				const unsigned am = __activemask(), ln = threadIdx.x & 31;
+				const int leader = __ffs(am) - 1;
+				unsigned long long first = 0;
+				if ((int)ln == leader) first = atomicAdd(P.ctr + 2, (unsigned long long)__popc(am));
+				first = __shfl_sync(am, first, leader);
+				job = (int64_t)(first + __popc(am & ((1u << ln) - 1)));
 				if (job >= P.n_jobs) { pc = PC_EXIT; yield = true; }
 				else {
 					jid = P.redo ? (int)P.redo[job] : (int)job;
@@ -627,6 +683,7 @@ __global__ void __launch_bounds__(EC_THREADS, EC_CTAS_PER_SM) k_ec_search(EcPara
 						bp = jr.w >= 0 ? jr.w >> 2 : -1, bb = jr.w & 3;
 						// the reverse-complement k-mer hashes like the forward one only for odd k (kmer.h:81)
 						memo_dir = dir == 0 || (k & 1) != 0;
+						ext = P.ext ? __ldg(P.ext + jid) : 0;
 						const int start = jr.z;
 						heap_n = n_init = n_edits = 0, max_heap = 0, n_fail = 0, n_paths = 0, rvl = -1, z_id = -1;
 						best_pen = INT_MAX, best_edit = -1, best_absent = 0, have_best = false;
@@ -688,6 +745,17 @@ __global__ void __launch_bounds__(EC_THREADS, EC_CTAS_PER_SM) k_ec_search(EcPara
 							} else osf = __ldg(P.fl + o + (dir ? f + k - 1 : f));
 						} else { req_b = cb; pc = PC_OWN_DONE; yield = true; }
 					}
+				} else if ((ext >> 63) && z.clean >= k - 1) {
+					// past the end with the read's own last k-1 bases (and k_ec_ext's bases after them): the four
+					// lookups of this position (correct.c:318-333) were made by k_ec_ext
+					const uint32_t m8 = (uint32_t)(ext >> (8 * (z.i - n))) & 0xff;
+#pragma unroll
+					for (int b = 0; b < 4; ++b)
+						if (m8 >> b & 1) cand |= (1u | ((m8 >> (4 + b) & 1) ? 16u : 0u)) << (8 * b), ++other_ext;
+					const uint32_t sol = m8 & 15;
+					cob = sol != 0 && (sol & (sol - 1)) == 0 ? __ffs(sol) - 1 : -1; // the base k_ec_ext went on with
+					fixed = z.i > n; // correct.c:295
+					pc = PC_FINISH;
 				}
 			}
 		}
@@ -810,11 +878,14 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 	// found on the device (one thread, a binary search per window) so the offsets never travel to the host
 	std::vector<uint64_t> cut_r, cut_b; // read index / byte offset of every window start, plus the end
 	if (host) {
-		for (int64_t r0 = 0; r0 < n;) {
-			int64_t r1 = r0 + 1;
-			while (r1 < n && batch->off[r1 + 1] - batch->off[r0] <= limit && r1 - r0 < (1LL << 30)) ++r1;
+		for (int64_t r0 = 0; r0 < n;) { // largest r1 in (r0, n] with off[r1] - off[r0] <= limit, at least r0 + 1
+			int64_t lo = r0 + 1, hi = n < r0 + (1LL << 30) ? n : r0 + (1LL << 30);
+			while (lo < hi) {
+				const int64_t mid = lo + (hi - lo + 1) / 2;
+				if (batch->off[mid] - batch->off[r0] <= limit) lo = mid; else hi = mid - 1;
+			}
 			cut_r.push_back(r0), cut_b.push_back(batch->off[r0]);
-			r0 = r1;
+			r0 = lo;
 		}
 		cut_r.push_back(n), cut_b.push_back(batch->off[n]);
 	} else {
@@ -836,7 +907,7 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 	const int heap_cap = opt->max_heap + 6; // the search never holds more than max_heap + 4 states
 	const int edit_cap = edit_cap0();
 
-	// one arena for every window: two sets of in/out buffers for host batches (window w+1 is copied in and
+	// one arena for every window: three sets of in/out buffers for host batches (window w+1 is copied in and
 	// window w-1 copied out, on their own streams, while window w is searched) + one set of scratch
 	uint64_t nb_max = 0;
 	int64_t nr_max = 0;
@@ -846,10 +917,11 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 	}
 	const uint64_t n_rec_max = enum_padded(nb_max), pl_words_max = (n_rec_max + PL_PAD) / 64 + 4;
 	const int64_t slots_max = std::min<int64_t>(max_slots, (2 * nr_max + threads - 1) / threads * threads);
-	size_t tot = 0, o_seq[2] = {0, 0}, o_qual[2] = {0, 0}, o_off[2] = {0, 0}, o_aux[2] = {0, 0};
-	size_t o_pl, o_fl, o_y0, o_y1, o_desc, o_jobs, o_res, o_pool, o_heapk, o_edits, o_ovf, o_ctr;
+	enum { NBUF = 3 };
+	size_t tot = 0, o_seq[NBUF] = {0}, o_qual[NBUF] = {0}, o_off[NBUF] = {0}, o_aux[NBUF] = {0};
+	size_t o_pl, o_fl, o_y0, o_y1, o_desc, o_jobs, o_res, o_ext, o_pool, o_heapk, o_edits, o_ovf, o_ctr;
 	if (host)
-		for (int b = 0; b < 2; ++b) {
+		for (int b = 0; b < NBUF; ++b) {
 			o_seq[b] = tot; tot = align_up(tot + nb_max, 256);
 			o_qual[b] = tot; tot = align_up(tot + nb_max, 256);
 			o_off[b] = tot; tot = align_up(tot + (nr_max + 1) * 8, 256);
@@ -862,6 +934,7 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 	o_desc = tot; tot = align_up(tot + nr_max * sizeof(ReadDesc), 256);
 	o_jobs = tot; tot = align_up(tot + 2 * nr_max * sizeof(int4), 256);
 	o_res = tot; tot = align_up(tot + 2 * nr_max * sizeof(int2), 256);
+	o_ext = tot; tot = align_up(tot + 2 * nr_max * 8, 256);
 	o_pool = tot; tot = align_up(tot + (size_t)slots_max * heap_cap * sizeof(EcState), 256);
 	o_heapk = tot; tot = align_up(tot + (size_t)slots_max * heap_cap * 4, 256);
 	o_edits = tot; tot = align_up(tot + (size_t)slots_max * edit_cap * sizeof(uint2), 256);
@@ -874,9 +947,9 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 	auto issue_copy_in = [&](size_t w) -> cudaError_t {
 		const int64_t r0 = (int64_t)cut_r[w], nr = (int64_t)cut_r[w + 1] - r0;
 		const uint64_t b0 = cut_b[w], nb = cut_b[w + 1] - b0;
-		const int b = (int)(w & 1);
+		const int b = (int)(w % NBUF);
 		cudaError_t ce;
-		if (w >= 2 && (ce = cudaStreamWaitEvent(rt.copy_in, rt.ev_out[b], 0)) != cudaSuccess) return ce; // buffer b was read out
+		if (w >= NBUF && (ce = cudaStreamWaitEvent(rt.copy_in, rt.ev_out[b], 0)) != cudaSuccess) return ce; // buffer b was read out
 		if ((ce = cudaMemcpyAsync(a + o_seq[b], batch->seq + b0, nb, cudaMemcpyHostToDevice, rt.copy_in)) != cudaSuccess) return ce;
 		if (batch->qual && (ce = cudaMemcpyAsync(a + o_qual[b], batch->qual + b0, nb, cudaMemcpyHostToDevice, rt.copy_in)) != cudaSuccess) return ce;
 		if ((ce = cudaMemcpyAsync(a + o_off[b], batch->off + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, rt.copy_in)) != cudaSuccess) return ce;
@@ -896,7 +969,7 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 		const uint64_t n_rec = enum_padded(nb);
 		const uint64_t pl_words = (n_rec + PL_PAD) / 64 + 4;
 		const int64_t slots = std::min<int64_t>(max_slots, (2 * nr + threads - 1) / threads * threads);
-		const int ib = (int)(w & 1);
+		const int ib = (int)(w % NBUF);
 
 		EcParams P;
 		memset(&P, 0, sizeof(P));
@@ -914,6 +987,7 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 		P.fl = (const uint16_t*)(a + o_fl);
 		P.desc = (ReadDesc*)(a + o_desc), P.jobs = (int4*)(a + o_jobs), P.res = (int2*)(a + o_res);
 		P.n_reads = nr, P.n_jobs = 2 * nr;
+		P.ext = opt->max_end_ext >= 0 && opt->max_end_ext < EC_EXT_STEPS && !getenv("BFC_B200_EC_NOEXT") ? (uint64_t*)(a + o_ext) : 0;
 		P.tab = tab_view(ch);
 		P.k = opt->k, P.q = opt->q, P.min_cov = opt->min_cov, P.win_multi_ec = opt->win_multi_ec, P.max_end_ext = opt->max_end_ext;
 		P.w_ec = opt->w_ec, P.w_ec_high = opt->w_ec_high, P.w_absent = opt->w_absent, P.w_absent_high = opt->w_absent_high;
@@ -945,6 +1019,10 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 		}
 		BFCG_LAUNCH_CHECK();
 		++rt.n_launches;
+		if (P.ext) {
+			{ KTime kt(KT_EC_EXT); k_ec_ext<<<(unsigned)((2 * nr + 255) / 256), 256, 0, rt.stream>>>(P); }
+			BFCG_LAUNCH_CHECK();
+		}
 		{ KTime kt(KT_CORRECT); k_ec_search<<<(unsigned)(slots / threads), threads, 0, rt.stream>>>(P); }
 		BFCG_LAUNCH_CHECK();
 		if (host && w + 1 < n_win) { // the next window travels while this one is searched (issued after the launches:
@@ -968,6 +1046,7 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 			BFCG_CUDA(cudaMalloc(&big, (size_t)rs * cap * sizeof(uint2)));
 			BFCG_CUDA(cudaMemcpyAsync(redo, P.overflow, n_redo * 4, cudaMemcpyDeviceToDevice, rt.stream));
 			BFCG_CUDA(cudaMemsetAsync(P.ctr, 0, 8, rt.stream));
+			BFCG_CUDA(cudaMemsetAsync(P.ctr + 2, 0, 8, rt.stream));
 			EcParams Q = P;
 			Q.redo = redo, Q.n_jobs = (int64_t)n_redo, Q.edits = big, Q.edit_cap = cap;
 			{ KTime kt(KT_CORRECT_REDO); k_ec_search<<<(unsigned)(rs / 32), 32, 0, rt.stream>>>(Q); }

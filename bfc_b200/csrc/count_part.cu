@@ -37,9 +37,7 @@
 #define EL_LEAD    64                            // plane bits in front of the segment (>= k - 1)
 #define EL_WORDS   ((EL_SEG + EL_LEAD) / 32 + 2)
 
-#define CP_SLOG2   10                            // log2(Bloom blocks per partition): 64 KB slices
-#define CP_BLOCKS  (1 << CP_SLOG2)
-#define CP_THREADS 256
+#define CP_SLOG2_MAX 10                          // log2(Bloom blocks per partition) <= 10: slices of at most 64 KB
 #define CP_BLK_BYTES 64                           // one Bloom block (bbf.h: 512 bits)
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -110,33 +108,58 @@ __global__ void __launch_bounds__(EL_THREADS) k_enum_lin(EnumLinParams p)
 
 // ------------------------------------------------------------------ K2': partition bounds
 
-__global__ void __launch_bounds__(256) k_part_bounds(const unsigned long long *y0, uint64_t n, uint32_t pmask, uint32_t *start, uint32_t *end)
+__global__ void __launch_bounds__(256) k_part_bounds(const unsigned long long *y0, uint64_t n, int shift, uint32_t pmask, uint32_t *start, uint32_t *end)
 {
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
-	const uint32_t p = (uint32_t)(__ldg(y0 + i) >> CP_SLOG2) & pmask;
-	if (i == 0 || ((uint32_t)(__ldg(y0 + i - 1) >> CP_SLOG2) & pmask) != p) start[p] = (uint32_t)i;
-	if (i + 1 == n || ((uint32_t)(__ldg(y0 + i + 1) >> CP_SLOG2) & pmask) != p) end[p] = (uint32_t)(i + 1);
+	const uint32_t p = (uint32_t)(__ldg(y0 + i) >> shift) & pmask;
+	if (i == 0 || ((uint32_t)(__ldg(y0 + i - 1) >> shift) & pmask) != p) start[p] = (uint32_t)i;
+	if (i + 1 == n || ((uint32_t)(__ldg(y0 + i + 1) >> shift) & pmask) != p) end[p] = (uint32_t)(i + 1);
 }
 
 // ------------------------------------------------------------------ K3': one CTA per partition
 
 struct PartParams {
-	const unsigned long long *y0, *y1; // records, stably partitioned
+	const unsigned long long *y0;      // records, stably partitioned
+	unsigned long long *y1;            //   y1 of a record that does not pass is overwritten with ~0 (normal mode)
 	const uint32_t *start, *end;       // record range per partition; 0 = a single partition [0, n_rec)
 	uint64_t n_rec;
 	uint32_t blocks_per_part;          // Bloom blocks per partition (power of two, <= CP_BLOCKS)
 	int k;
 	BloomView bf, bf_high;             // bf_high.w == 0 in normal mode
-	TabView tab;                       // tab.slots == 0 in trim mode
 	unsigned long long *ctr;           // [1] n_kmers [2] n_pass [3] occurrences that had to wait for an earlier one
 };
 
-__global__ void __launch_bounds__(CP_THREADS, 3) k_count_part(PartParams p)
+// reference bbf.c:35-42 on a block held in shared memory: test-then-set each probe, returns the number already set
+__device__ __forceinline__ int bloom_test_set_smem(uint32_t *w, int h1, int h2, int H)
+{
+	int z = h1, done = 0, cnt = 0;
+	while (done < H) {
+		if (z >= 8) {
+			const uint32_t bit = 1u << (z & 31), v = w[z >> 5];
+			cnt += (v & bit) != 0;
+			w[z >> 5] = v | bit;
+			++done;
+		}
+		z = (z + h2) & BFC_BLK_MASK;
+	}
+	return cnt;
+}
+
+// One round = CP_THREADS consecutive records of the partition.  Records whose bits are all set pass whatever the
+// order and write nothing.  Of the others, the EARLIEST of every block (shared-memory atomicMin claim) applies the
+// reference's test-then-set at once -- different blocks, disjoint words.  The few that lost a claim (a later
+// occurrence of the same block in the same round) are replayed afterwards by warp 0 in stream order: lane l walks
+// the losers' bitmap in ascending order and handles the blocks with index = l mod 32, so one block is always
+// replayed sequentially and different blocks in parallel.
+template <int CP_THREADS, int CP_MIN_CTAS, int CP_SLOG2>
+__global__ void __launch_bounds__(CP_THREADS, CP_MIN_CTAS) k_count_part(PartParams p)
 {
 	extern __shared__ __align__(16) uint32_t s_w[];  // the partition's slice of the filter: blocks_per_part x 16 words
-	__shared__ uint32_t s_claim[CP_BLOCKS];          // per block: lowest thread with a pending occurrence this round
-	const uint32_t part = blockIdx.x, nb = p.blocks_per_part, tid = threadIdx.x;
+	__shared__ uint32_t s_claim[1 << CP_SLOG2];      // per block: lowest thread with a pending occurrence this round
+	__shared__ uint32_t s_info[CP_THREADS];          // losers: block << 18 | h1 << 9 | h2
+	__shared__ uint32_t s_lose[CP_THREADS / 32], s_res[CP_THREADS / 32]; // bitmaps over the round's threads
+	const uint32_t part = blockIdx.x, nb = p.blocks_per_part, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	uint64_t beg = 0, end = p.n_rec;
 	if (p.start) beg = __ldg(p.start + part), end = __ldg(p.end + part);
 	if (beg >= end) return; // nothing for this slice in this window
@@ -144,8 +167,10 @@ __global__ void __launch_bounds__(CP_THREADS, 3) k_count_part(PartParams p)
 	uint4 *const s4 = (uint4*)s_w;
 	for (uint32_t i = tid; i < nb * 4; i += CP_THREADS) s4[i] = __ldcs(g4 + i);
 	for (uint32_t i = tid; i < nb; i += CP_THREADS) s_claim[i] = ~0u;
+	if (tid < CP_THREADS / 32) s_lose[tid] = 0, s_res[tid] = 0;
 	const int H = p.bf.n_hashes;
-	unsigned long long n_k = 0, n_pass = 0, n_new = 0, n_wait = 0;
+	const bool mark = p.bf_high.w == 0;
+	unsigned long long n_k = 0, n_pass = 0, n_wait = 0;
 	unsigned long long y0f = 0, y1 = ~0ULL;
 	if (beg + tid < end) y1 = __ldg(p.y1 + beg + tid), y0f = __ldg(p.y0 + beg + tid);
 	__syncthreads();
@@ -158,72 +183,105 @@ __global__ void __launch_bounds__(CP_THREADS, 3) k_count_part(PartParams p)
 		}
 		const bool valid = c1 != ~0ULL;
 		const uint64_t c0 = c0f & ~(1ULL << 63);
-		bool pass = false, pend = false, waited = false;
+		bool pass = false, pend = false;
 		BloomProbe pr;
 		pr.blk = 0, pr.h1 = pr.h2 = 0;
 		uint32_t lb = 0;
 		if (valid) {
 			pr = bloom_locate(hash_from_y(p.k, c0, c1), p.bf.n_shift);
 			lb = (uint32_t)pr.blk & (nb - 1);
-			// all bits already set: passes whatever the order, and writes nothing
-			pass = bloom_count_set<false>(s_w + (lb << 4), pr, H) == H;
+			pass = bloom_count_set<false>(s_w + (lb << 4), pr, H) == H; // all set: passes, writes nothing
 			pend = !pass;
 		}
-		// the others take turns per block in stream order (= thread order inside the round)
-		while (__syncthreads_or(pend)) {
+		if (__syncthreads_or(pend)) {
 			if (pend) atomicMin(&s_claim[lb], tid);
 			__syncthreads();
-			const bool win = pend && s_claim[lb] == tid;
-			if (win) { // reference bbf.c:35-42: test-then-set each probe; the only writer of this block now
-				uint32_t *w = s_w + (lb << 4);
-				int z = pr.h1, done = 0, cnt = 0;
-				while (done < H) {
-					if (z >= 8) {
-						const uint32_t bit = 1u << (z & 31), v = w[z >> 5];
-						cnt += (v & bit) != 0;
-						w[z >> 5] = v | bit;
-						++done;
-					}
-					z = (z + pr.h2) & BFC_BLK_MASK;
+			bool lost = false;
+			if (pend) {
+				if (s_claim[lb] == tid) pass = bloom_test_set_smem(s_w + (lb << 4), pr.h1, pr.h2, H) == H; // reference count.c:60
+				else {
+					lost = true;
+					s_info[tid] = lb << 18 | (uint32_t)pr.h1 << 9 | (uint32_t)pr.h2;
+					atomicOr(&s_lose[warp], 1u << lane);
 				}
-				pass = cnt == H; // reference count.c:60
-				pend = false;
-			} else if (pend) waited = true;
-			__syncthreads();
-			if (win) s_claim[lb] = ~0u;
+			}
+			if (__syncthreads_or(lost)) {
+				if (warp == 0) {
+					for (int wd = 0; wd < CP_THREADS / 32; ++wd)
+						for (uint32_t m = s_lose[wd]; m; m &= m - 1) {
+							const int t = wd * 32 + __ffs(m) - 1;
+							const uint32_t info = s_info[t];
+							if (((info >> 18) & 31) == lane && bloom_test_set_smem(s_w + ((info >> 18) << 4), info >> 9 & 511, info & 511, H) == H)
+								atomicOr(&s_res[wd], 1u << (t & 31));
+						}
+				}
+				__syncthreads();
+				if (lost) {
+					pass = s_res[warp] >> lane & 1;
+					atomicAnd(&s_lose[warp], ~(1u << lane));
+					atomicAnd(&s_res[warp], ~(1u << lane));
+					++n_wait;
+				}
+			}
+			if (pend && !lost) s_claim[lb] = ~0u; // the winner's claim; a loser's block was claimed by a winner
 		}
-		if (pass) {
-			if (p.tab.slots) n_new += tab_upsert(p.tab, c0, c1, (int)(c0f >> 63)) == 1;
-			else {
+		if (valid) {
+			if (mark) { if (!pass) p.y1[base + tid] = ~0ULL; } // the table upserts of the passing records follow in k_tab_apply_marked
+			else if (pass) {
 				const BloomProbe ph = bloom_locate(hash_from_y(p.k, c0, c1), p.bf_high.n_shift);
 				bloom_set_atomic(bloom_block(p.bf_high, ph.blk), ph, p.bf_high.n_hashes);
 			}
 		}
-		n_k += valid, n_pass += pass, n_wait += waited;
+		n_k += valid, n_pass += pass;
 	}
 	__syncthreads();
 	for (uint32_t i = tid; i < nb * 4; i += CP_THREADS) __stcs(g4 + i, s4[i]);
 	block_add(p.ctr + 1, n_k);
 	block_add(p.ctr + 2, n_pass);
 	block_add(p.ctr + 3, n_wait);
-	if (p.tab.slots) block_add(p.tab.counters, n_new);
+}
+
+// bfc_ch_insert (htab.c:60-82) for every record that passed, in partition order: a warp's 32 records belong to one
+// partition, whose sub-tables are neighbours in the table (tab_region), so the probes stay in L2
+__global__ void __launch_bounds__(256) k_tab_apply_marked(TabView t, const unsigned long long *y0, const unsigned long long *y1, uint64_t n)
+{
+	unsigned long long added = 0;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+		const unsigned long long b = __ldg(y1 + i);
+		if (b != ~0ULL) {
+			const unsigned long long a = __ldg(y0 + i);
+			added += tab_upsert(t, a & ~(1ULL << 63), b, (int)(a >> 63)) == 1;
+		}
+	}
+	block_add(t.counters, added);
 }
 
 // ------------------------------------------------------------------ host side
 
 struct PartGeom {
 	int x;              // log2(Bloom blocks this rank holds)
+	int slog2;          // log2(Bloom blocks per partition)
 	int pbits;          // log2(partitions)
+	int cfg;            // kernel variant
 	uint32_t n_parts, blocks_per_part;
 };
+
+// kernel variants (threads per CTA, CTAs per SM, slice): the launch geometry is a tuning knob, the results are the same
+static int part_cfg()
+{
+	const char *e = getenv("BFC_B200_PART_CFG");
+	return e && atoi(e) >= 0 && atoi(e) <= 4 ? atoi(e) : 3;
+}
 
 static PartGeom part_geom(const bfc_bf_t *bf, int owner_bits)
 {
 	PartGeom g;
+	g.cfg = part_cfg();
+	g.slog2 = g.cfg == 3 ? 8 : g.cfg == 2 || g.cfg == 4 ? 9 : 10;
 	g.x = bf->n_shift - BFC_BLK_SHIFT - owner_bits;
-	g.pbits = g.x > CP_SLOG2 ? g.x - CP_SLOG2 : 0;
+	g.pbits = g.x > g.slog2 ? g.x - g.slog2 : 0;
 	g.n_parts = 1u << g.pbits;
-	g.blocks_per_part = 1u << (g.x < CP_SLOG2 ? g.x : CP_SLOG2);
+	g.blocks_per_part = 1u << (g.x < g.slog2 ? g.x : g.slog2);
 	return g;
 }
 
@@ -233,7 +291,7 @@ bool bfcg_count_part_usable(const bfc_opt_t *opt, const bfc_bf_t *bf, int owner_
 	if (e && strcmp(e, "probe") == 0) return false;
 	const int x = bf->n_shift - BFC_BLK_SHIFT;
 	// the block index (bbf.c:27-28) must be a bit field of y0, and the partition index must fit the sort
-	return x <= opt->k && x - owner_bits >= 0 && x - owner_bits - CP_SLOG2 <= 30;
+	return x <= opt->k && x - owner_bits >= 0 && x - owner_bits <= 36;
 }
 
 struct PartScratch {
@@ -242,24 +300,24 @@ struct PartScratch {
 	size_t tmp_bytes;
 	uint32_t *bounds;                // start[n_parts], end[n_parts]
 	unsigned long long *ctr;
-	static size_t sort_temp(uint64_t n, int pbits)
+	static size_t sort_temp(uint64_t n, const PartGeom &g)
 	{
 		size_t t = 0;
-		if (pbits > 0)
+		if (g.pbits > 0)
 			cub::DeviceRadixSort::SortPairs((void*)0, t, (const unsigned long long*)0, (unsigned long long*)0,
-			                                (const unsigned long long*)0, (unsigned long long*)0, (int64_t)n, CP_SLOG2, CP_SLOG2 + pbits, bfcg_rt().stream);
+			                                (const unsigned long long*)0, (unsigned long long*)0, (int64_t)n, g.slog2, g.slog2 + g.pbits, bfcg_rt().stream);
 		return t;
 	}
 	static size_t bytes(uint64_t n, const PartGeom &g)
 	{
-		return 2 * align_up(n * 8, 256) + align_up(sort_temp(n, g.pbits), 256) + align_up((size_t)g.n_parts * 8, 256) + 256;
+		return 2 * align_up(n * 8, 256) + align_up(sort_temp(n, g), 256) + align_up((size_t)g.n_parts * 8, 256) + 256;
 	}
 	void carve(uint8_t *a, uint64_t n, const PartGeom &g)
 	{
 		size_t o = 0;
 		s_y0 = (unsigned long long*)(a + o); o += align_up(n * 8, 256);
 		s_y1 = (unsigned long long*)(a + o); o += align_up(n * 8, 256);
-		tmp_bytes = sort_temp(n, g.pbits);
+		tmp_bytes = sort_temp(n, g);
 		tmp = a + o; o += align_up(tmp_bytes, 256);
 		bounds = (uint32_t*)(a + o); o += align_up((size_t)g.n_parts * 8, 256);
 		ctr = (unsigned long long*)(a + o);
@@ -288,27 +346,39 @@ static int count_part_window(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_hi
 	p.k = opt->k, p.n_rec = n, p.blocks_per_part = g.blocks_per_part;
 	p.bf = bloom_view(bf), p.bf.blk_mask = blk_mask;
 	if (bf_high) p.bf_high = bloom_view(bf_high), p.bf_high.blk_mask = blk_mask;
-	if (ch) p.tab = tab_view(ch);
 	p.ctr = sc.ctr;
-	p.y0 = in_y0, p.y1 = in_y1;
+	p.y0 = in_y0, p.y1 = sc.s_y1;
 	if (g.pbits > 0) {
 		size_t tb = sc.tmp_bytes;
 		cudaError_t se;
 		{
 			KTime kt(KT_COUNT_SORT);
-			se = cub::DeviceRadixSort::SortPairs(sc.tmp, tb, in_y0, sc.s_y0, in_y1, sc.s_y1, (int64_t)n, CP_SLOG2, CP_SLOG2 + g.pbits, rt.stream);
+			se = cub::DeviceRadixSort::SortPairs(sc.tmp, tb, in_y0, sc.s_y0, in_y1, sc.s_y1, (int64_t)n, g.slog2, g.slog2 + g.pbits, rt.stream);
 		}
 		BFCG_CUDA(se);
 		rt.n_launches += 1 + (g.pbits + 7) / 8; // histogram + one onesweep pass per 8 bits
 		uint32_t *start = sc.bounds, *end = sc.bounds + g.n_parts;
 		BFCG_CUDA(cudaMemsetAsync(sc.bounds, 0, (size_t)g.n_parts * 8, rt.stream));
-		{ KTime kt(KT_COUNT_BOUNDS); k_part_bounds<<<(unsigned)((n + 255) / 256), 256, 0, rt.stream>>>(sc.s_y0, n, g.n_parts - 1, start, end); }
+		{ KTime kt(KT_COUNT_BOUNDS); k_part_bounds<<<(unsigned)((n + 255) / 256), 256, 0, rt.stream>>>(sc.s_y0, n, g.slog2, g.n_parts - 1, start, end); }
 		BFCG_LAUNCH_CHECK();
-		p.y0 = sc.s_y0, p.y1 = sc.s_y1, p.start = start, p.end = end;
-	}
+		p.y0 = sc.s_y0, p.start = start, p.end = end;
+	} else BFCG_CUDA(cudaMemcpyAsync(sc.s_y1, in_y1, n * 8, cudaMemcpyDeviceToDevice, rt.stream)); // k_count_part marks y1 in place
+
 	BFCG_CUDA(cudaMemsetAsync(p.ctr, 0, 64, rt.stream));
 	const size_t smem = (size_t)g.blocks_per_part * CP_BLK_BYTES;
-	{ KTime kt(KT_COUNT_PART); k_count_part<<<g.n_parts, CP_THREADS, smem, rt.stream>>>(p); }
+	{
+		KTime kt(KT_COUNT_PART);
+		if (g.cfg == 0) k_count_part<256, 3, 10><<<g.n_parts, 256, smem, rt.stream>>>(p);
+		else if (g.cfg == 1) k_count_part<512, 3, 10><<<g.n_parts, 512, smem, rt.stream>>>(p);
+		else if (g.cfg == 2) k_count_part<256, 6, 9><<<g.n_parts, 256, smem, rt.stream>>>(p);
+		else if (g.cfg == 3) k_count_part<128, 12, 8><<<g.n_parts, 128, smem, rt.stream>>>(p);
+		else k_count_part<128, 6, 9><<<g.n_parts, 128, smem, rt.stream>>>(p);
+	}
+	BFCG_LAUNCH_CHECK();
+	if (ch) {
+		KTime kt(KT_TAB_APPLY);
+		k_tab_apply_marked<<<(unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)rt.sm_count * 8), 256, 0, rt.stream>>>(tab_view(ch), p.y0, p.y1, n);
+	}
 	BFCG_LAUNCH_CHECK();
 	if (launched && (r = (*launched)()) != BFCG_OK) return r; // host work that should overlap the kernels just enqueued
 	unsigned long long c[4];
@@ -330,7 +400,11 @@ static int part_kernel_setup()
 {
 	static bool done = false;
 	if (!done) {
-		BFCG_CUDA(cudaFuncSetAttribute(k_count_part, cudaFuncAttributeMaxDynamicSharedMemorySize, CP_BLOCKS * CP_BLK_BYTES));
+		BFCG_CUDA(cudaFuncSetAttribute(k_count_part<256, 3, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * CP_BLK_BYTES));
+		BFCG_CUDA(cudaFuncSetAttribute(k_count_part<512, 3, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * CP_BLK_BYTES));
+		BFCG_CUDA(cudaFuncSetAttribute(k_count_part<256, 6, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * CP_BLK_BYTES));
+		BFCG_CUDA(cudaFuncSetAttribute(k_count_part<128, 12, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * CP_BLK_BYTES));
+		BFCG_CUDA(cudaFuncSetAttribute(k_count_part<128, 6, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * CP_BLK_BYTES));
 		done = true;
 	}
 	return BFCG_OK;
@@ -346,7 +420,7 @@ static uint64_t window_positions(uint64_t n_positions, bool host, const PartGeom
 		size_t fr = 0, tot = 0;
 		cudaMemGetInfo(&fr, &tot);
 		const double avail = 0.55 * (double)(fr + bfcg_rt().arena_bytes);
-		while (P > (1ULL << 22) && (double)(P * (host ? 36 : 32)) + (double)PartScratch::sort_temp(P, g.pbits) > avail) P >>= 1;
+		while (P > (1ULL << 22) && (double)(P * (host ? 36 : 32)) + (double)PartScratch::sort_temp(P, g) > avail) P >>= 1;
 	}
 	return std::min(P, el_padded(n_positions));
 }

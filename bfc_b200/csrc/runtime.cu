@@ -41,7 +41,7 @@ int bfcg_rt_init()
 	BFCG_CUDA(cudaStreamCreateWithFlags(&g_rt.copy_out, cudaStreamNonBlocking));
 	BFCG_CUDA(cudaEventCreate(&g_rt.ev0));
 	BFCG_CUDA(cudaEventCreate(&g_rt.ev1));
-	for (int i = 0; i < 2; ++i) {
+	for (int i = 0; i < 3; ++i) {
 		BFCG_CUDA(cudaEventCreateWithFlags(&g_rt.ev_in[i], cudaEventDisableTiming));
 		BFCG_CUDA(cudaEventCreateWithFlags(&g_rt.ev_free[i], cudaEventDisableTiming));
 		BFCG_CUDA(cudaEventCreateWithFlags(&g_rt.ev_done[i], cudaEventDisableTiming));

@@ -64,7 +64,8 @@ const char *bfcg_last_error(void);
  * 0 count_probe 1 count_resolve 2 conflict sort 3 count_replay 4 correct (search) 5 correct redo 6 trim
  * 7 table rehash 8 table hist 9 table deferred-apply 10 k-mer enumeration 11 correct: batched lookups
  * 12 correct: coverage flags + per-read setup 13 correct: merge + rewrite 14 sharded count: owner bucketing
- * 15 count: partition kernel (Bloom slices in shared memory) 16 count: partition bounds 17 count: stream-order enumeration.
+ * 15 count: partition kernel (Bloom slices in shared memory) 16 count: partition bounds 17 count: stream-order enumeration
+ * 18 correct: lookups past the end of the reads.
  * Returns the number of valid entries. */
 int  bfcg_kernel_times(double *ms, uint64_t *launches, int n);
 /* CUDA events on the engine's stream: record into slot 0..7, elapsed ms between two slots */
