@@ -125,26 +125,40 @@ __device__ __forceinline__ int bit1(const uint64_t *pl, int64_t pos)
 
 struct LookupParams {
 	TabView tab;
-	const unsigned long long *rec_y0, *rec_y1;
 	const uint8_t *seq, *qual;
 	uint64_t n_pos;
 	uint64_t *pl;
 	uint64_t pl_words;
-	int q, min_cov;
+	int k, q, min_cov;
 	unsigned long long *ctr;
 };
 
-__global__ void __launch_bounds__(ENUM_THREADS) k_ec_lookup(LookupParams p)
+// One CTA per EL_SEG stream positions: the window is staged as bit planes in shared memory (enum.cuh), the k-mer
+// ending at each position is cut out of them, hashed and looked up (bfc_ec_kcov's lookup, correct.c:106), and the
+// four things the search ever asks about a read k-mer's table value leave as plane words next to the base planes.
+__global__ void __launch_bounds__(EL_THREADS) k_ec_lookup(LookupParams p)
 {
-	__shared__ uint8_t s_fl[ENUM_SEG];
-	const uint64_t seg = blockIdx.x;
+	__shared__ uint32_t s_pl[4][EL_WORDS];
+	const int64_t seg0 = (int64_t)blockIdx.x * EL_SEG;
+	el_stage_planes(s_pl, p.seq, p.qual, p.n_pos, seg0, p.q);
+	uint32_t *pl32 = (uint32_t*)p.pl;
+	const uint64_t stride32 = p.pl_words * 2, w0 = (uint64_t)(seg0 + PL_PAD) / 32;
+	// the base planes of the segment: shared-memory word 2 + t = positions seg0 + 32 t ..
+	{
+		const int t = threadIdx.x;
+		pl32[PL_B0 * stride32 + w0 + t] = s_pl[0][2 + t], pl32[PL_B1 * stride32 + w0 + t] = s_pl[1][2 + t];
+		pl32[PL_NB * stride32 + w0 + t] = s_pl[2][2 + t], pl32[PL_Q * stride32 + w0 + t] = s_pl[3][2 + t];
+	}
+	const int k = p.k;
+	const uint64_t kmask = (1ULL << k) - 1;
 	unsigned long long n_lookups = 0;
-	for (int j = 0; j < ENUM_CHUNK; ++j) {
-		const uint64_t i = seg * ENUM_SEG + (uint64_t)j * ENUM_THREADS + threadIdx.x;
-		const unsigned long long y1 = __ldg(p.rec_y1 + i);
-		uint32_t f = 4; // bit 0 SOL, 1 HS, 2 A, 3 H
-		if (y1 != ~0ULL) {
-			const int r = tab_get(p.tab, __ldg(p.rec_y0 + i) & ~(1ULL << 63), y1);
+#pragma unroll 2
+	for (int j = 0; j < EL_ITERS; ++j) {
+		const uint32_t pp = (uint32_t)(j * EL_THREADS + threadIdx.x);
+		uint32_t f = 4; // bit 0 SOL, 1 HS, 2 A, 3 H; no k-mer or an absent one counts as "A" (os = -1 -> 255, correct.c:299-300)
+		uint64_t y[2];
+		if (el_kmer_at(s_pl, pp + EL_LEAD - (uint32_t)(k - 1), k, kmask, y)) {
+			const int r = tab_get(p.tab, y[0], y[1]);
 			if (r >= 0) {
 				const int cnt = r & 0xff, high = r >> 8 & 0x3f;
 				f = (cnt >= p.min_cov ? 1u : 0u) | (cnt >= p.min_cov && high >= p.min_cov + 1 ? 2u : 0u) |
@@ -152,26 +166,10 @@ __global__ void __launch_bounds__(ENUM_THREADS) k_ec_lookup(LookupParams p)
 			}
 			++n_lookups;
 		}
-		s_fl[threadIdx.x * ENUM_CHUNK + j] = (uint8_t)f;
-	}
-	__syncthreads();
-	uint32_t *pl32 = (uint32_t*)p.pl;
-	const uint64_t stride32 = p.pl_words * 2;
-	for (int idx = threadIdx.x; idx < ENUM_SEG; idx += ENUM_THREADS) {
-		const uint64_t pos = seg * ENUM_SEG + idx;
-		uint32_t c = 4, q = 0;
-		if (pos < p.n_pos) {
-			c = base_code(__ldg(p.seq + pos));
-			q = c < 4 && (p.qual == 0 || (int)__ldg(p.qual + pos) - 33 >= p.q);
-		}
-		const uint32_t f = s_fl[idx];
-		const uint32_t b0 = __ballot_sync(0xffffffffu, c & 1), b1 = __ballot_sync(0xffffffffu, c & 2);
-		const uint32_t nb = __ballot_sync(0xffffffffu, c > 3), bq = __ballot_sync(0xffffffffu, q);
 		const uint32_t sol = __ballot_sync(0xffffffffu, f & 1), hs = __ballot_sync(0xffffffffu, f & 2);
 		const uint32_t fa = __ballot_sync(0xffffffffu, f & 4), fh = __ballot_sync(0xffffffffu, f & 8);
 		if ((threadIdx.x & 31) == 0) {
-			uint32_t *w = pl32 + (pos + PL_PAD) / 32;
-			w[PL_B0 * stride32] = b0, w[PL_B1 * stride32] = b1, w[PL_NB * stride32] = nb, w[PL_Q * stride32] = bq;
+			uint32_t *w = pl32 + w0 + (pp >> 5);
 			w[PL_SOL * stride32] = sol, w[PL_HS * stride32] = hs, w[PL_A * stride32] = fa, w[PL_H * stride32] = fh;
 		}
 	}
@@ -915,11 +913,11 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 		nb_max = std::max<uint64_t>(nb_max, cut_b[w + 1] - cut_b[w]);
 		nr_max = std::max<int64_t>(nr_max, (int64_t)(cut_r[w + 1] - cut_r[w]));
 	}
-	const uint64_t n_rec_max = enum_padded(nb_max), pl_words_max = (n_rec_max + PL_PAD) / 64 + 4;
+	const uint64_t n_rec_max = el_padded(nb_max), pl_words_max = (n_rec_max + PL_PAD) / 64 + 4;
 	const int64_t slots_max = std::min<int64_t>(max_slots, (2 * nr_max + threads - 1) / threads * threads);
 	enum { NBUF = 3 };
 	size_t tot = 0, o_seq[NBUF] = {0}, o_qual[NBUF] = {0}, o_off[NBUF] = {0}, o_aux[NBUF] = {0};
-	size_t o_pl, o_fl, o_y0, o_y1, o_desc, o_jobs, o_res, o_ext, o_pool, o_heapk, o_edits, o_ovf, o_ctr;
+	size_t o_pl, o_fl, o_desc, o_jobs, o_res, o_ext, o_pool, o_heapk, o_edits, o_ovf, o_ctr;
 	if (host)
 		for (int b = 0; b < NBUF; ++b) {
 			o_seq[b] = tot; tot = align_up(tot + nb_max, 256);
@@ -929,8 +927,6 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 		}
 	o_pl = tot; tot = align_up(tot + (size_t)PL_N * pl_words_max * 8, 256);
 	o_fl = tot; tot = align_up(tot + n_rec_max * 2, 256);
-	o_y0 = tot; tot = align_up(tot + n_rec_max * 8, 256);
-	o_y1 = tot; tot = align_up(tot + n_rec_max * 8, 256);
 	o_desc = tot; tot = align_up(tot + nr_max * sizeof(ReadDesc), 256);
 	o_jobs = tot; tot = align_up(tot + 2 * nr_max * sizeof(int4), 256);
 	o_res = tot; tot = align_up(tot + 2 * nr_max * sizeof(int2), 256);
@@ -944,6 +940,15 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 	if (!a) return BFCG_ERR_NOMEM;
 
 	const size_t n_win = cut_r.size() - 1;
+	// the per-read stats of a host batch come back through a pinned ring: a copy straight into pageable caller
+	// memory would block the host until the window is done, and the next window's kernels with it
+	uint32_t *pin_aux = 0;
+	if (host && !(pin_aux = (uint32_t*)bfcg_pinned(0, (size_t)NBUF * nr_max * 8))) return BFCG_ERR_NOMEM;
+	auto drain_aux = [&](size_t w) { // window w's stats: pinned ring -> caller
+		const int64_t r0 = (int64_t)cut_r[w], nr = (int64_t)cut_r[w + 1] - r0;
+		cudaEventSynchronize(rt.ev_out[w % NBUF]);
+		memcpy(aux + 2 * r0, pin_aux + (size_t)(w % NBUF) * nr_max * 2, (size_t)nr * 8);
+	};
 	auto issue_copy_in = [&](size_t w) -> cudaError_t {
 		const int64_t r0 = (int64_t)cut_r[w], nr = (int64_t)cut_r[w + 1] - r0;
 		const uint64_t b0 = cut_b[w], nb = cut_b[w + 1] - b0;
@@ -966,7 +971,7 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 		const int64_t r0 = (int64_t)cut_r[w], r1 = (int64_t)cut_r[w + 1];
 		const int64_t nr = r1 - r0;
 		const uint64_t b0 = cut_b[w], nb = cut_b[w + 1] - b0;
-		const uint64_t n_rec = enum_padded(nb);
+		const uint64_t n_rec = el_padded(nb);
 		const uint64_t pl_words = (n_rec + PL_PAD) / 64 + 4;
 		const int64_t slots = std::min<int64_t>(max_slots, (2 * nr + threads - 1) / threads * threads);
 		const int ib = (int)(w % NBUF);
@@ -1000,17 +1005,10 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 
 		const uint8_t *w_seq = host ? a + o_seq[ib] : batch->seq + b0;
 		const uint8_t *w_qual = host ? (batch->qual ? a + o_qual[ib] : 0) : (batch->qual ? batch->qual + b0 : 0);
-		EnumParams ep;
-		memset(&ep, 0, sizeof(ep));
-		ep.seq = w_seq, ep.qual = 0; // the quality flag of a record is not used here
-		ep.len = nb, ep.emit_from = 0, ep.k = opt->k, ep.q = opt->q;
-		ep.rec_y0 = (unsigned long long*)(a + o_y0), ep.rec_y1 = (unsigned long long*)(a + o_y1);
-		{ KTime kt(KT_ENUM); k_enum<<<(unsigned)(n_rec / ENUM_SEG), ENUM_THREADS, 0, rt.stream>>>(ep); }
-		BFCG_LAUNCH_CHECK();
 		LookupParams lp;
-		lp.tab = P.tab, lp.rec_y0 = ep.rec_y0, lp.rec_y1 = ep.rec_y1, lp.seq = w_seq, lp.qual = w_qual, lp.n_pos = nb;
-		lp.pl = (uint64_t*)(a + o_pl), lp.pl_words = pl_words, lp.q = opt->q, lp.min_cov = opt->min_cov, lp.ctr = P.ctr;
-		{ KTime kt(KT_EC_LOOKUP); k_ec_lookup<<<(unsigned)(n_rec / ENUM_SEG), ENUM_THREADS, 0, rt.stream>>>(lp); }
+		lp.tab = P.tab, lp.seq = w_seq, lp.qual = w_qual, lp.n_pos = nb;
+		lp.pl = (uint64_t*)(a + o_pl), lp.pl_words = pl_words, lp.k = opt->k, lp.q = opt->q, lp.min_cov = opt->min_cov, lp.ctr = P.ctr;
+		{ KTime kt(KT_EC_LOOKUP); k_ec_lookup<<<(unsigned)(n_rec / EL_SEG), EL_THREADS, 0, rt.stream>>>(lp); }
 		BFCG_LAUNCH_CHECK();
 		{
 			KTime kt(KT_EC_SETUP);
@@ -1029,6 +1027,7 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 			const cudaError_t ce = issue_copy_in(w + 1); // a copy from pageable memory blocks the host, not the GPU)
 			if (ce != cudaSuccess) { rc = bfcg_fail(__func__, "staging copy", ce); break; }
 		}
+		if (host && w >= 1) drain_aux(w - 1);
 		unsigned long long c[2];
 		BFCG_CUDA(cudaMemcpyAsync(c, P.ctr, sizeof(c), cudaMemcpyDeviceToHost, rt.stream));
 		BFCG_CUDA(cudaStreamSynchronize(rt.stream));
@@ -1063,13 +1062,14 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 			if (ce == cudaSuccess) ce = cudaStreamWaitEvent(rt.copy_out, rt.ev_done[ib], 0);
 			if (ce == cudaSuccess) ce = cudaMemcpyAsync(batch->seq + b0, a + o_seq[ib], nb, cudaMemcpyDeviceToHost, rt.copy_out);
 			if (ce == cudaSuccess && batch->qual) ce = cudaMemcpyAsync(batch->qual + b0, a + o_qual[ib], nb, cudaMemcpyDeviceToHost, rt.copy_out);
-			if (ce == cudaSuccess) ce = cudaMemcpyAsync(aux + 2 * r0, a + o_aux[ib], nr * 8, cudaMemcpyDeviceToHost, rt.copy_out);
+			if (ce == cudaSuccess) ce = cudaMemcpyAsync(pin_aux + (size_t)ib * nr_max * 2, a + o_aux[ib], nr * 8, cudaMemcpyDeviceToHost, rt.copy_out);
 			if (ce == cudaSuccess) ce = cudaEventRecord(rt.ev_out[ib], rt.copy_out);
 			if (ce != cudaSuccess) { rc = bfcg_fail(__func__, "copy out", ce); break; }
 		}
 	}
 	if (host) { cudaStreamSynchronize(rt.copy_in); cudaStreamSynchronize(rt.copy_out); }
 	if (rc != BFCG_OK) { cudaStreamSynchronize(rt.stream); return rc; }
+	if (host) drain_aux(n_win - 1);
 	timer.stop();
 	BFCG_CUDA(cudaStreamSynchronize(rt.stream));
 	return BFCG_OK;

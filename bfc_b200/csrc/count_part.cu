@@ -27,21 +27,15 @@
 // index to be a bit field of y0 (n_shift - 9 <= k); otherwise count.cu's probe/resolve/
 // replay path (random access, same results) is used.
 #include "common.cuh"
+#include "enum.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
 #include <functional>
-
-#define EL_THREADS 256
-#define EL_ITERS   32
-#define EL_SEG     (EL_THREADS * EL_ITERS)       // stream positions per CTA
-#define EL_LEAD    64                            // plane bits in front of the segment (>= k - 1)
-#define EL_WORDS   ((EL_SEG + EL_LEAD) / 32 + 2)
 
 #define CP_SLOG2_MAX 10                          // log2(Bloom blocks per partition) <= 10: slices of at most 64 KB
 #define CP_BLK_BYTES 64                           // one Bloom block (bbf.h: 512 bits)
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-static inline uint64_t el_padded(uint64_t n_positions) { return (n_positions + EL_SEG - 1) / EL_SEG * EL_SEG; }
 
 // ------------------------------------------------------------------ K0': enumeration in stream order
 
@@ -53,14 +47,6 @@ struct EnumLinParams {
 	unsigned long long *rec_y0, *rec_y1;
 };
 
-// 64 plane bits starting at bit index `bit`
-__device__ __forceinline__ uint64_t win64(const uint32_t *pl, uint32_t bit)
-{
-	const uint32_t w = bit >> 5, r = bit & 31;
-	const uint32_t a = pl[w], b = pl[w + 1], c = pl[w + 2];
-	return (uint64_t)__funnelshift_r(b, c, r) << 32 | __funnelshift_r(a, b, r);
-}
-
 // What worker_count does per base (count.c:76-88): map the character (bseq.c:9-26), restart on
 // a non-ACGT one, and once k bases are in, hash the canonical k-mer (kmer.h:79-88) with
 // is_high = all k bases have Q >= q.  Instead of rolling, the k-mer ending at a position is cut
@@ -69,20 +55,7 @@ __global__ void __launch_bounds__(EL_THREADS) k_enum_lin(EnumLinParams p)
 {
 	__shared__ uint32_t s_pl[4][EL_WORDS]; // B0, B1 (base code bits), NB (not ACGT / outside), Q (Q >= q)
 	const int64_t seg0 = (int64_t)p.emit_from + (int64_t)blockIdx.x * EL_SEG;
-	const unsigned lane = threadIdx.x & 31;
-	if (threadIdx.x < 8) s_pl[threadIdx.x & 3][EL_WORDS - 1 - (threadIdx.x >> 2)] = 0;
-	for (int i = threadIdx.x; i < EL_SEG + EL_LEAD; i += EL_THREADS) { // whole warps in or out
-		const int64_t pos = seg0 - EL_LEAD + i;
-		uint32_t c = 4, q = 0;
-		if (pos >= 0 && (uint64_t)pos < p.len) {
-			c = base_code(__ldg(p.seq + pos));
-			q = c < 4 && (p.qual == 0 || (int)__ldg(p.qual + pos) - 33 >= p.q);
-		}
-		const uint32_t b0 = __ballot_sync(0xffffffffu, c & 1), b1 = __ballot_sync(0xffffffffu, c & 2);
-		const uint32_t nb = __ballot_sync(0xffffffffu, c > 3), bq = __ballot_sync(0xffffffffu, q);
-		if (lane == 0) s_pl[0][i >> 5] = b0, s_pl[1][i >> 5] = b1, s_pl[2][i >> 5] = nb, s_pl[3][i >> 5] = bq;
-	}
-	__syncthreads();
+	el_stage_planes(s_pl, p.seq, p.qual, p.len, seg0, p.q);
 	const int k = p.k;
 	const uint64_t kmask = (1ULL << k) - 1;
 	unsigned long long *o0 = p.rec_y0 + (uint64_t)blockIdx.x * EL_SEG + threadIdx.x;
@@ -94,13 +67,7 @@ __global__ void __launch_bounds__(EL_THREADS) k_enum_lin(EnumLinParams p)
 		// a position where no k-mer ends still gets a record (y1 = ~0); its y0 is spread so that the
 		// partitions stay balanced
 		uint64_t y[2] = { ((uint64_t)(seg0 + pp) * 0x9E3779B97F4A7C15ULL) >> 1, ~0ULL };
-		if ((win64(s_pl[2], bit) & kmask) == 0) {
-			const uint64_t w0 = win64(s_pl[0], bit) & kmask, w1 = win64(s_pl[1], bit) & kmask;
-			const uint64_t qw = win64(s_pl[3], bit) & kmask;
-			const uint64_t x[4] = { __brevll(w0) >> (64 - k), __brevll(w1) >> (64 - k), ~w0 & kmask, ~w1 & kmask };
-			bfc_kmer_hash(k, x, y);
-			y[0] |= (unsigned long long)(qw == kmask) << 63;
-		}
+		if (el_kmer_at(s_pl, bit, k, kmask, y)) y[0] |= (unsigned long long)((win64(s_pl[3], bit) & kmask) == kmask) << 63;
 		o0[j * EL_THREADS] = y[0];
 		o1[j * EL_THREADS] = y[1];
 	}
@@ -243,7 +210,7 @@ __global__ void __launch_bounds__(CP_THREADS, CP_MIN_CTAS) k_count_part(PartPara
 
 // bfc_ch_insert (htab.c:60-82) for every record that passed, in partition order: a warp's 32 records belong to one
 // partition, whose sub-tables are neighbours in the table (tab_region), so the probes stay in L2
-__global__ void __launch_bounds__(256) k_tab_apply_marked(TabView t, const unsigned long long *y0, const unsigned long long *y1, uint64_t n)
+__global__ void __launch_bounds__(256, 6) k_tab_apply_marked(TabView t, const unsigned long long *y0, const unsigned long long *y1, uint64_t n)
 {
 	unsigned long long added = 0;
 	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -377,7 +344,7 @@ static int count_part_window(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_hi
 	BFCG_LAUNCH_CHECK();
 	if (ch) {
 		KTime kt(KT_TAB_APPLY);
-		k_tab_apply_marked<<<(unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)rt.sm_count * 8), 256, 0, rt.stream>>>(tab_view(ch), p.y0, p.y1, n);
+		k_tab_apply_marked<<<(unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)rt.sm_count * 6), 256, 0, rt.stream>>>(tab_view(ch), p.y0, p.y1, n);
 	}
 	BFCG_LAUNCH_CHECK();
 	if (launched && (r = (*launched)()) != BFCG_OK) return r; // host work that should overlap the kernels just enqueued

@@ -46,7 +46,57 @@ __host__ __device__ __forceinline__ uint64_t enum_record_of_pos(uint64_t pos)
 	return seg * ENUM_SEG + (rem % ENUM_CHUNK) * ENUM_THREADS + rem / ENUM_CHUNK;
 }
 
+// ---- stream-order enumeration from bit planes (k_enum_lin in count_part.cu, k_ec_lookup in correct.cu)
+#define EL_THREADS 256
+#define EL_ITERS   32
+#define EL_SEG     (EL_THREADS * EL_ITERS)       // stream positions per CTA
+#define EL_LEAD    64                            // plane bits in front of the segment (>= k - 1)
+#define EL_WORDS   ((EL_SEG + EL_LEAD) / 32 + 2)
+
+static inline uint64_t el_padded(uint64_t n_positions) { return (n_positions + EL_SEG - 1) / EL_SEG * EL_SEG; }
+
 #ifdef __CUDACC__
+// 64 plane bits starting at bit index `bit`
+__device__ __forceinline__ uint64_t win64(const uint32_t *pl, uint32_t bit)
+{
+	const uint32_t w = bit >> 5, r = bit & 31;
+	const uint32_t a = pl[w], b = pl[w + 1], c = pl[w + 2];
+	return (uint64_t)__funnelshift_r(b, c, r) << 32 | __funnelshift_r(a, b, r);
+}
+
+// Stage EL_LEAD + EL_SEG stream positions starting at seg0 - EL_LEAD as four bit planes in shared memory: B0, B1
+// (base code bits, bseq.c:9-26), NB (not ACGT, or outside [0, len)), Q (an ACGT base with Q >= q; every ACGT base
+// when qual == 0).  Bit i of a plane = position seg0 - EL_LEAD + i.  Ends with a __syncthreads().
+__device__ __forceinline__ void el_stage_planes(uint32_t (*s_pl)[EL_WORDS], const uint8_t *seq, const uint8_t *qual, uint64_t len, int64_t seg0, int q_min)
+{
+	const unsigned lane = threadIdx.x & 31;
+	if (threadIdx.x < 8) s_pl[threadIdx.x & 3][EL_WORDS - 1 - (threadIdx.x >> 2)] = 0;
+	for (int i = threadIdx.x; i < EL_SEG + EL_LEAD; i += EL_THREADS) { // whole warps in or out
+		const int64_t pos = seg0 - EL_LEAD + i;
+		uint32_t c = 4, q = 0;
+		if (pos >= 0 && (uint64_t)pos < len) {
+			c = base_code(__ldg(seq + pos));
+			q = c < 4 && (qual == 0 || (int)__ldg(qual + pos) - 33 >= q_min);
+		}
+		const uint32_t b0 = __ballot_sync(0xffffffffu, c & 1), b1 = __ballot_sync(0xffffffffu, c & 2);
+		const uint32_t nb = __ballot_sync(0xffffffffu, c > 3), bq = __ballot_sync(0xffffffffu, q);
+		if (lane == 0) s_pl[0][i >> 5] = b0, s_pl[1][i >> 5] = b1, s_pl[2][i >> 5] = nb, s_pl[3][i >> 5] = bq;
+	}
+	__syncthreads();
+}
+
+// The canonical k-mer hash (kmer.h:79-88) of the k bases whose oldest one is plane bit `bit`; false when one of them
+// is not ACGT.  The 4-plane k-mer (kmer.h:10-17) is cut out of the base planes: forward planes = the window
+// bit-reversed (newest base at bit 0), reverse-complement planes = the window complemented (newest base at bit k-1).
+__device__ __forceinline__ bool el_kmer_at(const uint32_t (*s_pl)[EL_WORDS], uint32_t bit, int k, uint64_t kmask, uint64_t y[2])
+{
+	if ((win64(s_pl[2], bit) & kmask) != 0) return false;
+	const uint64_t w0 = win64(s_pl[0], bit) & kmask, w1 = win64(s_pl[1], bit) & kmask;
+	const uint64_t x[4] = { __brevll(w0) >> (64 - k), __brevll(w1) >> (64 - k), ~w0 & kmask, ~w1 & kmask };
+	bfc_kmer_hash(k, x, y);
+	return true;
+}
+
 static __global__ void __launch_bounds__(ENUM_THREADS) k_enum(EnumParams p)
 {
 	__shared__ uint8_t s_code[ENUM_SEG + ENUM_HALO_MAX];
