@@ -850,7 +850,7 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 static uint64_t batch_bytes_limit()
 {
 	const char *e = getenv("BFC_B200_EC_BATCH");
-	return e && atoll(e) >= 4096 ? (uint64_t)atoll(e) : 1ULL << 28;
+	return e && atoll(e) >= 4096 && atoll(e) <= (1LL << 30) ? (uint64_t)atoll(e) : 1ULL << 30; // window offsets are 31-bit
 }
 
 static int edit_cap0()

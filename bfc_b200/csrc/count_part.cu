@@ -210,7 +210,8 @@ __global__ void __launch_bounds__(CP_THREADS, CP_MIN_CTAS) k_count_part(PartPara
 
 // bfc_ch_insert (htab.c:60-82) for every record that passed, in partition order: a warp's 32 records belong to one
 // partition, whose sub-tables are neighbours in the table (tab_region), so the probes stay in L2
-__global__ void __launch_bounds__(256, 6) k_tab_apply_marked(TabView t, const unsigned long long *y0, const unsigned long long *y1, uint64_t n)
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(256, MIN_CTAS) k_tab_apply_marked(TabView t, const unsigned long long *y0, const unsigned long long *y1, uint64_t n)
 {
 	unsigned long long added = 0;
 	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -344,7 +345,8 @@ static int count_part_window(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_hi
 	BFCG_LAUNCH_CHECK();
 	if (ch) {
 		KTime kt(KT_TAB_APPLY);
-		k_tab_apply_marked<<<(unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)rt.sm_count * 6), 256, 0, rt.stream>>>(tab_view(ch), p.y0, p.y1, n);
+		// latency-bound (a load, then a CAS, per record): as many threads as the register file takes
+		k_tab_apply_marked<8><<<(unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)rt.sm_count * 8), 256, 0, rt.stream>>>(tab_view(ch), p.y0, p.y1, n);
 	}
 	BFCG_LAUNCH_CHECK();
 	if (launched && (r = (*launched)()) != BFCG_OK) return r; // host work that should overlap the kernels just enqueued
