@@ -320,14 +320,24 @@ def main():
         r0, r1 = 0, n_mine
 
         def step():
+            t0 = time.perf_counter()
             be.reset()
             cudart.cudaMemcpy(C.c_void_p(w_seq), C.c_void_p(src_seq), C.c_size_t(nb_mine), 3)
             cudart.cudaMemcpy(C.c_void_p(w_qual), C.c_void_p(src_qual), C.c_size_t(nb_mine), 3)
+            t1 = time.perf_counter()
             for b in count_pieces:
                 sc.count_piece(b)
+            L.bfcg_sync()
+            t2 = time.perf_counter()
             sc.gather()
+            L.bfcg_sync()
+            t3 = time.perf_counter()
             if n_mine:
                 be.correct_batch(work_b, d_aux)
+            if sc.prof is not None and rank == 0:
+                print("[dist profile] reset+copy %.3f count %.3f gather %.3f correct %.3f s; phases %s" % (
+                    t1 - t0, t2 - t1, t3 - t2, time.perf_counter() - t3, {k_: round(v, 3) for k_, v in sc.prof.items()}), file=sys.stderr)
+                sc.prof.clear()
 
         def get_stats():
             return be.stats.as_dict()

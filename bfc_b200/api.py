@@ -116,6 +116,8 @@ def lib():
     L.bfcg_trim_batch.argtypes = [C.POINTER(Opt), C.POINTER(BF), C.POINTER(Batch), C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.POINTER(Stats)]
     L.bfcg_enum_records.argtypes = [C.POINTER(Opt), C.POINTER(Batch), C.c_int, C.c_void_p, C.c_void_p, u64p]
+    L.bfcg_count_record_runs.argtypes = [C.POINTER(Opt), C.POINTER(BF), C.POINTER(BF), C.c_void_p, C.c_int, u64p,
+                                         C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Stats)]
     L.bfcg_count_records.argtypes = [C.POINTER(Opt), C.POINTER(BF), C.POINTER(BF), C.c_void_p, C.c_uint64,
                                      C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Stats)]
     L.bfcg_bf_init_shard.restype = C.POINTER(BF)

@@ -147,10 +147,13 @@ int bfcg_tab_align_to_filter(bfc_ch_s *ch, int x);
 int bfcg_tab_drain_deferred(bfc_ch_s *ch);
 
 // the partitioned count path (count_part.cu); count.cu dispatches to it when it applies
-bool bfcg_count_part_usable(const bfc_opt_t *opt, const bfc_bf_t *bf, int owner_bits);
+bool bfcg_count_part_usable(const bfc_opt_t *opt, int n_shift, int owner_bits);
 int bfcg_count_part_batch(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, bfc_ch_t *ch, const bfcg_batch_t *batch, bfcg_stats_t *stats);
 int bfcg_count_part_records(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, bfc_ch_t *ch, uint64_t n_rec,
                             const uint64_t *d_y0, const uint64_t *d_y1, int owner_bits, bfcg_stats_t *stats);
+int bfcg_enum_part_records(const bfc_opt_t *opt, const bfcg_batch_t *batch, int owner_bits, uint64_t *d_y0, uint64_t *d_y1, uint64_t *counts);
+int bfcg_count_part_runs(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, bfc_ch_t *ch, int n_runs, const uint64_t *run_counts,
+                         const uint64_t *d_y0, uint64_t *d_y1, int owner_bits, bfcg_stats_t *stats);
 
 #ifdef __CUDACC__
 

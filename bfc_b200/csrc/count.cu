@@ -259,7 +259,7 @@ extern "C" int bfcg_count_batch(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf
 	if (!batch || !count_args_ok(opt, bf, bf_high, ch))
 		return bfcg_fail(__func__, "invalid arguments", cudaSuccess), BFCG_ERR_ARG;
 	if (batch->n_bytes == 0) return BFCG_OK;
-	if (bfcg_count_part_usable(opt, bf, 0)) return bfcg_count_part_batch(opt, bf, bf_high, ch, batch, stats);
+	if (bfcg_count_part_usable(opt, bf->n_shift, 0)) return bfcg_count_part_batch(opt, bf, bf_high, ch, batch, stats);
 
 	const uint64_t sub = sub_batch_positions(opt);
 	const uint64_t halo = opt->k - 1;
@@ -422,6 +422,7 @@ extern "C" int bfcg_enum_records(const bfc_opt_t *opt, const bfcg_batch_t *batch
 		return bfcg_fail(__func__, "invalid arguments (owners must be 1, 2, 4 or 8; at most 2^31 bytes per call)", cudaSuccess), BFCG_ERR_ARG;
 	for (int o = 0; o < n_owners; ++o) counts[o] = 0;
 	if (batch->n_bytes == 0) return BFCG_OK;
+	if (bfcg_count_part_usable(opt, opt->bf_shift, owner_bits)) return bfcg_enum_part_records(opt, batch, owner_bits, d_y0, d_y1, counts);
 	const bool host = batch->where == BFCG_HOST;
 	const uint64_t nb = batch->n_bytes, n_rec = enum_padded(nb), n_seg = n_rec / ENUM_SEG;
 	size_t o_seq = 0, o_qual = 0, o_y0, o_y1, o_cnt, o_tot, tot = 0;
@@ -477,7 +478,7 @@ extern "C" int bfcg_count_records(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *
 	if (!count_args_ok(opt, bf, bf_high, ch) || owner_bits < 0 || bf->n_shift - BFC_BLK_SHIFT < owner_bits || (n_rec && (!d_y0 || !d_y1)))
 		return bfcg_fail(__func__, "invalid arguments", cudaSuccess), BFCG_ERR_ARG;
 	if (n_rec == 0) return BFCG_OK;
-	if (bfcg_count_part_usable(opt, bf, owner_bits)) return bfcg_count_part_records(opt, bf, bf_high, ch, n_rec, d_y0, d_y1, owner_bits, stats);
+	if (bfcg_count_part_usable(opt, bf->n_shift, owner_bits)) return bfcg_count_part_records(opt, bf, bf_high, ch, n_rec, d_y0, d_y1, owner_bits, stats);
 	const uint64_t sub = std::min<uint64_t>(sub_batch_positions(opt), 1ULL << 31);
 	const uint64_t rec_max = std::min<uint64_t>(sub, n_rec);
 	CountScratch sc;
@@ -499,4 +500,20 @@ extern "C" int bfcg_count_records(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *
 	timer.stop();
 	BFCG_CUDA(cudaStreamSynchronize(rt.stream));
 	return BFCG_OK;
+}
+
+extern "C" int bfcg_count_record_runs(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, bfc_ch_t *ch, int n_runs, const uint64_t *run_counts,
+                                      uint64_t *d_y0, uint64_t *d_y1, int n_owners, bfcg_stats_t *stats)
+{
+	int r;
+	if ((r = bfcg_rt_init()) != BFCG_OK) return r;
+	const int owner_bits = log2_exact(n_owners);
+	if (!count_args_ok(opt, bf, bf_high, ch) || owner_bits < 0 || bf->n_shift - BFC_BLK_SHIFT < owner_bits || n_runs < 1 || n_runs > BK_MAX_OWNERS || !run_counts)
+		return bfcg_fail(__func__, "invalid arguments", cudaSuccess), BFCG_ERR_ARG;
+	uint64_t n = 0;
+	for (int i = 0; i < n_runs; ++i) n += run_counts[i];
+	if (n && (!d_y0 || !d_y1)) return bfcg_fail(__func__, "invalid arguments", cudaSuccess), BFCG_ERR_ARG;
+	if (bfcg_count_part_usable(opt, bf->n_shift, owner_bits))
+		return bfcg_count_part_runs(opt, bf, bf_high, ch, n_runs, run_counts, d_y0, d_y1, owner_bits, stats);
+	return bfcg_count_records(opt, bf, bf_high, ch, n, d_y0, d_y1, n_owners, stats); // pieces in stream order
 }

@@ -75,13 +75,13 @@ __global__ void __launch_bounds__(EL_THREADS) k_enum_lin(EnumLinParams p)
 
 // ------------------------------------------------------------------ K2': partition bounds
 
-__global__ void __launch_bounds__(256) k_part_bounds(const unsigned long long *y0, uint64_t n, int shift, uint32_t pmask, uint32_t *start, uint32_t *end)
+__global__ void __launch_bounds__(256) k_part_bounds(const unsigned long long *y0, uint64_t n, uint64_t base, int shift, uint32_t pmask, uint32_t *start, uint32_t *end)
 {
-	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; // y0 points at record `base` of the array the bounds refer to
 	if (i >= n) return;
 	const uint32_t p = (uint32_t)(__ldg(y0 + i) >> shift) & pmask;
-	if (i == 0 || ((uint32_t)(__ldg(y0 + i - 1) >> shift) & pmask) != p) start[p] = (uint32_t)i;
-	if (i + 1 == n || ((uint32_t)(__ldg(y0 + i + 1) >> shift) & pmask) != p) end[p] = (uint32_t)(i + 1);
+	if (i == 0 || ((uint32_t)(__ldg(y0 + i - 1) >> shift) & pmask) != p) start[p] = (uint32_t)(base + i);
+	if (i + 1 == n || ((uint32_t)(__ldg(y0 + i + 1) >> shift) & pmask) != p) end[p] = (uint32_t)(base + i + 1);
 }
 
 // ------------------------------------------------------------------ K3': one CTA per partition
@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(256) k_part_bounds(const unsigned long long *y
 struct PartParams {
 	const unsigned long long *y0;      // records, stably partitioned
 	unsigned long long *y1;            //   y1 of a record that does not pass is overwritten with ~0 (normal mode)
-	const uint32_t *start, *end;       // record range per partition; 0 = a single partition [0, n_rec)
+	const uint32_t *start, *end;       // record range per (run, partition): [run * n_parts + partition]; 0 = one range [0, n_rec)
+	uint32_t n_runs, n_parts;          // runs = record arrays partitioned separately, to be replayed one after the other
 	uint64_t n_rec;
 	uint32_t blocks_per_part;          // Bloom blocks per partition (power of two, <= CP_BLOCKS)
 	int k;
@@ -127,9 +128,11 @@ __global__ void __launch_bounds__(CP_THREADS, CP_MIN_CTAS) k_count_part(PartPara
 	__shared__ uint32_t s_info[CP_THREADS];          // losers: block << 18 | h1 << 9 | h2
 	__shared__ uint32_t s_lose[CP_THREADS / 32], s_res[CP_THREADS / 32]; // bitmaps over the round's threads
 	const uint32_t part = blockIdx.x, nb = p.blocks_per_part, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	uint64_t beg = 0, end = p.n_rec;
-	if (p.start) beg = __ldg(p.start + part), end = __ldg(p.end + part);
-	if (beg >= end) return; // nothing for this slice in this window
+	if (p.start) { // nothing for this slice in this window?
+		bool any = false;
+		for (uint32_t r = 0; r < p.n_runs; ++r) any |= __ldg(p.start + (uint64_t)r * p.n_parts + part) < __ldg(p.end + (uint64_t)r * p.n_parts + part);
+		if (!any) return;
+	} else if (p.n_rec == 0) return;
 	uint4 *const g4 = (uint4*)(p.bf.w + ((uint64_t)part * nb << 4));
 	uint4 *const s4 = (uint4*)s_w;
 	for (uint32_t i = tid; i < nb * 4; i += CP_THREADS) s4[i] = __ldcs(g4 + i);
@@ -138,9 +141,12 @@ __global__ void __launch_bounds__(CP_THREADS, CP_MIN_CTAS) k_count_part(PartPara
 	const int H = p.bf.n_hashes;
 	const bool mark = p.bf_high.w == 0;
 	unsigned long long n_k = 0, n_pass = 0, n_wait = 0;
+	__syncthreads();
+	for (uint32_t run = 0; run < p.n_runs; ++run) {
+	uint64_t beg = 0, end = p.n_rec;
+	if (p.start) beg = __ldg(p.start + (uint64_t)run * p.n_parts + part), end = __ldg(p.end + (uint64_t)run * p.n_parts + part);
 	unsigned long long y0f = 0, y1 = ~0ULL;
 	if (beg + tid < end) y1 = __ldg(p.y1 + beg + tid), y0f = __ldg(p.y0 + beg + tid);
-	__syncthreads();
 	for (uint64_t base = beg; base < end; base += CP_THREADS) {
 		const unsigned long long c0f = y0f, c1 = y1;
 		{ // next round's records are in flight while this round is replayed
@@ -201,6 +207,7 @@ __global__ void __launch_bounds__(CP_THREADS, CP_MIN_CTAS) k_count_part(PartPara
 		}
 		n_k += valid, n_pass += pass;
 	}
+	}
 	__syncthreads();
 	for (uint32_t i = tid; i < nb * 4; i += CP_THREADS) __stcs(g4 + i, s4[i]);
 	block_add(p.ctr + 1, n_k);
@@ -228,7 +235,8 @@ __global__ void __launch_bounds__(256, MIN_CTAS) k_tab_apply_marked(TabView t, c
 
 struct PartGeom {
 	int x;              // log2(Bloom blocks this rank holds)
-	int slog2;          // log2(Bloom blocks per partition)
+	int slog2;          // log2(Bloom blocks per partition) of the kernel variant
+	int pshift;         // log2(Bloom blocks per partition) in effect: min(slog2, x) = first partition bit of y0
 	int pbits;          // log2(partitions)
 	int cfg;            // kernel variant
 	uint32_t n_parts, blocks_per_part;
@@ -241,24 +249,25 @@ static int part_cfg()
 	return e && atoi(e) >= 0 && atoi(e) <= 4 ? atoi(e) : 3;
 }
 
-static PartGeom part_geom(const bfc_bf_t *bf, int owner_bits)
+static PartGeom part_geom(int n_shift, int owner_bits)
 {
 	PartGeom g;
 	g.cfg = part_cfg();
 	g.slog2 = g.cfg == 3 ? 8 : g.cfg == 2 || g.cfg == 4 ? 9 : 10;
-	g.x = bf->n_shift - BFC_BLK_SHIFT - owner_bits;
-	g.pbits = g.x > g.slog2 ? g.x - g.slog2 : 0;
+	g.x = n_shift - BFC_BLK_SHIFT - owner_bits;
+	g.pshift = g.x < g.slog2 ? g.x : g.slog2;
+	g.pbits = g.x - g.pshift;
 	g.n_parts = 1u << g.pbits;
-	g.blocks_per_part = 1u << (g.x < g.slog2 ? g.x : g.slog2);
+	g.blocks_per_part = 1u << g.pshift;
 	return g;
 }
 
-bool bfcg_count_part_usable(const bfc_opt_t *opt, const bfc_bf_t *bf, int owner_bits)
+bool bfcg_count_part_usable(const bfc_opt_t *opt, int n_shift, int owner_bits)
 {
 	const char *e = getenv("BFC_B200_COUNT");
 	if (e && strcmp(e, "probe") == 0) return false;
-	const int x = bf->n_shift - BFC_BLK_SHIFT;
-	// the block index (bbf.c:27-28) must be a bit field of y0, and the partition index must fit the sort
+	const int x = n_shift - BFC_BLK_SHIFT;
+	// the block index (bbf.c:27-28) must be a bit field of y0
 	return x <= opt->k && x - owner_bits >= 0 && x - owner_bits <= 36;
 }
 
@@ -273,7 +282,7 @@ struct PartScratch {
 		size_t t = 0;
 		if (g.pbits > 0)
 			cub::DeviceRadixSort::SortPairs((void*)0, t, (const unsigned long long*)0, (unsigned long long*)0,
-			                                (const unsigned long long*)0, (unsigned long long*)0, (int64_t)n, g.slog2, g.slog2 + g.pbits, bfcg_rt().stream);
+			                                (const unsigned long long*)0, (unsigned long long*)0, (int64_t)n, g.pshift, g.pshift + g.pbits, bfcg_rt().stream);
 		return t;
 	}
 	static size_t bytes(uint64_t n, const PartGeom &g)
@@ -292,46 +301,53 @@ struct PartScratch {
 	}
 };
 
-// K1'-K3' over n records in stream order (in_y0 / in_y1, device)
-static int count_part_window(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, bfc_ch_t *ch, const PartGeom &g, uint64_t blk_mask,
-                             const unsigned long long *in_y0, const unsigned long long *in_y1, uint64_t n, PartScratch &sc, bfcg_stats_t *stats,
-                             const std::function<int()> *launched = 0)
+// room for the keys a window of n records can add, at load <= 1/2: at most every second occurrence is new unless
+// the filter misfires; after the first window the previous one's growth is the estimate.  A region that fills up
+// anyway parks its inserts (tab_upsert) and the load is put right after the window (tab_after_window).
+static int tab_before_window(bfc_ch_t *ch, uint64_t n, unsigned long long *before)
+{
+	*before = bfc_ch_count(ch);
+	uint64_t extra = n / 2;
+	if (ch->have_prev) extra = std::min<uint64_t>(extra, std::max<uint64_t>(2 * ch->prev_new, n / 16));
+	return bfcg_tab_reserve(ch, std::max<uint64_t>(extra, 1024));
+}
+
+static int tab_after_window(bfc_ch_t *ch, unsigned long long before)
+{
+	int r;
+	if ((r = bfcg_tab_drain_deferred(ch)) != BFCG_OK) return r;
+	ch->prev_new = bfc_ch_count(ch) - before, ch->have_prev = 1;
+	return bfcg_tab_reserve(ch, 0);
+}
+
+// K2'-K3' + the table upserts over records that are already partitioned: n_runs arrays back to back in y0 / y1 (run r =
+// records [run_off[r], run_off[r+1])), each stably sorted by partition; the runs are replayed one after the other.
+// y1 is overwritten (marks).  `bounds` has room for 2 * n_runs * n_parts words.
+static int count_part_sorted(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, bfc_ch_t *ch, const PartGeom &g, uint64_t blk_mask,
+                             const unsigned long long *y0, unsigned long long *y1, int n_runs, const uint64_t *run_off,
+                             uint32_t *bounds, unsigned long long *ctr, bfcg_stats_t *stats, const std::function<int()> *launched)
 {
 	BfcgRuntime &rt = bfcg_rt();
 	int r;
-	unsigned long long before = 0;
-	if (ch) {
-		// room for the keys this window can add, at load <= 1/2: at most every second occurrence is new unless the
-		// filter misfires; after the first window the previous one's growth is the estimate.  A region that fills up
-		// anyway parks its inserts (tab_upsert) and the load is put right after the window.
-		before = bfc_ch_count(ch);
-		uint64_t extra = n / 2;
-		if (ch->have_prev) extra = std::min<uint64_t>(extra, std::max<uint64_t>(2 * ch->prev_new, n / 16));
-		if ((r = bfcg_tab_reserve(ch, std::max<uint64_t>(extra, 1024))) != BFCG_OK) return r;
-	}
+	const uint64_t n = run_off[n_runs];
 	PartParams p;
 	memset(&p, 0, sizeof(p));
-	p.k = opt->k, p.n_rec = n, p.blocks_per_part = g.blocks_per_part;
+	p.k = opt->k, p.n_rec = n, p.blocks_per_part = g.blocks_per_part, p.n_runs = n_runs, p.n_parts = g.n_parts;
 	p.bf = bloom_view(bf), p.bf.blk_mask = blk_mask;
 	if (bf_high) p.bf_high = bloom_view(bf_high), p.bf_high.blk_mask = blk_mask;
-	p.ctr = sc.ctr;
-	p.y0 = in_y0, p.y1 = sc.s_y1;
-	if (g.pbits > 0) {
-		size_t tb = sc.tmp_bytes;
-		cudaError_t se;
-		{
-			KTime kt(KT_COUNT_SORT);
-			se = cub::DeviceRadixSort::SortPairs(sc.tmp, tb, in_y0, sc.s_y0, in_y1, sc.s_y1, (int64_t)n, g.slog2, g.slog2 + g.pbits, rt.stream);
+	p.ctr = ctr, p.y0 = y0, p.y1 = y1;
+	uint32_t *start = bounds, *end = bounds + (size_t)n_runs * g.n_parts;
+	BFCG_CUDA(cudaMemsetAsync(bounds, 0, (size_t)n_runs * g.n_parts * 8, rt.stream));
+	{
+		KTime kt(KT_COUNT_BOUNDS);
+		for (int i = 0; i < n_runs; ++i) {
+			const uint64_t m = run_off[i + 1] - run_off[i];
+			if (m) k_part_bounds<<<(unsigned)((m + 255) / 256), 256, 0, rt.stream>>>(y0 + run_off[i], m, run_off[i], g.pshift, g.n_parts - 1,
+			                                                                        start + (size_t)i * g.n_parts, end + (size_t)i * g.n_parts);
 		}
-		BFCG_CUDA(se);
-		rt.n_launches += 1 + (g.pbits + 7) / 8; // histogram + one onesweep pass per 8 bits
-		uint32_t *start = sc.bounds, *end = sc.bounds + g.n_parts;
-		BFCG_CUDA(cudaMemsetAsync(sc.bounds, 0, (size_t)g.n_parts * 8, rt.stream));
-		{ KTime kt(KT_COUNT_BOUNDS); k_part_bounds<<<(unsigned)((n + 255) / 256), 256, 0, rt.stream>>>(sc.s_y0, n, g.slog2, g.n_parts - 1, start, end); }
-		BFCG_LAUNCH_CHECK();
-		p.y0 = sc.s_y0, p.start = start, p.end = end;
-	} else BFCG_CUDA(cudaMemcpyAsync(sc.s_y1, in_y1, n * 8, cudaMemcpyDeviceToDevice, rt.stream)); // k_count_part marks y1 in place
-
+	}
+	BFCG_LAUNCH_CHECK();
+	p.start = start, p.end = end;
 	BFCG_CUDA(cudaMemsetAsync(p.ctr, 0, 64, rt.stream));
 	const size_t smem = (size_t)g.blocks_per_part * CP_BLK_BYTES;
 	{
@@ -344,8 +360,7 @@ static int count_part_window(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_hi
 	}
 	BFCG_LAUNCH_CHECK();
 	if (ch) {
-		KTime kt(KT_TAB_APPLY);
-		// latency-bound (a load, then a CAS, per record): as many threads as the register file takes
+		KTime kt(KT_TAB_APPLY); // latency-bound (a load, then a CAS, per record): as many threads as the register file takes
 		k_tab_apply_marked<8><<<(unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)rt.sm_count * 8), 256, 0, rt.stream>>>(tab_view(ch), p.y0, p.y1, n);
 	}
 	BFCG_LAUNCH_CHECK();
@@ -353,16 +368,37 @@ static int count_part_window(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_hi
 	unsigned long long c[4];
 	BFCG_CUDA(cudaMemcpyAsync(c, p.ctr, sizeof(c), cudaMemcpyDeviceToHost, rt.stream));
 	BFCG_CUDA(cudaStreamSynchronize(rt.stream));
-	if (ch) {
-		if ((r = bfcg_tab_drain_deferred(ch)) != BFCG_OK) return r;
-		ch->prev_new = bfc_ch_count(ch) - before, ch->have_prev = 1;
-		if ((r = bfcg_tab_reserve(ch, 0)) != BFCG_OK) return r;
-	}
 	if (stats) {
 		stats->n_kmers += c[1], stats->n_pass += c[2];
 		stats->n_pending += c[1] - c[2], stats->n_conflict += c[3];
 	}
 	return BFCG_OK;
+}
+
+// K1'-K3' over n records in stream order (in_y0 / in_y1, device)
+static int count_part_window(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, bfc_ch_t *ch, const PartGeom &g, uint64_t blk_mask,
+                             const unsigned long long *in_y0, const unsigned long long *in_y1, uint64_t n, PartScratch &sc, bfcg_stats_t *stats,
+                             const std::function<int()> *launched = 0)
+{
+	BfcgRuntime &rt = bfcg_rt();
+	int r;
+	unsigned long long before = 0;
+	if (ch && (r = tab_before_window(ch, n, &before)) != BFCG_OK) return r;
+	const unsigned long long *y0 = in_y0;
+	if (g.pbits > 0) {
+		size_t tb = sc.tmp_bytes;
+		cudaError_t se;
+		{
+			KTime kt(KT_COUNT_SORT);
+			se = cub::DeviceRadixSort::SortPairs(sc.tmp, tb, in_y0, sc.s_y0, in_y1, sc.s_y1, (int64_t)n, g.pshift, g.pshift + g.pbits, rt.stream);
+		}
+		BFCG_CUDA(se);
+		rt.n_launches += 1 + (g.pbits + 7) / 8; // histogram + one onesweep pass per 8 bits
+		y0 = sc.s_y0;
+	} else BFCG_CUDA(cudaMemcpyAsync(sc.s_y1, in_y1, n * 8, cudaMemcpyDeviceToDevice, rt.stream)); // y1 gets marked in place
+	const uint64_t run_off[2] = { 0, n };
+	if ((r = count_part_sorted(opt, bf, bf_high, ch, g, blk_mask, y0, sc.s_y1, 1, run_off, sc.bounds, sc.ctr, stats, launched)) != BFCG_OK) return r;
+	return ch ? tab_after_window(ch, before) : BFCG_OK;
 }
 
 static int part_kernel_setup()
@@ -399,7 +435,7 @@ int bfcg_count_part_batch(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high,
 	BfcgRuntime &rt = bfcg_rt();
 	int r;
 	if ((r = part_kernel_setup()) != BFCG_OK) return r;
-	const PartGeom g = part_geom(bf, 0);
+	const PartGeom g = part_geom(bf->n_shift, 0);
 	if (ch && (r = bfcg_tab_align_to_filter(ch, bf->n_shift - BFC_BLK_SHIFT)) != BFCG_OK) return r;
 	const bool host = batch->where == BFCG_HOST;
 	const uint64_t nbytes = batch->n_bytes, halo = opt->k - 1;
@@ -474,7 +510,7 @@ int bfcg_count_part_records(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_hig
 	BfcgRuntime &rt = bfcg_rt();
 	int r;
 	if ((r = part_kernel_setup()) != BFCG_OK) return r;
-	const PartGeom g = part_geom(bf, owner_bits);
+	const PartGeom g = part_geom(bf->n_shift, owner_bits);
 	if (ch && (r = bfcg_tab_align_to_filter(ch, bf->n_shift - BFC_BLK_SHIFT)) != BFCG_OK) return r;
 	const uint64_t P = std::min<uint64_t>(window_positions(n_rec, false, g), n_rec);
 	PartScratch sc;
@@ -487,6 +523,100 @@ int bfcg_count_part_records(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_hig
 		const uint64_t n = std::min(P, n_rec - s);
 		if ((r = count_part_window(opt, bf, bf_high, ch, g, blk_mask, (const unsigned long long*)d_y0 + s, (const unsigned long long*)d_y1 + s, n, sc, stats)) != BFCG_OK) return r;
 	}
+	timer.stop();
+	BFCG_CUDA(cudaStreamSynchronize(rt.stream));
+	return BFCG_OK;
+}
+
+// ------------------------------------------------------------------ sharded counting with the partition done by the sender
+
+// bfcg_enum_records when the partitioned path applies: enumerate in stream order, then ONE stable radix sort over the
+// whole block prefix -- owner bits on top, partition bits below -- so that the buckets of the owners are contiguous for
+// the all-to-all AND every bucket arrives already partitioned: the receiver replays the pieces of the ranks one after
+// the other (count_part_sorted with n_runs = ranks) and never sorts.
+int bfcg_enum_part_records(const bfc_opt_t *opt, const bfcg_batch_t *batch, int owner_bits, uint64_t *d_y0, uint64_t *d_y1, uint64_t *counts)
+{
+	BfcgRuntime &rt = bfcg_rt();
+	const int n_owners = 1 << owner_bits;
+	const PartGeom g = part_geom(opt->bf_shift, owner_bits);
+	const bool host = batch->where == BFCG_HOST;
+	const uint64_t nb = batch->n_bytes, n_rec = el_padded(nb);
+	const int sort_bits = g.pbits + owner_bits;
+	size_t temp = 0;
+	if (sort_bits > 0)
+		cub::DeviceRadixSort::SortPairs((void*)0, temp, (const unsigned long long*)0, (unsigned long long*)0, (const unsigned long long*)0,
+		                                (unsigned long long*)0, (int64_t)n_rec, g.pshift, g.pshift + sort_bits, rt.stream);
+	size_t o_seq = 0, o_qual = 0, o_y0, o_y1, o_tmp, o_bnd, tot = 0;
+	if (host) { o_seq = tot; tot = align_up(tot + nb, 256); o_qual = tot; tot = align_up(tot + nb, 256); }
+	o_y0 = tot; tot = align_up(tot + n_rec * 8, 256);
+	o_y1 = tot; tot = align_up(tot + n_rec * 8, 256);
+	o_tmp = tot; tot = align_up(tot + temp, 256);
+	o_bnd = tot; tot += 256;
+	uint8_t *a = (uint8_t*)bfcg_arena(tot);
+	if (!a) return BFCG_ERR_NOMEM;
+	EnumLinParams ep;
+	memset(&ep, 0, sizeof(ep));
+	ep.k = opt->k, ep.q = opt->q, ep.len = nb, ep.emit_from = 0;
+	ep.rec_y0 = (unsigned long long*)(a + o_y0), ep.rec_y1 = (unsigned long long*)(a + o_y1); // n_rec (padded) records
+	if (host) {
+		BFCG_CUDA(cudaMemcpyAsync(a + o_seq, batch->seq, nb, cudaMemcpyHostToDevice, rt.stream));
+		if (batch->qual) BFCG_CUDA(cudaMemcpyAsync(a + o_qual, batch->qual, nb, cudaMemcpyHostToDevice, rt.stream));
+		ep.seq = a + o_seq, ep.qual = batch->qual ? a + o_qual : 0;
+	} else ep.seq = batch->seq, ep.qual = batch->qual;
+	{ KTime kt(KT_ENUM_LIN); k_enum_lin<<<(unsigned)(n_rec / EL_SEG), EL_THREADS, 0, rt.stream>>>(ep); }
+	BFCG_LAUNCH_CHECK();
+	// the caller's arrays hold batch->n_bytes records: the padding (no k-mer ends there) stays behind
+	if (sort_bits > 0) {
+		cudaError_t se;
+		{
+			KTime kt(KT_COUNT_SORT);
+			se = cub::DeviceRadixSort::SortPairs(a + o_tmp, temp, ep.rec_y0, (unsigned long long*)d_y0, ep.rec_y1, (unsigned long long*)d_y1,
+			                                     (int64_t)nb, g.pshift, g.pshift + sort_bits, rt.stream);
+		}
+		BFCG_CUDA(se);
+		rt.n_launches += 1 + (sort_bits + 7) / 8;
+	} else {
+		BFCG_CUDA(cudaMemcpyAsync(d_y0, ep.rec_y0, nb * 8, cudaMemcpyDeviceToDevice, rt.stream));
+		BFCG_CUDA(cudaMemcpyAsync(d_y1, ep.rec_y1, nb * 8, cudaMemcpyDeviceToDevice, rt.stream));
+	}
+	uint32_t h_bnd[2 * 8];
+	memset(h_bnd, 0, sizeof(h_bnd));
+	if (owner_bits > 0) { // bucket sizes = runs of the owner bits in the sorted keys
+		uint32_t *bnd = (uint32_t*)(a + o_bnd);
+		BFCG_CUDA(cudaMemsetAsync(bnd, 0, 64, rt.stream));
+		{ KTime kt(KT_BUCKET); k_part_bounds<<<(unsigned)((nb + 255) / 256), 256, 0, rt.stream>>>((const unsigned long long*)d_y0, nb, 0, g.pshift + g.pbits, n_owners - 1, bnd, bnd + 8); }
+		BFCG_LAUNCH_CHECK();
+		BFCG_CUDA(cudaMemcpyAsync(h_bnd, bnd, 64, cudaMemcpyDeviceToHost, rt.stream));
+	} else h_bnd[8] = (uint32_t)nb;
+	BFCG_CUDA(cudaStreamSynchronize(rt.stream));
+	for (int o = 0; o < n_owners; ++o) counts[o] = h_bnd[8 + o] - h_bnd[o];
+	return BFCG_OK;
+}
+
+// The cascade over the pieces an all-to-all delivered, back to back in source-rank order (= global read order), each
+// piece partitioned by its sender (bfcg_enum_part_records).  d_y1 is overwritten.
+int bfcg_count_part_runs(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, bfc_ch_t *ch, int n_runs, const uint64_t *run_counts,
+                         const uint64_t *d_y0, uint64_t *d_y1, int owner_bits, bfcg_stats_t *stats)
+{
+	BfcgRuntime &rt = bfcg_rt();
+	int r;
+	if ((r = part_kernel_setup()) != BFCG_OK) return r;
+	const PartGeom g = part_geom(bf->n_shift, owner_bits);
+	if (ch && (r = bfcg_tab_align_to_filter(ch, bf->n_shift - BFC_BLK_SHIFT)) != BFCG_OK) return r;
+	uint64_t run_off[9];
+	run_off[0] = 0;
+	for (int i = 0; i < n_runs; ++i) run_off[i + 1] = run_off[i] + run_counts[i];
+	const uint64_t n = run_off[n_runs];
+	if (n == 0) return BFCG_OK;
+	if (n >= (1ULL << 32)) return bfcg_fail(__func__, "more than 2^32 records in one exchange", cudaSuccess), BFCG_ERR_ARG;
+	uint8_t *a = (uint8_t*)bfcg_arena(align_up((size_t)n_runs * g.n_parts * 8, 256) + 256);
+	if (!a) return BFCG_ERR_NOMEM;
+	BfcgTimer timer(stats);
+	unsigned long long before = 0;
+	if (ch && (r = tab_before_window(ch, n, &before)) != BFCG_OK) return r;
+	if ((r = count_part_sorted(opt, bf, bf_high, ch, g, (1ULL << g.x) - 1, (const unsigned long long*)d_y0, (unsigned long long*)d_y1, n_runs, run_off,
+	                           (uint32_t*)a, (unsigned long long*)(a + align_up((size_t)n_runs * g.n_parts * 8, 256)), stats, 0)) != BFCG_OK) return r;
+	if (ch && (r = tab_after_window(ch, before)) != BFCG_OK) return r;
 	timer.stop();
 	BFCG_CUDA(cudaStreamSynchronize(rt.stream));
 	return BFCG_OK;

@@ -50,6 +50,8 @@ class ShardedCount:
         self.be, self.rank, self.world, self.group = backend, rank, world, group
         self.sent_records = 0
         self.recv_records = 0
+        import os
+        self.prof = {} if os.environ.get("BFC_DIST_PROFILE") else None
 
     # -- collectives (world == 1 short-circuits so a single process needs no process group)
     def _all_gather_counts(self, counts):
@@ -68,20 +70,43 @@ class ShardedCount:
         dist.all_to_all_single(out, src[:int(sum(in_splits))], list(out_splits), list(in_splits), group=self.group)
         return out
 
+    def _tick(self, name, t0):
+        """Phase boundary: the library works on its own stream and torch / NCCL on theirs, so every phase ends with a
+        device synchronisation (the count path is host-synchronous anyway).  BFC_DIST_PROFILE=1 also attributes the
+        wall clock to the phases."""
+        import time
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        if self.prof is None:
+            return 0.0
+        t = time.perf_counter()
+        if t0:
+            self.prof[name] = self.prof.get(name, 0.0) + (t - t0)
+        return t
+
     def count_piece(self, piece):
         """Count this rank's piece of the current global chunk (every rank must call this once per chunk)."""
+        t = self._tick("other", 0.0)
         y0, y1, counts = self.be.enum_records(piece, self.world)
+        t = self._tick("enum+bucket", t)
         m = self._all_gather_counts(counts)              # m[src][dst]
         in_splits = [int(v) for v in m[self.rank]]
         out_splits = [int(m[src][self.rank]) for src in range(self.world)]
+        t = self._tick("counts", t)
         r0 = self._all_to_all(y0, in_splits, out_splits)
         r1 = self._all_to_all(y1, in_splits, out_splits)
+        t = self._tick("all_to_all", t)
         self.sent_records += sum(in_splits) - in_splits[self.rank]
         self.recv_records += sum(out_splits)
-        self.be.count_records(r0, r1, int(sum(out_splits)), self.world)
+        if hasattr(self.be, "count_record_runs"):     # pieces as delivered: the sender may have partitioned them
+            self.be.count_record_runs(r0, r1, out_splits, self.world)
+        else:
+            self.be.count_records(r0, r1, int(sum(out_splits)), self.world)
+        self._tick("count_records", t)
 
     def gather(self):
         """Replicate the result on every rank: the complete table (normal mode) or bf_high (trim mode)."""
+        t = self._tick("other", 0.0)
         if self.be.filter_mode:
             shard = self.be.bf_high_shard()
             if self.world == 1:
@@ -92,6 +117,7 @@ class ShardedCount:
             self.be.set_bf_high_full(full)
             return
         sub, key = self.be.export_table()
+        t = self._tick("export", t)
         n = int(sub.numel())
         if self.world == 1:
             self.be.import_table([(sub, key)])
@@ -106,7 +132,9 @@ class ShardedCount:
         gsub, gkey = self.be.empty(cap * self.world, torch.int32), self.be.empty(cap * self.world, torch.int64)
         dist.all_gather_into_tensor(gsub, psub, group=self.group)
         dist.all_gather_into_tensor(gkey, pkey, group=self.group)
+        t = self._tick("all_gather", t)
         self.be.import_table([(gsub[r * cap:r * cap + sizes[r]], gkey[r * cap:r * cap + sizes[r]]) for r in range(self.world)])
+        self._tick("import", t)
 
 
 class CudaBackend:
@@ -157,6 +185,13 @@ class CudaBackend:
         self._check(self.L.bfcg_count_records(C.byref(self.opt), self.bf, self.bf_high, self.ch, n,
                                               C.c_void_p(y0.data_ptr()), C.c_void_p(y1.data_ptr()), world,
                                               C.byref(self.stats)), "bfcg_count_records")
+
+    def count_record_runs(self, y0, y1, run_counts, world):
+        torch.cuda.current_stream(self.device).synchronize()
+        rc = (C.c_uint64 * len(run_counts))(*[int(v) for v in run_counts])
+        self._check(self.L.bfcg_count_record_runs(C.byref(self.opt), self.bf, self.bf_high, self.ch, len(run_counts), rc,
+                                                  C.c_void_p(y0.data_ptr()), C.c_void_p(y1.data_ptr()), world,
+                                                  C.byref(self.stats)), "bfcg_count_record_runs")
 
     def shard_bytes(self) -> int:
         return (1 << (self.opt.bf_shift - 3)) // self.world

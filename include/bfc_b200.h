@@ -96,8 +96,8 @@ int bfcg_trim_batch(const bfc_opt_t *opt, const bfc_bf_t *bf_high, const bfcg_ba
  * holds blocks [r, r+1) * 2^(b-9) / N of the first filter (and of bf_high) and the table entries of exactly
  * those k-mers.  Records are 16 bytes: y0 | is_high << 63 and y1 (the two words of bfc_kmer_hash).
  *
- * bfcg_enum_records: enumerate the k-mers of a batch (count.c:72-89) and bucket them by owner, stream order
- * kept inside a bucket.  d_y0 / d_y1: device arrays with room for batch->n_bytes records; counts[n_owners]
+ * bfcg_enum_records: enumerate the k-mers of a batch (count.c:72-89) and bucket them by owner; inside a bucket the
+ * records of one Bloom block keep the stream order (see bfcg_count_record_runs).  d_y0 / d_y1: device arrays with room for batch->n_bytes records; counts[n_owners]
  * (host) receives the bucket sizes; bucket o starts at counts[0] + ... + counts[o-1].
  * bfcg_count_records: the Bloom -> table cascade (count.c:54-70) over records in stream order (what the
  * all-to-all delivers: the pieces of the ranks concatenated in rank order), against this rank's shard. */
@@ -105,6 +105,13 @@ int bfcg_enum_records(const bfc_opt_t *opt, const bfcg_batch_t *batch, int n_own
                       uint64_t *d_y0, uint64_t *d_y1, uint64_t *counts);
 int bfcg_count_records(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, bfc_ch_t *ch, uint64_t n_rec,
                        const uint64_t *d_y0, const uint64_t *d_y1, int n_owners, bfcg_stats_t *stats);
+/* bfcg_count_record_runs: the same cascade over exactly what an all-to-all of bfcg_enum_records buckets delivers: n_runs
+ * pieces back to back in source-rank order (= global read order), piece i holding run_counts[i] records.  When the Bloom
+ * block index is a bit field of y0 (n_shift - 9 <= k) bfcg_enum_records orders every bucket by count partition (stable,
+ * so the order inside a Bloom block is still the read order) and this call replays the pieces without sorting again;
+ * otherwise both keep stream order.  d_y1 is overwritten. */
+int bfcg_count_record_runs(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, bfc_ch_t *ch, int n_runs, const uint64_t *run_counts,
+                           uint64_t *d_y0, uint64_t *d_y1, int n_owners, bfcg_stats_t *stats);
 bfc_bf_t *bfcg_bf_init_shard(int n_shift, int n_hashes, int n_owners);   /* 2^(n_shift-3) / n_owners bytes */
 /* table exchange: entries as (sub-table index, key50<<14 | val14) in DEVICE arrays, unsorted; returns n
  * (pass NULLs to get n); import adds entries that are not present yet (shards are disjoint) */

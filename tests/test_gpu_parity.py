@@ -207,14 +207,16 @@ def test_cli_matches_reference_golden(bfc, tmp_path):
         assert out == c.corrected
 
 
-@pytest.mark.parametrize("world,k,b,trim", [(4, 31, 22, False), (2, 33, 20, True), (8, 55, 24, False)])
-def test_sharded_count_kernels_emulated_on_one_gpu(bfc, monkeypatch, world, k, b, trim):
+@pytest.mark.parametrize("path", ["part", "probe"])
+@pytest.mark.parametrize("world,k,b,trim", [(4, 31, 22, False), (2, 33, 20, True), (8, 55, 24, False), (2, 33, 30, False)])
+def test_sharded_count_kernels_emulated_on_one_gpu(bfc, monkeypatch, world, k, b, trim, path):
     """The sharded count path (bfcg_enum_records -> bucket exchange -> bfcg_count_records on 1/N filters) with
     the N ranks emulated one after the other on one GPU: the shards concatenate to the oracle's filter and the
     union of the shard tables is the oracle's table."""
     import ctypes as C
     import torch
     from bfc_b200.dist import CudaBackend, piece_bounds
+    monkeypatch.setenv("BFC_B200_COUNT", path)
     monkeypatch.setenv("BFC_B200_SUBBATCH", str(1 << 17))
     monkeypatch.setenv("BFC_B200_COUNT_WINDOW", str(1 << 17))
     seq, qual, off = synth_batch(60000, 16000, 120, seed=k + world, repeat=0.2)
@@ -237,7 +239,7 @@ def test_sharded_count_kernels_emulated_on_one_gpu(bfc, monkeypatch, world, k, b
             for d in range(world):  # the all-to-all: destination d receives the pieces in source-rank order
                 r0 = torch.cat([sent[r][d][0] for r in range(world)])
                 r1 = torch.cat([sent[r][d][1] for r in range(world)])
-                ranks[d].count_records(r0, r1, int(r0.numel()), world)
+                ranks[d].count_record_runs(r0, r1, [int(sent[r][d][0].numel()) for r in range(world)], world)
         bloom = np.concatenate([ranks[r].bf_shard().cpu().numpy() for r in range(world)])
         assert np.array_equal(bloom, o.bloom_bytes())
         assert sum(int(r.stats.n_kmers) for r in ranks) == int(o.stats[0])
