@@ -198,7 +198,7 @@ def main():
     ap.add_argument("--reads", type=int, default=int(os.environ.get("BFC_BENCH_READS", 100_000_000)))
     ap.add_argument("--k", type=int, default=33)
     ap.add_argument("--bf-shift", type=int, default=37)
-    ap.add_argument("--chunk-reads", type=int, default=4_000_000, help="N > 1: reads per global chunk (one all-to-all each)")
+    ap.add_argument("--chunk-reads", type=int, default=16_000_000, help="N > 1: reads per global chunk (one all-to-all each)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -235,7 +235,7 @@ class CudaBackend:
         if self.world == 1:
             self.full_ch = self.ch   # a single rank already holds everything
             return
-        full = L.bfc_ch_init(self.opt.k, self.opt.l_pre)
+        full = self.full_ch if self.full_ch and self.full_ch != self.ch else L.bfc_ch_init(self.opt.k, self.opt.l_pre)
         if not full:
             raise self.api.BfcError("bfc_ch_init failed: " + L.bfcg_last_error().decode())
         self._check(L.bfcg_ch_reserve(full, total), "bfcg_ch_reserve")
@@ -244,28 +244,24 @@ class CudaBackend:
             if sub.numel():
                 self._check(L.bfcg_ch_import_device(full, int(sub.numel()), C.c_void_p(sub.data_ptr()),
                                                     C.c_void_p(key.data_ptr())), "bfcg_ch_import_device")
-        L.bfc_ch_destroy(self.ch)    # the shard is not needed any more
-        self.ch = None
         self.full_ch = full
 
     def reset(self):
-        """Empty shards and table (between bench steps)."""
-        L, opt = self.L, self.opt
-        if self.full_ch and self.full_ch != self.ch:
-            L.bfc_ch_destroy(self.full_ch)
-        if self.ch:
-            L.bfc_ch_destroy(self.ch)
-        self.full_ch = self.ch = None
-        for name in ("bf", "bf_high"):
-            if getattr(self, name):
-                L.bfc_bf_destroy(getattr(self, name))
-                setattr(self, name, None)
+        """Empty shards and tables (between bench steps); the allocations are kept, as Engine.reset() keeps them."""
+        L = self.L
+        cudart = C.CDLL("libcudart.so.12")
+        torch.cuda.synchronize(self.device)
+        for bf in (self.bf, self.bf_high):
+            if bf:
+                rc = cudart.cudaMemset(C.c_void_p(bf.contents.b), 0, C.c_size_t(self.shard_bytes()))
+                if rc != 0:
+                    raise self.api.BfcError(f"cudaMemset failed: {rc}")
+        for ch in {self.ch, self.full_ch}:
+            if ch:
+                self._check(L.bfcg_ch_clear(ch), "bfcg_ch_clear")
         self.full_bf_high = self._bf_high_view = None
-        self.bf = L.bfcg_bf_init_shard(opt.bf_shift, opt.n_hashes, self.world)
-        self.bf_high = L.bfcg_bf_init_shard(opt.bf_shift, opt.n_hashes, self.world) if self.filter_mode else None
-        self.ch = None if self.filter_mode else L.bfc_ch_init(opt.k, opt.l_pre)
-        if not self.bf or (self.filter_mode and not self.bf_high) or (not self.filter_mode and not self.ch):
-            raise self.api.BfcError("allocation failed: " + L.bfcg_last_error().decode())
+        if self.world > 1 and self.full_ch == self.ch:
+            self.full_ch = None
 
     def mode(self) -> int:
         """bfc_ch_hist of the gathered table (reference correct.c:633)."""
