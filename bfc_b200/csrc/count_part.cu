@@ -32,10 +32,56 @@
 #include <algorithm>
 #include <functional>
 
-#define CP_SLOG2_MAX 10                          // log2(Bloom blocks per partition) <= 10: slices of at most 64 KB
+#define CP_SLOG2   8                             // log2(Bloom blocks per partition): 16 KB slices
+#define CP_THREADS 128                           // 12 CTAs per SM (measured best; 64 KB / 256 threads / 3 CTAs: +40 %)
+#define CP_MIN_CTAS 12
 #define CP_BLK_BYTES 64                           // one Bloom block (bbf.h: 512 bits)
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ------------------------------------------------------------------ record formats
+//
+// A record is (y0, y1, is_high): 2k + 1 bits.  Two layouts, both "a 64-bit key whose low bits are y0" (what the
+// partition sort keys on) plus a value:
+//   wire (PACKED = false, VT = u64): key = y0 | is_high << 63, value = y1; ~0 in the value = no k-mer / does not
+//       pass.  The format of the multi-GPU exchange and of count.cu.
+//   packed (PACKED = true): key = y0 | is_high << k | (low 63-k bits of y1) << (k+1), value = the remaining 2k-63
+//       bits of y1 in the smallest of u8/u16/u32/u64 that leaves the top bit free; top bit set = no k-mer / does
+//       not pass.  9 bytes per record at k <= 35 instead of 16: the sort, the replay and the table apply all
+//       stream less.
+template <typename VT, bool PACKED> struct Rec {
+	static __device__ __forceinline__ VT mark() { return PACKED ? (VT)((VT)1 << (8 * sizeof(VT) - 1)) : (VT)~(VT)0; }
+	static __device__ __forceinline__ void pack(int k, uint64_t y0, uint64_t y1, int high, unsigned long long &key, VT &val)
+	{
+		if (PACKED) {
+			const int lb = 63 - k;
+			key = y0 | (unsigned long long)high << k | (lb ? (y1 & ((1ULL << lb) - 1)) << (k + 1) : 0ULL);
+			val = (VT)(y1 >> lb);
+		} else key = y0 | (unsigned long long)high << 63, val = (VT)y1;
+	}
+	static __device__ __forceinline__ bool valid(VT val) { return PACKED ? (val & mark()) == 0 : val != mark(); }
+	// y0f = y0 | is_high << 63
+	static __device__ __forceinline__ void unpack(int k, unsigned long long key, VT val, unsigned long long &y0f, unsigned long long &y1)
+	{
+		if (PACKED) {
+			const int lb = 63 - k;
+			y0f = (key & ((1ULL << k) - 1)) | (key >> k & 1) << 63;
+			y1 = (lb ? key >> (k + 1) : 0ULL) | (unsigned long long)val << lb;
+		} else y0f = key, y1 = (unsigned long long)val;
+	}
+};
+
+static int packed_value_bytes(int k) { return k <= 35 ? 1 : k <= 39 ? 2 : k <= 47 ? 4 : 8; }
+
+// run `call` with the record format: vb = bytes of a packed value, or 0 = wire format
+#define REC_DISPATCH(vb, call)                                                             \
+	do {                                                                                   \
+		if ((vb) == 0) { typedef unsigned long long VT; const bool PK = false; (void)PK; call; }   \
+		else if ((vb) == 1) { typedef uint8_t VT; const bool PK = true; (void)PK; call; }        \
+		else if ((vb) == 2) { typedef uint16_t VT; const bool PK = true; (void)PK; call; }       \
+		else if ((vb) == 4) { typedef uint32_t VT; const bool PK = true; (void)PK; call; }       \
+		else { typedef unsigned long long VT; const bool PK = true; (void)PK; call; }            \
+	} while (0)
 
 // ------------------------------------------------------------------ K0': enumeration in stream order
 
@@ -44,13 +90,15 @@ struct EnumLinParams {
 	uint64_t len;                // bytes in the window
 	uint64_t emit_from;          // records are emitted for window positions >= emit_from
 	int k, q;
-	unsigned long long *rec_y0, *rec_y1;
+	unsigned long long *key;
+	void *val;
 };
 
 // What worker_count does per base (count.c:76-88): map the character (bseq.c:9-26), restart on
 // a non-ACGT one, and once k bases are in, hash the canonical k-mer (kmer.h:79-88) with
 // is_high = all k bases have Q >= q.  Instead of rolling, the k-mer ending at a position is cut
 // out of the base bit planes of the segment (the same construction as correct.cu's extract_kmer).
+template <typename VT, bool PACKED>
 __global__ void __launch_bounds__(EL_THREADS) k_enum_lin(EnumLinParams p)
 {
 	__shared__ uint32_t s_pl[4][EL_WORDS]; // B0, B1 (base code bits), NB (not ACGT / outside), Q (Q >= q)
@@ -58,18 +106,20 @@ __global__ void __launch_bounds__(EL_THREADS) k_enum_lin(EnumLinParams p)
 	el_stage_planes(s_pl, p.seq, p.qual, p.len, seg0, p.q);
 	const int k = p.k;
 	const uint64_t kmask = (1ULL << k) - 1;
-	unsigned long long *o0 = p.rec_y0 + (uint64_t)blockIdx.x * EL_SEG + threadIdx.x;
-	unsigned long long *o1 = p.rec_y1 + (uint64_t)blockIdx.x * EL_SEG + threadIdx.x;
+	unsigned long long *ok = p.key + (uint64_t)blockIdx.x * EL_SEG + threadIdx.x;
+	VT *ov = (VT*)p.val + (uint64_t)blockIdx.x * EL_SEG + threadIdx.x;
 #pragma unroll 4
 	for (int j = 0; j < EL_ITERS; ++j) {
 		const uint32_t pp = (uint32_t)(j * EL_THREADS + threadIdx.x);   // position inside the segment
 		const uint32_t bit = pp + EL_LEAD - (uint32_t)(k - 1);          // oldest base of the k-mer ending at pp
-		// a position where no k-mer ends still gets a record (y1 = ~0); its y0 is spread so that the
+		// a position where no k-mer ends still gets a record (marked); its key is spread so that the
 		// partitions stay balanced
-		uint64_t y[2] = { ((uint64_t)(seg0 + pp) * 0x9E3779B97F4A7C15ULL) >> 1, ~0ULL };
-		if (el_kmer_at(s_pl, bit, k, kmask, y)) y[0] |= (unsigned long long)((win64(s_pl[3], bit) & kmask) == kmask) << 63;
-		o0[j * EL_THREADS] = y[0];
-		o1[j * EL_THREADS] = y[1];
+		unsigned long long key = ((uint64_t)(seg0 + pp) * 0x9E3779B97F4A7C15ULL) >> 1;
+		VT val = Rec<VT, PACKED>::mark();
+		uint64_t y[2];
+		if (el_kmer_at(s_pl, bit, k, kmask, y)) Rec<VT, PACKED>::pack(k, y[0], y[1], (win64(s_pl[3], bit) & kmask) == kmask, key, val);
+		ok[j * EL_THREADS] = key;
+		ov[j * EL_THREADS] = val;
 	}
 }
 
@@ -87,12 +137,11 @@ __global__ void __launch_bounds__(256) k_part_bounds(const unsigned long long *y
 // ------------------------------------------------------------------ K3': one CTA per partition
 
 struct PartParams {
-	const unsigned long long *y0;      // records, stably partitioned
-	unsigned long long *y1;            //   y1 of a record that does not pass is overwritten with ~0 (normal mode)
-	const uint32_t *start, *end;       // record range per (run, partition): [run * n_parts + partition]; 0 = one range [0, n_rec)
+	const unsigned long long *key;     // records, stably partitioned
+	void *val;                         //   the value of a record that does not pass is overwritten with the mark (normal mode)
+	const uint32_t *start, *end;       // record range per (run, partition): [run * n_parts + partition]
 	uint32_t n_runs, n_parts;          // runs = record arrays partitioned separately, to be replayed one after the other
-	uint64_t n_rec;
-	uint32_t blocks_per_part;          // Bloom blocks per partition (power of two, <= CP_BLOCKS)
+	uint32_t blocks_per_part;          // Bloom blocks per partition (power of two, <= 2^CP_SLOG2)
 	int k;
 	BloomView bf, bf_high;             // bf_high.w == 0 in normal mode
 	unsigned long long *ctr;           // [1] n_kmers [2] n_pass [3] occurrences that had to wait for an earlier one
@@ -120,19 +169,20 @@ __device__ __forceinline__ int bloom_test_set_smem(uint32_t *w, int h1, int h2, 
 // occurrence of the same block in the same round) are replayed afterwards by warp 0 in stream order: lane l walks
 // the losers' bitmap in ascending order and handles the blocks with index = l mod 32, so one block is always
 // replayed sequentially and different blocks in parallel.
-template <int CP_THREADS, int CP_MIN_CTAS, int CP_SLOG2>
+template <typename VT, bool PACKED>
 __global__ void __launch_bounds__(CP_THREADS, CP_MIN_CTAS) k_count_part(PartParams p)
 {
 	extern __shared__ __align__(16) uint32_t s_w[];  // the partition's slice of the filter: blocks_per_part x 16 words
 	__shared__ uint32_t s_claim[1 << CP_SLOG2];      // per block: lowest thread with a pending occurrence this round
 	__shared__ uint32_t s_info[CP_THREADS];          // losers: block << 18 | h1 << 9 | h2
 	__shared__ uint32_t s_lose[CP_THREADS / 32], s_res[CP_THREADS / 32]; // bitmaps over the round's threads
+	typedef Rec<VT, PACKED> R;
 	const uint32_t part = blockIdx.x, nb = p.blocks_per_part, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	if (p.start) { // nothing for this slice in this window?
+	{ // nothing for this slice in this window?
 		bool any = false;
 		for (uint32_t r = 0; r < p.n_runs; ++r) any |= __ldg(p.start + (uint64_t)r * p.n_parts + part) < __ldg(p.end + (uint64_t)r * p.n_parts + part);
 		if (!any) return;
-	} else if (p.n_rec == 0) return;
+	}
 	uint4 *const g4 = (uint4*)(p.bf.w + ((uint64_t)part * nb << 4));
 	uint4 *const s4 = (uint4*)s_w;
 	for (uint32_t i = tid; i < nb * 4; i += CP_THREADS) s4[i] = __ldcs(g4 + i);
@@ -140,73 +190,77 @@ __global__ void __launch_bounds__(CP_THREADS, CP_MIN_CTAS) k_count_part(PartPara
 	if (tid < CP_THREADS / 32) s_lose[tid] = 0, s_res[tid] = 0;
 	const int H = p.bf.n_hashes;
 	const bool mark = p.bf_high.w == 0;
+	VT *const vals = (VT*)p.val;
 	unsigned long long n_k = 0, n_pass = 0, n_wait = 0;
 	__syncthreads();
 	for (uint32_t run = 0; run < p.n_runs; ++run) {
-	uint64_t beg = 0, end = p.n_rec;
-	if (p.start) beg = __ldg(p.start + (uint64_t)run * p.n_parts + part), end = __ldg(p.end + (uint64_t)run * p.n_parts + part);
-	unsigned long long y0f = 0, y1 = ~0ULL;
-	if (beg + tid < end) y1 = __ldg(p.y1 + beg + tid), y0f = __ldg(p.y0 + beg + tid);
-	for (uint64_t base = beg; base < end; base += CP_THREADS) {
-		const unsigned long long c0f = y0f, c1 = y1;
-		{ // next round's records are in flight while this round is replayed
-			const uint64_t ni = base + CP_THREADS + tid;
-			y1 = ~0ULL;
-			if (ni < end) y1 = __ldg(p.y1 + ni), y0f = __ldg(p.y0 + ni);
-		}
-		const bool valid = c1 != ~0ULL;
-		const uint64_t c0 = c0f & ~(1ULL << 63);
-		bool pass = false, pend = false;
-		BloomProbe pr;
-		pr.blk = 0, pr.h1 = pr.h2 = 0;
-		uint32_t lb = 0;
-		if (valid) {
-			pr = bloom_locate(hash_from_y(p.k, c0, c1), p.bf.n_shift);
-			lb = (uint32_t)pr.blk & (nb - 1);
-			pass = bloom_count_set<false>(s_w + (lb << 4), pr, H) == H; // all set: passes, writes nothing
-			pend = !pass;
-		}
-		if (__syncthreads_or(pend)) {
-			if (pend) atomicMin(&s_claim[lb], tid);
-			__syncthreads();
-			bool lost = false;
-			if (pend) {
-				if (s_claim[lb] == tid) pass = bloom_test_set_smem(s_w + (lb << 4), pr.h1, pr.h2, H) == H; // reference count.c:60
-				else {
-					lost = true;
-					s_info[tid] = lb << 18 | (uint32_t)pr.h1 << 9 | (uint32_t)pr.h2;
-					atomicOr(&s_lose[warp], 1u << lane);
-				}
+		const uint64_t beg = __ldg(p.start + (uint64_t)run * p.n_parts + part), end = __ldg(p.end + (uint64_t)run * p.n_parts + part);
+		unsigned long long key = 0;
+		VT val = R::mark();
+		if (beg + tid < end) val = __ldg(vals + beg + tid), key = __ldg(p.key + beg + tid);
+		for (uint64_t base = beg; base < end; base += CP_THREADS) {
+			const unsigned long long ckey = key;
+			const VT cval = val;
+			{ // next round's records are in flight while this round is replayed
+				const uint64_t ni = base + CP_THREADS + tid;
+				val = R::mark();
+				if (ni < end) val = __ldg(vals + ni), key = __ldg(p.key + ni);
 			}
-			if (__syncthreads_or(lost)) {
-				if (warp == 0) {
-					for (int wd = 0; wd < CP_THREADS / 32; ++wd)
-						for (uint32_t m = s_lose[wd]; m; m &= m - 1) {
-							const int t = wd * 32 + __ffs(m) - 1;
-							const uint32_t info = s_info[t];
-							if (((info >> 18) & 31) == lane && bloom_test_set_smem(s_w + ((info >> 18) << 4), info >> 9 & 511, info & 511, H) == H)
-								atomicOr(&s_res[wd], 1u << (t & 31));
-						}
-				}
+			const bool valid = R::valid(cval);
+			unsigned long long c0f = 0, c1 = 0;
+			R::unpack(p.k, ckey, cval, c0f, c1);
+			const uint64_t c0 = c0f & ~(1ULL << 63);
+			bool pass = false, pend = false;
+			BloomProbe pr;
+			pr.blk = 0, pr.h1 = pr.h2 = 0;
+			uint32_t lb = 0;
+			if (valid) {
+				pr = bloom_locate(hash_from_y(p.k, c0, c1), p.bf.n_shift);
+				lb = (uint32_t)pr.blk & (nb - 1);
+				pass = bloom_count_set<false>(s_w + (lb << 4), pr, H) == H; // all set: passes, writes nothing
+				pend = !pass;
+			}
+			if (__syncthreads_or(pend)) {
+				if (pend) atomicMin(&s_claim[lb], tid);
 				__syncthreads();
-				if (lost) {
-					pass = s_res[warp] >> lane & 1;
-					atomicAnd(&s_lose[warp], ~(1u << lane));
-					atomicAnd(&s_res[warp], ~(1u << lane));
-					++n_wait;
+				bool lost = false;
+				if (pend) {
+					if (s_claim[lb] == tid) pass = bloom_test_set_smem(s_w + (lb << 4), pr.h1, pr.h2, H) == H; // reference count.c:60
+					else {
+						lost = true;
+						s_info[tid] = lb << 18 | (uint32_t)pr.h1 << 9 | (uint32_t)pr.h2;
+						atomicOr(&s_lose[warp], 1u << lane);
+					}
+				}
+				if (__syncthreads_or(lost)) {
+					if (warp == 0) {
+						for (int wd = 0; wd < CP_THREADS / 32; ++wd)
+							for (uint32_t m = s_lose[wd]; m; m &= m - 1) {
+								const int t = wd * 32 + __ffs(m) - 1;
+								const uint32_t info = s_info[t];
+								if (((info >> 18) & 31) == lane && bloom_test_set_smem(s_w + ((info >> 18) << 4), info >> 9 & 511, info & 511, H) == H)
+									atomicOr(&s_res[wd], 1u << (t & 31));
+							}
+					}
+					__syncthreads();
+					if (lost) {
+						pass = s_res[warp] >> lane & 1;
+						atomicAnd(&s_lose[warp], ~(1u << lane));
+						atomicAnd(&s_res[warp], ~(1u << lane));
+						++n_wait;
+					}
+				}
+				if (pend && !lost) s_claim[lb] = ~0u; // the winner's claim; a loser's block was claimed by a winner
+			}
+			if (valid) {
+				if (mark) { if (!pass) vals[base + tid] = R::mark(); } // the table upserts of the passing records follow in k_tab_apply_marked
+				else if (pass) {
+					const BloomProbe ph = bloom_locate(hash_from_y(p.k, c0, c1), p.bf_high.n_shift);
+					bloom_set_atomic(bloom_block(p.bf_high, ph.blk), ph, p.bf_high.n_hashes);
 				}
 			}
-			if (pend && !lost) s_claim[lb] = ~0u; // the winner's claim; a loser's block was claimed by a winner
+			n_k += valid, n_pass += pass;
 		}
-		if (valid) {
-			if (mark) { if (!pass) p.y1[base + tid] = ~0ULL; } // the table upserts of the passing records follow in k_tab_apply_marked
-			else if (pass) {
-				const BloomProbe ph = bloom_locate(hash_from_y(p.k, c0, c1), p.bf_high.n_shift);
-				bloom_set_atomic(bloom_block(p.bf_high, ph.blk), ph, p.bf_high.n_hashes);
-			}
-		}
-		n_k += valid, n_pass += pass;
-	}
 	}
 	__syncthreads();
 	for (uint32_t i = tid; i < nb * 4; i += CP_THREADS) __stcs(g4 + i, s4[i]);
@@ -216,16 +270,18 @@ __global__ void __launch_bounds__(CP_THREADS, CP_MIN_CTAS) k_count_part(PartPara
 }
 
 // bfc_ch_insert (htab.c:60-82) for every record that passed, in partition order: a warp's 32 records belong to one
-// partition, whose sub-tables are neighbours in the table (tab_region), so the probes stay in L2
-template <int MIN_CTAS>
-__global__ void __launch_bounds__(256, MIN_CTAS) k_tab_apply_marked(TabView t, const unsigned long long *y0, const unsigned long long *y1, uint64_t n)
+// partition, whose sub-tables are neighbours in the table (tab_region), so the probes stay in L2.  Latency-bound (a
+// load, then a CAS, per record): as many threads as the register file takes.
+template <typename VT, bool PACKED>
+__global__ void __launch_bounds__(256, 8) k_tab_apply_marked(TabView t, const unsigned long long *key, const VT *val, uint64_t n)
 {
 	unsigned long long added = 0;
 	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-		const unsigned long long b = __ldg(y1 + i);
-		if (b != ~0ULL) {
-			const unsigned long long a = __ldg(y0 + i);
-			added += tab_upsert(t, a & ~(1ULL << 63), b, (int)(a >> 63)) == 1;
+		const VT v = __ldg(val + i);
+		if (Rec<VT, PACKED>::valid(v)) {
+			unsigned long long y0f, y1;
+			Rec<VT, PACKED>::unpack(t.k, __ldg(key + i), v, y0f, y1);
+			added += tab_upsert(t, y0f & ~(1ULL << 63), y1, (int)(y0f >> 63)) == 1;
 		}
 	}
 	block_add(t.counters, added);
@@ -235,27 +291,16 @@ __global__ void __launch_bounds__(256, MIN_CTAS) k_tab_apply_marked(TabView t, c
 
 struct PartGeom {
 	int x;              // log2(Bloom blocks this rank holds)
-	int slog2;          // log2(Bloom blocks per partition) of the kernel variant
-	int pshift;         // log2(Bloom blocks per partition) in effect: min(slog2, x) = first partition bit of y0
+	int pshift;         // log2(Bloom blocks per partition) = min(CP_SLOG2, x) = first partition bit of y0
 	int pbits;          // log2(partitions)
-	int cfg;            // kernel variant
 	uint32_t n_parts, blocks_per_part;
 };
-
-// kernel variants (threads per CTA, CTAs per SM, slice): the launch geometry is a tuning knob, the results are the same
-static int part_cfg()
-{
-	const char *e = getenv("BFC_B200_PART_CFG");
-	return e && atoi(e) >= 0 && atoi(e) <= 4 ? atoi(e) : 3;
-}
 
 static PartGeom part_geom(int n_shift, int owner_bits)
 {
 	PartGeom g;
-	g.cfg = part_cfg();
-	g.slog2 = g.cfg == 3 ? 8 : g.cfg == 2 || g.cfg == 4 ? 9 : 10;
 	g.x = n_shift - BFC_BLK_SHIFT - owner_bits;
-	g.pshift = g.x < g.slog2 ? g.x : g.slog2;
+	g.pshift = g.x < CP_SLOG2 ? g.x : CP_SLOG2;
 	g.pbits = g.x - g.pshift;
 	g.n_parts = 1u << g.pbits;
 	g.blocks_per_part = 1u << g.pshift;
@@ -271,30 +316,42 @@ bool bfcg_count_part_usable(const bfc_opt_t *opt, int n_shift, int owner_bits)
 	return x <= opt->k && x - owner_bits >= 0 && x - owner_bits <= 36;
 }
 
+// stable partition of n records by bits [begin, end) of the key (cub onesweep); vb = record format (REC_DISPATCH)
+static cudaError_t sort_records(void *tmp, size_t &tmp_bytes, int vb, const unsigned long long *k_in, unsigned long long *k_out,
+                                const void *v_in, void *v_out, uint64_t n, int begin, int end)
+{
+	cudaError_t e = cudaSuccess;
+	REC_DISPATCH(vb, e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, (const VT*)v_in, (VT*)v_out, (int64_t)n, begin, end, bfcg_rt().stream));
+	return e;
+}
+
+static size_t sort_temp_bytes(int vb, uint64_t n, int begin, int end)
+{
+	size_t t = 0;
+	if (end > begin) sort_records(0, t, vb, 0, 0, 0, 0, n, begin, end);
+	return t;
+}
+
+static inline int value_bytes(int vb) { return vb ? vb : 8; }
+
 struct PartScratch {
-	unsigned long long *s_y0, *s_y1; // sorted records
+	unsigned long long *s_key; // sorted records
+	void *s_val;
 	uint8_t *tmp;
 	size_t tmp_bytes;
-	uint32_t *bounds;                // start[n_parts], end[n_parts]
+	uint32_t *bounds;          // start[n_parts], end[n_parts]
 	unsigned long long *ctr;
-	static size_t sort_temp(uint64_t n, const PartGeom &g)
+	static size_t bytes(uint64_t n, const PartGeom &g, int vb)
 	{
-		size_t t = 0;
-		if (g.pbits > 0)
-			cub::DeviceRadixSort::SortPairs((void*)0, t, (const unsigned long long*)0, (unsigned long long*)0,
-			                                (const unsigned long long*)0, (unsigned long long*)0, (int64_t)n, g.pshift, g.pshift + g.pbits, bfcg_rt().stream);
-		return t;
+		return align_up(n * 8, 256) + align_up(n * value_bytes(vb), 256) + align_up(sort_temp_bytes(vb, n, g.pshift, g.pshift + g.pbits), 256) +
+		       align_up((size_t)g.n_parts * 8, 256) + 256;
 	}
-	static size_t bytes(uint64_t n, const PartGeom &g)
-	{
-		return 2 * align_up(n * 8, 256) + align_up(sort_temp(n, g), 256) + align_up((size_t)g.n_parts * 8, 256) + 256;
-	}
-	void carve(uint8_t *a, uint64_t n, const PartGeom &g)
+	void carve(uint8_t *a, uint64_t n, const PartGeom &g, int vb)
 	{
 		size_t o = 0;
-		s_y0 = (unsigned long long*)(a + o); o += align_up(n * 8, 256);
-		s_y1 = (unsigned long long*)(a + o); o += align_up(n * 8, 256);
-		tmp_bytes = sort_temp(n, g);
+		s_key = (unsigned long long*)(a + o); o += align_up(n * 8, 256);
+		s_val = a + o; o += align_up(n * value_bytes(vb), 256);
+		tmp_bytes = sort_temp_bytes(vb, n, g.pshift, g.pshift + g.pbits);
 		tmp = a + o; o += align_up(tmp_bytes, 256);
 		bounds = (uint32_t*)(a + o); o += align_up((size_t)g.n_parts * 8, 256);
 		ctr = (unsigned long long*)(a + o);
@@ -320,11 +377,11 @@ static int tab_after_window(bfc_ch_t *ch, unsigned long long before)
 	return bfcg_tab_reserve(ch, 0);
 }
 
-// K2'-K3' + the table upserts over records that are already partitioned: n_runs arrays back to back in y0 / y1 (run r =
-// records [run_off[r], run_off[r+1])), each stably sorted by partition; the runs are replayed one after the other.
-// y1 is overwritten (marks).  `bounds` has room for 2 * n_runs * n_parts words.
-static int count_part_sorted(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, bfc_ch_t *ch, const PartGeom &g, uint64_t blk_mask,
-                             const unsigned long long *y0, unsigned long long *y1, int n_runs, const uint64_t *run_off,
+// K2'-K3' + the table upserts over records that are already partitioned: n_runs arrays back to back in key / val (run r
+// = records [run_off[r], run_off[r+1])), each stably sorted by partition; the runs are replayed one after the other.
+// The values are overwritten (marks).  `bounds` has room for 2 * n_runs * n_parts words.
+static int count_part_sorted(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, bfc_ch_t *ch, const PartGeom &g, uint64_t blk_mask, int vb,
+                             const unsigned long long *key, void *val, int n_runs, const uint64_t *run_off,
                              uint32_t *bounds, unsigned long long *ctr, bfcg_stats_t *stats, const std::function<int()> *launched)
 {
 	BfcgRuntime &rt = bfcg_rt();
@@ -332,17 +389,17 @@ static int count_part_sorted(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_hi
 	const uint64_t n = run_off[n_runs];
 	PartParams p;
 	memset(&p, 0, sizeof(p));
-	p.k = opt->k, p.n_rec = n, p.blocks_per_part = g.blocks_per_part, p.n_runs = n_runs, p.n_parts = g.n_parts;
+	p.k = opt->k, p.blocks_per_part = g.blocks_per_part, p.n_runs = n_runs, p.n_parts = g.n_parts;
 	p.bf = bloom_view(bf), p.bf.blk_mask = blk_mask;
 	if (bf_high) p.bf_high = bloom_view(bf_high), p.bf_high.blk_mask = blk_mask;
-	p.ctr = ctr, p.y0 = y0, p.y1 = y1;
+	p.ctr = ctr, p.key = key, p.val = val;
 	uint32_t *start = bounds, *end = bounds + (size_t)n_runs * g.n_parts;
 	BFCG_CUDA(cudaMemsetAsync(bounds, 0, (size_t)n_runs * g.n_parts * 8, rt.stream));
 	{
 		KTime kt(KT_COUNT_BOUNDS);
 		for (int i = 0; i < n_runs; ++i) {
 			const uint64_t m = run_off[i + 1] - run_off[i];
-			if (m) k_part_bounds<<<(unsigned)((m + 255) / 256), 256, 0, rt.stream>>>(y0 + run_off[i], m, run_off[i], g.pshift, g.n_parts - 1,
+			if (m) k_part_bounds<<<(unsigned)((m + 255) / 256), 256, 0, rt.stream>>>(key + run_off[i], m, run_off[i], g.pshift, g.n_parts - 1,
 			                                                                        start + (size_t)i * g.n_parts, end + (size_t)i * g.n_parts);
 		}
 	}
@@ -352,16 +409,13 @@ static int count_part_sorted(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_hi
 	const size_t smem = (size_t)g.blocks_per_part * CP_BLK_BYTES;
 	{
 		KTime kt(KT_COUNT_PART);
-		if (g.cfg == 0) k_count_part<256, 3, 10><<<g.n_parts, 256, smem, rt.stream>>>(p);
-		else if (g.cfg == 1) k_count_part<512, 3, 10><<<g.n_parts, 512, smem, rt.stream>>>(p);
-		else if (g.cfg == 2) k_count_part<256, 6, 9><<<g.n_parts, 256, smem, rt.stream>>>(p);
-		else if (g.cfg == 3) k_count_part<128, 12, 8><<<g.n_parts, 128, smem, rt.stream>>>(p);
-		else k_count_part<128, 6, 9><<<g.n_parts, 128, smem, rt.stream>>>(p);
+		REC_DISPATCH(vb, (k_count_part<VT, PK><<<g.n_parts, CP_THREADS, smem, rt.stream>>>(p)));
 	}
 	BFCG_LAUNCH_CHECK();
 	if (ch) {
-		KTime kt(KT_TAB_APPLY); // latency-bound (a load, then a CAS, per record): as many threads as the register file takes
-		k_tab_apply_marked<8><<<(unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)rt.sm_count * 8), 256, 0, rt.stream>>>(tab_view(ch), p.y0, p.y1, n);
+		KTime kt(KT_TAB_APPLY);
+		const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)rt.sm_count * 8);
+		REC_DISPATCH(vb, (k_tab_apply_marked<VT, PK><<<grid, 256, 0, rt.stream>>>(tab_view(ch), key, (const VT*)val, n)));
 	}
 	BFCG_LAUNCH_CHECK();
 	if (launched && (r = (*launched)()) != BFCG_OK) return r; // host work that should overlap the kernels just enqueued
@@ -375,29 +429,29 @@ static int count_part_sorted(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_hi
 	return BFCG_OK;
 }
 
-// K1'-K3' over n records in stream order (in_y0 / in_y1, device)
-static int count_part_window(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, bfc_ch_t *ch, const PartGeom &g, uint64_t blk_mask,
-                             const unsigned long long *in_y0, const unsigned long long *in_y1, uint64_t n, PartScratch &sc, bfcg_stats_t *stats,
+// K1'-K3' over n records in stream order (in_key / in_val, device)
+static int count_part_window(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, bfc_ch_t *ch, const PartGeom &g, uint64_t blk_mask, int vb,
+                             const unsigned long long *in_key, const void *in_val, uint64_t n, PartScratch &sc, bfcg_stats_t *stats,
                              const std::function<int()> *launched = 0)
 {
 	BfcgRuntime &rt = bfcg_rt();
 	int r;
 	unsigned long long before = 0;
 	if (ch && (r = tab_before_window(ch, n, &before)) != BFCG_OK) return r;
-	const unsigned long long *y0 = in_y0;
+	const unsigned long long *key = in_key;
 	if (g.pbits > 0) {
 		size_t tb = sc.tmp_bytes;
 		cudaError_t se;
 		{
 			KTime kt(KT_COUNT_SORT);
-			se = cub::DeviceRadixSort::SortPairs(sc.tmp, tb, in_y0, sc.s_y0, in_y1, sc.s_y1, (int64_t)n, g.pshift, g.pshift + g.pbits, rt.stream);
+			se = sort_records(sc.tmp, tb, vb, in_key, sc.s_key, in_val, sc.s_val, n, g.pshift, g.pshift + g.pbits);
 		}
 		BFCG_CUDA(se);
 		rt.n_launches += 1 + (g.pbits + 7) / 8; // histogram + one onesweep pass per 8 bits
-		y0 = sc.s_y0;
-	} else BFCG_CUDA(cudaMemcpyAsync(sc.s_y1, in_y1, n * 8, cudaMemcpyDeviceToDevice, rt.stream)); // y1 gets marked in place
+		key = sc.s_key;
+	} else BFCG_CUDA(cudaMemcpyAsync(sc.s_val, in_val, n * value_bytes(vb), cudaMemcpyDeviceToDevice, rt.stream)); // the values get marked in place
 	const uint64_t run_off[2] = { 0, n };
-	if ((r = count_part_sorted(opt, bf, bf_high, ch, g, blk_mask, y0, sc.s_y1, 1, run_off, sc.bounds, sc.ctr, stats, launched)) != BFCG_OK) return r;
+	if ((r = count_part_sorted(opt, bf, bf_high, ch, g, blk_mask, vb, key, sc.s_val, 1, run_off, sc.bounds, sc.ctr, stats, launched)) != BFCG_OK) return r;
 	return ch ? tab_after_window(ch, before) : BFCG_OK;
 }
 
@@ -405,18 +459,19 @@ static int part_kernel_setup()
 {
 	static bool done = false;
 	if (!done) {
-		BFCG_CUDA(cudaFuncSetAttribute(k_count_part<256, 3, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * CP_BLK_BYTES));
-		BFCG_CUDA(cudaFuncSetAttribute(k_count_part<512, 3, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * CP_BLK_BYTES));
-		BFCG_CUDA(cudaFuncSetAttribute(k_count_part<256, 6, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * CP_BLK_BYTES));
-		BFCG_CUDA(cudaFuncSetAttribute(k_count_part<128, 12, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * CP_BLK_BYTES));
-		BFCG_CUDA(cudaFuncSetAttribute(k_count_part<128, 6, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * CP_BLK_BYTES));
+		const int bytes = (1 << CP_SLOG2) * CP_BLK_BYTES;
+		BFCG_CUDA(cudaFuncSetAttribute(k_count_part<unsigned long long, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+		BFCG_CUDA(cudaFuncSetAttribute(k_count_part<uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+		BFCG_CUDA(cudaFuncSetAttribute(k_count_part<uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+		BFCG_CUDA(cudaFuncSetAttribute(k_count_part<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+		BFCG_CUDA(cudaFuncSetAttribute(k_count_part<unsigned long long, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
 		done = true;
 	}
 	return BFCG_OK;
 }
 
 // stream positions per window: as many as the free memory takes, at most 2^30
-static uint64_t window_positions(uint64_t n_positions, bool host, const PartGeom &g)
+static uint64_t window_positions(uint64_t n_positions, bool host, const PartGeom &g, int vb)
 {
 	const char *e = getenv("BFC_B200_COUNT_WINDOW");
 	uint64_t P = 1ULL << 30;
@@ -425,9 +480,16 @@ static uint64_t window_positions(uint64_t n_positions, bool host, const PartGeom
 		size_t fr = 0, tot = 0;
 		cudaMemGetInfo(&fr, &tot);
 		const double avail = 0.55 * (double)(fr + bfcg_rt().arena_bytes);
-		while (P > (1ULL << 22) && (double)(P * (host ? 36 : 32)) + (double)PartScratch::sort_temp(P, g) > avail) P >>= 1;
+		while (P > (1ULL << 22) && (double)(P * (2 * (8 + value_bytes(vb)) + (host ? 4 : 0))) + (double)sort_temp_bytes(vb, P, g.pshift, g.pshift + g.pbits) > avail) P >>= 1;
 	}
 	return std::min(P, el_padded(n_positions));
+}
+
+static void launch_enum_lin(int vb, const EnumLinParams &ep, uint64_t n_rec)
+{
+	BfcgRuntime &rt = bfcg_rt();
+	KTime kt(KT_ENUM_LIN);
+	REC_DISPATCH(vb, (k_enum_lin<VT, PK><<<(unsigned)(n_rec / EL_SEG), EL_THREADS, 0, rt.stream>>>(ep)));
 }
 
 int bfcg_count_part_batch(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, bfc_ch_t *ch, const bfcg_batch_t *batch, bfcg_stats_t *stats)
@@ -437,22 +499,24 @@ int bfcg_count_part_batch(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high,
 	if ((r = part_kernel_setup()) != BFCG_OK) return r;
 	const PartGeom g = part_geom(bf->n_shift, 0);
 	if (ch && (r = bfcg_tab_align_to_filter(ch, bf->n_shift - BFC_BLK_SHIFT)) != BFCG_OK) return r;
+	const int vb = getenv("BFC_B200_COUNT_WIRE") ? 0 : packed_value_bytes(opt->k); // records never leave the device: packed
 	const bool host = batch->where == BFCG_HOST;
 	const uint64_t nbytes = batch->n_bytes, halo = opt->k - 1;
-	const uint64_t P = window_positions(nbytes, host, g);
+	const uint64_t P = window_positions(nbytes, host, g, vb);
 	const uint64_t W = align_up(P + halo, 256);
 	PartScratch sc;
-	size_t o_stage[2][2] = {{0, 0}, {0, 0}}, o_y0, o_y1, o_sc, tot = 0;
+	size_t o_stage[2][2] = {{0, 0}, {0, 0}}, o_key, o_val, o_sc, tot = 0;
 	if (host)
 		for (int b = 0; b < 2; ++b)
 			for (int j = 0; j < 2; ++j) { o_stage[b][j] = tot; tot += W; }
-	o_y0 = tot; tot += align_up(P * 8, 256);
-	o_y1 = tot; tot += align_up(P * 8, 256);
-	o_sc = tot; tot += PartScratch::bytes(P, g);
+	o_key = tot; tot += align_up(P * 8, 256);
+	o_val = tot; tot += align_up(P * value_bytes(vb), 256);
+	o_sc = tot; tot += PartScratch::bytes(P, g, vb);
 	uint8_t *a = (uint8_t*)bfcg_arena(tot);
 	if (!a) return BFCG_ERR_NOMEM;
-	sc.carve(a + o_sc, P, g);
-	unsigned long long *rec_y0 = (unsigned long long*)(a + o_y0), *rec_y1 = (unsigned long long*)(a + o_y1);
+	sc.carve(a + o_sc, P, g, vb);
+	unsigned long long *rec_key = (unsigned long long*)(a + o_key);
+	void *rec_val = a + o_val;
 
 	const uint64_t n_win = (nbytes + P - 1) / P;
 	// host batches: the copy of window i+1 runs on its own stream while window i is counted
@@ -476,7 +540,7 @@ int bfcg_count_part_batch(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high,
 		const int b = (int)(wi & 1);
 		EnumLinParams ep;
 		memset(&ep, 0, sizeof(ep));
-		ep.k = opt->k, ep.q = opt->q, ep.rec_y0 = rec_y0, ep.rec_y1 = rec_y1;
+		ep.k = opt->k, ep.q = opt->q, ep.key = rec_key, ep.val = rec_val;
 		ep.len = e - w0, ep.emit_from = s - w0;
 		if (host) {
 			const cudaError_t ce = cudaStreamWaitEvent(rt.stream, rt.ev_in[b], 0);
@@ -484,7 +548,7 @@ int bfcg_count_part_batch(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high,
 			ep.seq = a + o_stage[b][0], ep.qual = batch->qual ? a + o_stage[b][1] : 0;
 		} else ep.seq = batch->seq + w0, ep.qual = batch->qual ? batch->qual + w0 : 0;
 		const uint64_t n_rec = el_padded(e - s);
-		{ KTime kt(KT_ENUM_LIN); k_enum_lin<<<(unsigned)(n_rec / EL_SEG), EL_THREADS, 0, rt.stream>>>(ep); }
+		launch_enum_lin(vb, ep, n_rec);
 		++rt.n_launches;
 		{ const cudaError_t le = cudaGetLastError(); if (le != cudaSuccess) { r = bfcg_fail(__func__, "kernel launch", le); break; } }
 		if (host) cudaEventRecord(rt.ev_free[b], rt.stream);
@@ -495,7 +559,7 @@ int bfcg_count_part_batch(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high,
 			const cudaError_t ce = issue_copy(wi + 1);
 			return ce == cudaSuccess ? BFCG_OK : bfcg_fail("bfcg_count_part_batch", "staging copy", ce);
 		};
-		r = count_part_window(opt, bf, bf_high, ch, g, ~0ULL, rec_y0, rec_y1, n_rec, sc, stats, &next_copy);
+		r = count_part_window(opt, bf, bf_high, ch, g, ~0ULL, vb, rec_key, rec_val, n_rec, sc, stats, &next_copy);
 	}
 	if (host) cudaStreamSynchronize(rt.copy_in);
 	if (r != BFCG_OK) { cudaStreamSynchronize(rt.stream); return r; }
@@ -504,6 +568,7 @@ int bfcg_count_part_batch(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high,
 	return BFCG_OK;
 }
 
+// records in stream order in the wire format (count.cu's bucket exchange): partitioned here
 int bfcg_count_part_records(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, bfc_ch_t *ch, uint64_t n_rec,
                             const uint64_t *d_y0, const uint64_t *d_y1, int owner_bits, bfcg_stats_t *stats)
 {
@@ -512,16 +577,16 @@ int bfcg_count_part_records(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_hig
 	if ((r = part_kernel_setup()) != BFCG_OK) return r;
 	const PartGeom g = part_geom(bf->n_shift, owner_bits);
 	if (ch && (r = bfcg_tab_align_to_filter(ch, bf->n_shift - BFC_BLK_SHIFT)) != BFCG_OK) return r;
-	const uint64_t P = std::min<uint64_t>(window_positions(n_rec, false, g), n_rec);
+	const uint64_t P = std::min<uint64_t>(window_positions(n_rec, false, g, 0), n_rec);
 	PartScratch sc;
-	uint8_t *a = (uint8_t*)bfcg_arena(PartScratch::bytes(P, g));
+	uint8_t *a = (uint8_t*)bfcg_arena(PartScratch::bytes(P, g, 0));
 	if (!a) return BFCG_ERR_NOMEM;
-	sc.carve(a, P, g);
+	sc.carve(a, P, g, 0);
 	const uint64_t blk_mask = (1ULL << g.x) - 1; // this rank holds 1/n_owners of the blocks
 	BfcgTimer timer(stats);
 	for (uint64_t s = 0; s < n_rec; s += P) {
 		const uint64_t n = std::min(P, n_rec - s);
-		if ((r = count_part_window(opt, bf, bf_high, ch, g, blk_mask, (const unsigned long long*)d_y0 + s, (const unsigned long long*)d_y1 + s, n, sc, stats)) != BFCG_OK) return r;
+		if ((r = count_part_window(opt, bf, bf_high, ch, g, blk_mask, 0, (const unsigned long long*)d_y0 + s, d_y1 + s, n, sc, stats)) != BFCG_OK) return r;
 	}
 	timer.stop();
 	BFCG_CUDA(cudaStreamSynchronize(rt.stream));
@@ -542,10 +607,7 @@ int bfcg_enum_part_records(const bfc_opt_t *opt, const bfcg_batch_t *batch, int 
 	const bool host = batch->where == BFCG_HOST;
 	const uint64_t nb = batch->n_bytes, n_rec = el_padded(nb);
 	const int sort_bits = g.pbits + owner_bits;
-	size_t temp = 0;
-	if (sort_bits > 0)
-		cub::DeviceRadixSort::SortPairs((void*)0, temp, (const unsigned long long*)0, (unsigned long long*)0, (const unsigned long long*)0,
-		                                (unsigned long long*)0, (int64_t)n_rec, g.pshift, g.pshift + sort_bits, rt.stream);
+	size_t temp = sort_temp_bytes(0, n_rec, g.pshift, g.pshift + sort_bits);
 	size_t o_seq = 0, o_qual = 0, o_y0, o_y1, o_tmp, o_bnd, tot = 0;
 	if (host) { o_seq = tot; tot = align_up(tot + nb, 256); o_qual = tot; tot = align_up(tot + nb, 256); }
 	o_y0 = tot; tot = align_up(tot + n_rec * 8, 256);
@@ -557,27 +619,26 @@ int bfcg_enum_part_records(const bfc_opt_t *opt, const bfcg_batch_t *batch, int 
 	EnumLinParams ep;
 	memset(&ep, 0, sizeof(ep));
 	ep.k = opt->k, ep.q = opt->q, ep.len = nb, ep.emit_from = 0;
-	ep.rec_y0 = (unsigned long long*)(a + o_y0), ep.rec_y1 = (unsigned long long*)(a + o_y1); // n_rec (padded) records
+	ep.key = (unsigned long long*)(a + o_y0), ep.val = a + o_y1; // n_rec (padded) records, wire format
 	if (host) {
 		BFCG_CUDA(cudaMemcpyAsync(a + o_seq, batch->seq, nb, cudaMemcpyHostToDevice, rt.stream));
 		if (batch->qual) BFCG_CUDA(cudaMemcpyAsync(a + o_qual, batch->qual, nb, cudaMemcpyHostToDevice, rt.stream));
 		ep.seq = a + o_seq, ep.qual = batch->qual ? a + o_qual : 0;
 	} else ep.seq = batch->seq, ep.qual = batch->qual;
-	{ KTime kt(KT_ENUM_LIN); k_enum_lin<<<(unsigned)(n_rec / EL_SEG), EL_THREADS, 0, rt.stream>>>(ep); }
+	launch_enum_lin(0, ep, n_rec);
 	BFCG_LAUNCH_CHECK();
 	// the caller's arrays hold batch->n_bytes records: the padding (no k-mer ends there) stays behind
 	if (sort_bits > 0) {
 		cudaError_t se;
 		{
 			KTime kt(KT_COUNT_SORT);
-			se = cub::DeviceRadixSort::SortPairs(a + o_tmp, temp, ep.rec_y0, (unsigned long long*)d_y0, ep.rec_y1, (unsigned long long*)d_y1,
-			                                     (int64_t)nb, g.pshift, g.pshift + sort_bits, rt.stream);
+			se = sort_records(a + o_tmp, temp, 0, ep.key, (unsigned long long*)d_y0, ep.val, d_y1, nb, g.pshift, g.pshift + sort_bits);
 		}
 		BFCG_CUDA(se);
 		rt.n_launches += 1 + (sort_bits + 7) / 8;
 	} else {
-		BFCG_CUDA(cudaMemcpyAsync(d_y0, ep.rec_y0, nb * 8, cudaMemcpyDeviceToDevice, rt.stream));
-		BFCG_CUDA(cudaMemcpyAsync(d_y1, ep.rec_y1, nb * 8, cudaMemcpyDeviceToDevice, rt.stream));
+		BFCG_CUDA(cudaMemcpyAsync(d_y0, ep.key, nb * 8, cudaMemcpyDeviceToDevice, rt.stream));
+		BFCG_CUDA(cudaMemcpyAsync(d_y1, ep.val, nb * 8, cudaMemcpyDeviceToDevice, rt.stream));
 	}
 	uint32_t h_bnd[2 * 8];
 	memset(h_bnd, 0, sizeof(h_bnd));
@@ -614,7 +675,7 @@ int bfcg_count_part_runs(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, 
 	BfcgTimer timer(stats);
 	unsigned long long before = 0;
 	if (ch && (r = tab_before_window(ch, n, &before)) != BFCG_OK) return r;
-	if ((r = count_part_sorted(opt, bf, bf_high, ch, g, (1ULL << g.x) - 1, (const unsigned long long*)d_y0, (unsigned long long*)d_y1, n_runs, run_off,
+	if ((r = count_part_sorted(opt, bf, bf_high, ch, g, (1ULL << g.x) - 1, 0, (const unsigned long long*)d_y0, d_y1, n_runs, run_off,
 	                           (uint32_t*)a, (unsigned long long*)(a + align_up((size_t)n_runs * g.n_parts * 8, 256)), stats, 0)) != BFCG_OK) return r;
 	if (ch && (r = tab_after_window(ch, before)) != BFCG_OK) return r;
 	timer.stop();
