@@ -567,7 +567,17 @@ __global__ void __launch_bounds__(EC_THREADS, EC_CTAS_PER_SM) k_ec_search(EcPara
 						if (has_c) z.n_absent += (int)(c >> 3 & 1);
 						bfc_kmer_append(k, z.x, b);
 						if (heap_n == 0) top_valid = true;
-						else if (!job_done) {
+						else if (heap_n <= 3 && (uint32_t)z.tot_pen <= hk_pen(heapk.get(0))) {
+							// Not above the cheapest other state: pushed, the successor rises to the root (ties keep rising
+							// in ks_heapup) and the pop that follows hands it straight back.  The up-to-3 other keys end
+							// where they were, except that two keys of equal penalty swap places (ksort.h:125-146 worked
+							// through, as for the jumps below) -- so z stays in registers and the heap is not touched.
+							if (heap_n == 2) {
+								const uint32_t k0 = heapk.get(0), k1 = heapk.get(1);
+								if (hk_pen(k0) == hk_pen(k1)) heapk.set(0, k1), heapk.set(1, k0);
+							}
+							top_valid = true;
+						} else if (!job_done) {
 							uint32_t id;
 							if (heap_n < n_init) id = heapk.get(heap_n) & 0xfff;
 							else id = (uint32_t)n_init++;
