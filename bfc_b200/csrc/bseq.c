@@ -29,6 +29,8 @@ typedef struct { size_t l, m; char *s; } str_t;
 struct bseq_file_s {
 	gzFile fp;
 	unsigned char *buf;
+	const unsigned char *pre; /* text to consume before the file (fqblock.c hands its unread block over), owned */
+	size_t pre_len, pre_pos;
 	int begin, end, eof;
 	int pending;            /* header character already consumed ('>' or '@'), or 0 */
 	int comment_seen;       /* comment.s is valid (sticky, see above) */
@@ -45,6 +47,12 @@ static inline void str_reserve(str_t *s, size_t need)
 
 static int rd_fill(bseq_file_t *f)
 {
+	if (f->pre_pos < f->pre_len) {
+		const size_t n = f->pre_len - f->pre_pos < RD_BUF ? f->pre_len - f->pre_pos : RD_BUF;
+		memcpy(f->buf, f->pre + f->pre_pos, n);
+		f->pre_pos += n, f->begin = 0, f->end = (int)n;
+		return 1;
+	}
 	if (f->eof) return 0;
 	f->begin = 0;
 	f->end = gzread(f->fp, f->buf, RD_BUF);
@@ -66,7 +74,7 @@ static long rd_until(bseq_file_t *f, int line, str_t *str, int *dret, int append
 {
 	if (dret) *dret = 0;
 	if (!append) str->l = 0;
-	if (f->begin >= f->end && f->eof) return -1;
+	if (f->begin >= f->end && f->eof && f->pre_pos >= f->pre_len) return -1;
 	for (;;) {
 		int i;
 		if (f->begin >= f->end && !rd_fill(f)) break;
@@ -131,10 +139,28 @@ bseq_file_t *bseq_open(const char *fn)
 	return f;
 }
 
+/* fqblock.c: go on with an open stream in the tolerant parser; `pre` (malloc'd, taken over) is read before the file,
+ * `comment` is kseq's sticky comment so far (NULL = none seen) */
+bseq_file_t *bseq_open_from(void *gz, unsigned char *pre, size_t pre_len, const char *comment)
+{
+	bseq_file_t *f = (bseq_file_t*)calloc(1, sizeof(bseq_file_t));
+	f->fp = (gzFile)gz;
+	f->buf = (unsigned char*)malloc(RD_BUF);
+	f->pre = pre, f->pre_len = pre_len;
+	if (comment) {
+		const size_t l = strlen(comment);
+		str_reserve(&f->comment, l + 2);
+		memcpy(f->comment.s, comment, l + 1);
+		f->comment.l = l, f->comment_seen = 1;
+	}
+	return f;
+}
+
 void bseq_close(bseq_file_t *f)
 {
 	if (f == 0) return;
 	gzclose(f->fp);
+	free((void*)f->pre);
 	free(f->name.s); free(f->comment.s); free(f->seq.s); free(f->qual.s); free(f->buf);
 	free(f);
 }

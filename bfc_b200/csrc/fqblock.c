@@ -1,0 +1,487 @@
+/* fqblock.c -- block-wise FASTA/FASTQ ingest and egress (see fqblock.h). */
+#include <zlib.h>
+#include <ctype.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include "bfc.h"
+#include "fqblock.h"
+
+bseq_file_t *bseq_open_from(void *gz, unsigned char *pre, size_t pre_len, const char *comment); /* bseq.c */
+
+struct fq_reader_s {
+	gzFile fp;
+	int fd;                     /* >= 0: an uncompressed regular file, read with parallel pread()s; the gzFile then only
+	                               serves the hand-over to the tolerant parser (repositioned with gzseek) */
+	int64_t pos, size;
+	int n_threads, eof, fast;
+	char *carry;                /* text read but not yet delivered (the incomplete tail of the previous block) */
+	size_t carry_len;
+	char *last_comment;         /* kseq's sticky comment (bseq.c header) */
+	bseq_file_t *slow;          /* the tolerant parser, once the input stopped being plain four-line FASTQ */
+};
+
+fq_reader_t *fq_open(const char *fn, int n_threads)
+{
+	gzFile g = fn && strcmp(fn, "-") ? gzopen(fn, "r") : gzdopen(fileno(stdin), "r");
+	fq_reader_t *r;
+	if (g == 0) return 0;
+	gzbuffer(g, 1 << 20);
+	r = (fq_reader_t*)calloc(1, sizeof(fq_reader_t));
+	r->fp = g, r->n_threads = n_threads < 1 ? 1 : n_threads, r->fast = 1, r->fd = -1;
+	if (fn && strcmp(fn, "-")) { /* plain regular file? (zlib would copy it through its own buffer on one thread) */
+		struct stat st;
+		unsigned char magic[2] = {0, 0};
+		const int fd = open(fn, O_RDONLY);
+		if (fd >= 0 && fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && !(pread(fd, magic, 2, 0) == 2 && magic[0] == 0x1f && magic[1] == 0x8b))
+			r->fd = fd, r->size = (int64_t)st.st_size;
+		else if (fd >= 0) close(fd);
+	}
+	return r;
+}
+
+typedef struct { int fd; char *dst; int64_t pos, len; int err; } pread_t;
+#define PREAD_PIECE (8 << 20)
+
+static void pread_worker(void *data, long i, int tid)
+{
+	pread_t *p = (pread_t*)data;
+	int64_t o = i * (int64_t)PREAD_PIECE, e = o + PREAD_PIECE < p->len ? o + PREAD_PIECE : p->len;
+	(void)tid;
+	while (o < e) {
+		const ssize_t got = pread(p->fd, p->dst + o, (size_t)(e - o), (off_t)(p->pos + o));
+		if (got <= 0) { p->err = 1; return; }
+		o += got;
+	}
+}
+
+/* up to `want` more bytes of input at dst; 0 at end of input */
+static size_t rd_more(fq_reader_t *rd, char *dst, size_t want)
+{
+	if (rd->fd >= 0) {
+		pread_t p;
+		p.fd = rd->fd, p.dst = dst, p.pos = rd->pos, p.err = 0;
+		p.len = rd->size - rd->pos < (int64_t)want ? rd->size - rd->pos : (int64_t)want;
+		if (p.len <= 0) return 0;
+		kt_for(rd->n_threads, pread_worker, &p, (long)((p.len + PREAD_PIECE - 1) / PREAD_PIECE));
+		if (p.err) return 0;
+		rd->pos += p.len;
+		return (size_t)p.len;
+	} else {
+		const int got = gzread(rd->fp, dst, (unsigned)(want > (1u << 30) ? (1u << 30) : want));
+		return got > 0 ? (size_t)got : 0;
+	}
+}
+
+void fq_close(fq_reader_t *r)
+{
+	if (r == 0) return;
+	if (r->slow) bseq_close(r->slow); /* owns the stream by now */
+	else gzclose(r->fp);
+	if (r->fd >= 0) close(r->fd);
+	free(r->carry); free(r->last_comment);
+	free(r);
+}
+
+int fq_reader_is_fast(const fq_reader_t *r) { return r->fast; }
+
+void fq_block_free(fq_block_t *b)
+{
+	free(b->buf); free(b->name_off); free(b->com_off); free(b->seq_off); free(b->qual_off);
+	free(b->name_len); free(b->com_len); free(b->seq_len);
+	memset(b, 0, sizeof(*b));
+}
+
+static int blk_alloc(fq_block_t *b, int64_t n)
+{
+	const size_t m = n > 0 ? (size_t)n : 1;
+	b->n = n;
+	b->name_off = (uint64_t*)malloc(m * 8), b->com_off = (uint64_t*)malloc(m * 8);
+	b->seq_off = (uint64_t*)malloc(m * 8), b->qual_off = (uint64_t*)malloc(m * 8);
+	b->name_len = (uint32_t*)malloc(m * 4), b->com_len = (uint32_t*)malloc(m * 4), b->seq_len = (uint32_t*)malloc(m * 4);
+	return b->name_off && b->com_off && b->seq_off && b->qual_off && b->name_len && b->com_len && b->seq_len ? 0 : -1;
+}
+
+/* ---------------------------------------------------------------- the parallel path */
+
+typedef struct {
+	const char *s;
+	size_t len;
+	int n_parts;
+	size_t *cnt;        /* newlines per part, then exclusive prefix */
+	uint64_t *nl;       /* positions of the newlines */
+	/* phase 2 */
+	fq_block_t *b;
+	int keep_comment, bad;
+} split_t;
+
+static void part_range(const split_t *sp, long i, size_t *lo, size_t *hi)
+{
+	*lo = sp->len / sp->n_parts * i;
+	*hi = i + 1 == sp->n_parts ? sp->len : sp->len / sp->n_parts * (i + 1);
+}
+
+static void count_nl_worker(void *data, long i, int tid)
+{
+	split_t *sp = (split_t*)data;
+	size_t lo, hi, c = 0;
+	const char *p, *e;
+	(void)tid;
+	part_range(sp, i, &lo, &hi);
+	for (p = sp->s + lo, e = sp->s + hi; p < e && (p = (const char*)memchr(p, '\n', e - p)) != 0; ++p) ++c;
+	sp->cnt[i] = c;
+}
+
+static void fill_nl_worker(void *data, long i, int tid)
+{
+	split_t *sp = (split_t*)data;
+	size_t lo, hi;
+	uint64_t *out = sp->nl + sp->cnt[i];
+	const char *p, *e;
+	(void)tid;
+	part_range(sp, i, &lo, &hi);
+	for (p = sp->s + lo, e = sp->s + hi; p < e && (p = (const char*)memchr(p, '\n', e - p)) != 0; ++p) *out++ = (uint64_t)(p - sp->s);
+}
+
+#define REC_PER_ITEM 4096
+
+/* records [i * REC_PER_ITEM, ...): four lines each; anything kseq would read differently flags the block */
+static void parse_worker(void *data, long i, int tid)
+{
+	split_t *sp = (split_t*)data;
+	fq_block_t *b = sp->b;
+	const char *s = sp->s;
+	int64_t r, r1 = (i + 1) * (int64_t)REC_PER_ITEM < b->n ? (i + 1) * (int64_t)REC_PER_ITEM : b->n;
+	(void)tid;
+	for (r = i * (int64_t)REC_PER_ITEM; r < r1; ++r) {
+		const uint64_t l0 = r ? sp->nl[4 * r - 1] + 1 : 0, e0 = sp->nl[4 * r], e1 = sp->nl[4 * r + 1], e2 = sp->nl[4 * r + 2], e3 = sp->nl[4 * r + 3];
+		const uint64_t l1 = e0 + 1, l2 = e1 + 1, l3 = e2 + 1;
+		uint64_t p;
+		if (e0 == l0 || s[l0] != '@' || e1 == l1 || s[l2] != '+' || e2 == l2 || e3 - l3 != e1 - l1 ||
+			s[l1] == '>' || s[l1] == '+' || s[l1] == '@' || s[e0 - 1] == '\r' || s[e1 - 1] == '\r' || s[e2 - 1] == '\r' || s[e3 - 1] == '\r' ||
+			e1 - l1 > 0x7fffffffULL) { sp->bad = 1; return; }
+		for (p = l0 + 1; p < e0 && !isspace((unsigned char)s[p]); ++p) {}
+		b->name_off[r] = l0 + 1, b->name_len[r] = (uint32_t)(p - (l0 + 1));
+		if (p < e0) b->com_off[r] = p + 1, b->com_len[r] = (uint32_t)(e0 - (p + 1)); /* the rest of the line after ONE delimiter */
+		else b->com_off[r] = FQ_NONE, b->com_len[r] = 0;
+		b->seq_off[r] = l1, b->seq_len[r] = (uint32_t)(e1 - l1), b->qual_off[r] = l3;
+	}
+}
+
+/* kseq never clears its comment buffer: a record without one inherits the latest (bseq.c header) */
+static void sticky_comments(fq_reader_t *rd, fq_block_t *b, int keep_comment)
+{
+	int64_t r, last = -1;
+	for (r = 0; r < b->n; ++r) {
+		if (b->com_off[r] != FQ_NONE) last = r;
+		else if (keep_comment) {
+			if (last >= 0) b->com_off[r] = b->com_off[last], b->com_len[r] = b->com_len[last];
+			else if (rd->last_comment) b->com_off[r] = FQ_NONE - 1; /* patched below: lives outside this block */
+		}
+	}
+	if (keep_comment && rd->last_comment) { /* comments inherited from an earlier block: append the text to the block */
+		const size_t l = strlen(rd->last_comment);
+		int any = 0;
+		for (r = 0; r < b->n && b->com_off[r] == FQ_NONE - 1; ++r) any = 1;
+		if (any) {
+			b->buf = (char*)realloc(b->buf, b->buf_len + l + 1);
+			memcpy(b->buf + b->buf_len, rd->last_comment, l + 1);
+			for (r = 0; r < b->n && b->com_off[r] == FQ_NONE - 1; ++r) b->com_off[r] = b->buf_len, b->com_len[r] = (uint32_t)l;
+			b->buf_len += l + 1;
+		}
+	}
+	if (last >= 0) {
+		free(rd->last_comment);
+		rd->last_comment = (char*)malloc((size_t)b->com_len[last] + 1);
+		memcpy(rd->last_comment, b->buf + b->com_off[last], b->com_len[last]);
+		rd->last_comment[b->com_len[last]] = 0;
+	}
+	if (!keep_comment) for (r = 0; r < b->n; ++r) b->com_off[r] = FQ_NONE, b->com_len[r] = 0;
+}
+
+/* 1 = block delivered, 0 = not plain four-line FASTQ (nothing consumed; *data is handed back), -1 = out of memory */
+static int fast_block(fq_reader_t *rd, char *data, size_t len, int keep_comment, fq_block_t *b, size_t *used)
+{
+	split_t sp;
+	size_t run = 0, n_lines;
+	long i;
+	int64_t r;
+	memset(&sp, 0, sizeof(sp));
+	sp.s = data, sp.len = len, sp.n_parts = rd->n_threads * 4;
+	if (len == 0 || data[0] != '@') return 0;
+	sp.cnt = (size_t*)calloc((size_t)sp.n_parts + 1, sizeof(size_t));
+	kt_for(rd->n_threads, count_nl_worker, &sp, sp.n_parts);
+	for (i = 0; i < sp.n_parts; ++i) { const size_t c = sp.cnt[i]; sp.cnt[i] = run; run += c; }
+	n_lines = run;
+	sp.nl = (uint64_t*)malloc((n_lines + 2) * sizeof(uint64_t));
+	if (sp.nl == 0) { free(sp.cnt); return -1; }
+	kt_for(rd->n_threads, fill_nl_worker, &sp, sp.n_parts);
+	if (rd->eof && (n_lines == 0 || sp.nl[n_lines - 1] + 1 != len)) sp.nl[n_lines++] = len; /* last line without a newline */
+	if (n_lines < 4 || (rd->eof && n_lines % 4 != 0)) { free(sp.cnt); free(sp.nl); return 0; }
+	memset(b, 0, sizeof(*b));
+	if (blk_alloc(b, (int64_t)(n_lines / 4)) < 0) { free(sp.cnt); free(sp.nl); fq_block_free(b); return -1; }
+	sp.b = b, sp.keep_comment = keep_comment;
+	kt_for(rd->n_threads, parse_worker, &sp, (long)((b->n + REC_PER_ITEM - 1) / REC_PER_ITEM));
+	*used = sp.nl[4 * b->n - 1] + 1 > len ? len : sp.nl[4 * b->n - 1] + 1;
+	free(sp.cnt); free(sp.nl);
+	if (sp.bad) { fq_block_free(b); return 0; }
+	b->buf = data, b->buf_len = len, b->any_qual = 1;
+	for (r = 0; r < b->n; ++r) b->n_bases += b->seq_len[r];
+	sticky_comments(rd, b, keep_comment);
+	return 1;
+}
+
+/* ---------------------------------------------------------------- the tolerant path */
+
+static int slow_block(fq_reader_t *rd, size_t target, int keep_comment, fq_block_t *b)
+{
+	int n = 0, i;
+	const long chunk = target > 0x7fffffffUL / 2 ? 0x7fffffff / 2 : (long)(target / 2 + 1); /* bases ~ half of the text */
+	bseq1_t *seqs = bseq_read(rd->slow, (int)chunk, keep_comment, &n);
+	size_t tot = 0, at = 0;
+	memset(b, 0, sizeof(*b));
+	if (seqs == 0 || n == 0) { free(seqs); return 0; }
+	for (i = 0; i < n; ++i)
+		tot += strlen(seqs[i].name) + 1 + (seqs[i].comment ? strlen(seqs[i].comment) + 1 : 0) + (size_t)seqs[i].l_seq * (seqs[i].qual ? 2 : 1) + 2;
+	if (blk_alloc(b, n) < 0 || (b->buf = (char*)malloc(tot + 1)) == 0) { fq_block_free(b); return -1; }
+	for (i = 0; i < n; ++i) {
+		bseq1_t *s = &seqs[i];
+		size_t l = strlen(s->name);
+		memcpy(b->buf + at, s->name, l + 1); b->name_off[i] = at, b->name_len[i] = (uint32_t)l; at += l + 1;
+		if (s->comment) { l = strlen(s->comment); memcpy(b->buf + at, s->comment, l + 1); b->com_off[i] = at, b->com_len[i] = (uint32_t)l; at += l + 1; }
+		else b->com_off[i] = FQ_NONE, b->com_len[i] = 0;
+		memcpy(b->buf + at, s->seq, (size_t)s->l_seq + 1); b->seq_off[i] = at, b->seq_len[i] = (uint32_t)s->l_seq; at += (size_t)s->l_seq + 1;
+		if (s->qual) { memcpy(b->buf + at, s->qual, (size_t)s->l_seq + 1); b->qual_off[i] = at; at += (size_t)s->l_seq + 1; b->any_qual = 1; }
+		else b->qual_off[i] = FQ_NONE;
+		b->n_bases += (uint64_t)s->l_seq;
+		free(s->name); free(s->comment); free(s->seq); free(s->qual);
+	}
+	b->buf_len = at;
+	free(seqs);
+	return 1;
+}
+
+int fq_next(fq_reader_t *rd, size_t target, int keep_comment, fq_block_t *b)
+{
+	memset(b, 0, sizeof(*b));
+	if (target < 4096) target = 4096;
+	while (rd->fast) {
+		const size_t carry0 = rd->carry_len;
+		char *data = (char*)malloc(carry0 + target + 1);
+		size_t len = carry0, used = 0;
+		int rc;
+		if (data == 0) return 0;
+		if (carry0) memcpy(data, rd->carry, carry0);
+		free(rd->carry); rd->carry = 0, rd->carry_len = 0;
+		while (!rd->eof && len < carry0 + target) {
+			const size_t got = rd_more(rd, data + len, carry0 + target - len);
+			if (got == 0) { rd->eof = 1; break; }
+			len += got;
+		}
+		if (len == 0) { free(data); return 0; }
+		rc = fast_block(rd, data, len, keep_comment, b, &used);
+		if (rc == 1) {
+			if (used < len) { /* the incomplete tail waits for the next block */
+				rd->carry_len = len - used;
+				rd->carry = (char*)malloc(rd->carry_len);
+				memcpy(rd->carry, b->buf + used, rd->carry_len); /* (b->buf: sticky_comments may have moved the text) */
+			}
+			return 1;
+		}
+		if (rc < 0) { free(data); return 0; }
+		/* not plain four-line FASTQ: the tolerant parser takes the stream over, starting with this block's text */
+		rd->fast = 0;
+		if (rd->fd >= 0) gzseek(rd->fp, (z_off_t)rd->pos, SEEK_SET); /* the stream goes on where the pread()s stopped */
+		rd->slow = bseq_open_from(rd->fp, (unsigned char*)data, len, rd->last_comment);
+	}
+	return slow_block(rd, target, keep_comment, b) == 1;
+}
+
+/* ---------------------------------------------------------------- flat batch */
+
+typedef struct { fq_flat_t *f; const fq_block_t *b; } fill_t;
+
+static void fill_worker(void *data, long i, int tid)
+{
+	fill_t *ft = (fill_t*)data;
+	const fq_block_t *b = ft->b;
+	fq_flat_t *f = ft->f;
+	int64_t r, r1 = (i + 1) * (int64_t)REC_PER_ITEM < b->n ? (i + 1) * (int64_t)REC_PER_ITEM : b->n;
+	(void)tid;
+	for (r = i * (int64_t)REC_PER_ITEM; r < r1; ++r) {
+		const uint64_t o = f->off[r];
+		const uint32_t l = b->seq_len[r];
+		memcpy(f->b.seq + o, b->buf + b->seq_off[r], l);
+		f->b.seq[o + l] = 0;
+		if (f->b.qual) {
+			if (b->qual_off[r] != FQ_NONE) memcpy(f->b.qual + o, b->buf + b->qual_off[r], l);
+			else memset(f->b.qual + o, 0xFF, l); /* "no quality" marker (bfc_b200.h) */
+			f->b.qual[o + l] = 0;
+		}
+	}
+}
+
+/* pinning host memory costs ~0.3 s per GB: buffers released by one phase are parked here for the next one */
+#define FLAT_CACHE 4
+static struct { uint8_t *seq, *qual; size_t cap; } flat_cache[FLAT_CACHE];
+
+static int flat_cache_take(fq_flat_t *f, size_t need)
+{
+	int i;
+	for (i = 0; i < FLAT_CACHE; ++i)
+		if (flat_cache[i].seq && flat_cache[i].cap >= need) {
+			f->seq_buf = flat_cache[i].seq, f->qual_buf = flat_cache[i].qual, f->cap_bytes = flat_cache[i].cap, f->pinned = 1;
+			flat_cache[i].seq = 0;
+			return 1;
+		}
+	return 0;
+}
+
+static int flat_cache_put(uint8_t *seq, uint8_t *qual, size_t cap)
+{
+	int i;
+	for (i = 0; i < FLAT_CACHE; ++i)
+		if (flat_cache[i].seq == 0) { flat_cache[i].seq = seq, flat_cache[i].qual = qual, flat_cache[i].cap = cap; return 1; }
+	return 0;
+}
+
+int fq_flat_fill(fq_flat_t *f, const fq_block_t *b, int n_threads)
+{
+	const size_t need = (size_t)(b->n_bases + (uint64_t)b->n) + 1;
+	int64_t r;
+	uint64_t tot = 0;
+	fill_t ft;
+	if (need > f->cap_bytes) { /* grow-only, reused from batch to batch: pinning memory is expensive */
+		fq_flat_t old = *f;
+		if (!flat_cache_take(f, need)) {
+			f->cap_bytes = need + need / 8;
+			f->seq_buf = (uint8_t*)bfcg_host_alloc_pinned(f->cap_bytes);
+			f->qual_buf = f->seq_buf ? (uint8_t*)bfcg_host_alloc_pinned(f->cap_bytes) : 0;
+			f->pinned = f->seq_buf && f->qual_buf;
+			if (!f->pinned) { /* pageable memory works too: the copies just do not overlap */
+				if (f->seq_buf) bfcg_host_free_pinned(f->seq_buf);
+				f->seq_buf = (uint8_t*)malloc(f->cap_bytes), f->qual_buf = (uint8_t*)malloc(f->cap_bytes);
+			}
+		}
+		if (old.pinned) { bfcg_host_free_pinned(old.seq_buf); bfcg_host_free_pinned(old.qual_buf); }
+		else { free(old.seq_buf); free(old.qual_buf); }
+		if (f->seq_buf == 0 || f->qual_buf == 0) return -1;
+	}
+	if ((size_t)b->n + 1 > f->cap_reads) {
+		free(f->off);
+		f->cap_reads = (size_t)b->n + 1 + (size_t)b->n / 8;
+		f->off = (uint64_t*)malloc(f->cap_reads * 8);
+		if (f->off == 0) return -1;
+	}
+	for (r = 0; r < b->n; ++r) { f->off[r] = tot; tot += (uint64_t)b->seq_len[r] + 1; }
+	f->off[b->n] = tot;
+	f->b.n_reads = b->n, f->b.n_bytes = tot, f->b.where = BFCG_HOST, f->b.off = f->off;
+	f->b.seq = f->seq_buf, f->b.qual = b->any_qual ? f->qual_buf : 0;
+	ft.f = f, ft.b = b;
+	kt_for(n_threads, fill_worker, &ft, (long)((b->n + REC_PER_ITEM - 1) / REC_PER_ITEM));
+	return 0;
+}
+
+void fq_flat_free(fq_flat_t *f)
+{
+	if (f->pinned && f->seq_buf && flat_cache_put(f->seq_buf, f->qual_buf, f->cap_bytes)) {}
+	else if (f->pinned) { bfcg_host_free_pinned(f->seq_buf); bfcg_host_free_pinned(f->qual_buf); }
+	else { free(f->seq_buf); free(f->qual_buf); }
+	free(f->off);
+	memset(f, 0, sizeof(*f));
+}
+
+/* ---------------------------------------------------------------- writer */
+
+typedef struct {
+	const fq_block_t *b;
+	const fq_flat_t *flat;
+	const fq_out_t *o;
+	int n_items;
+	char **piece;
+	size_t *piece_len;
+	int oom;
+} wr_t;
+
+static inline char *put_uint(char *p, unsigned v)
+{
+	char t[12];
+	int n = 0;
+	do { t[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+	while (n) *p++ = t[--n];
+	return p;
+}
+
+static void write_worker(void *data, long i, int tid)
+{
+	wr_t *w = (wr_t*)data;
+	const fq_block_t *b = w->b;
+	const fq_out_t *o = w->o;
+	const int64_t per = (b->n + w->n_items - 1) / w->n_items;
+	const int64_t r0 = i * per, r1 = r0 + per < b->n ? r0 + per : b->n;
+	int64_t r;
+	size_t cap = 16;
+	char *out, *p;
+	(void)tid;
+	for (r = r0; r < r1; ++r) cap += (size_t)b->name_len[r] + b->com_len[r] + 2 * (size_t)b->seq_len[r] + 96;
+	out = p = (char*)malloc(cap);
+	if (out == 0) { w->oom = 1; w->piece[i] = 0, w->piece_len[i] = 0; return; }
+	for (r = r0; r < r1; ++r) {
+		const uint64_t fo = w->flat->b.off[r];
+		const int has_qual = b->qual_off[r] != FQ_NONE && w->flat->b.qual != 0;
+		const int is_fq = has_qual && !o->no_qual;
+		const uint8_t *seq = w->flat->b.seq + fo, *qual = has_qual ? w->flat->b.qual + fo : 0;
+		uint32_t l = b->seq_len[r];
+		if (!o->filter_mode) { /* correct.c:596-603 */
+			const uint32_t aux = o->aux[2 * r], aux2 = o->aux[2 * r + 1];
+			if (o->discard && (aux & 7)) continue;
+			*p++ = is_fq ? '@' : '>';
+			memcpy(p, b->buf + b->name_off[r], b->name_len[r]); p += b->name_len[r];
+			if (b->com_off[r] == FQ_NONE) {
+				memcpy(p, "\tec:Z:", 6); p += 6;
+				p = put_uint(p, aux & 7);
+				if ((aux & 7) == 0) {
+					*p++ = '_'; p = put_uint(p, aux2 >> 10); *p++ = ':'; p = put_uint(p, aux2 & 0xff);
+					*p++ = '_'; p = put_uint(p, aux >> 3 & 1);
+					*p++ = '_'; p = put_uint(p, aux >> 18 & 0x3fff); *p++ = ':'; p = put_uint(p, aux >> 4 & 0x3fff);
+					*p++ = '_'; p = put_uint(p, aux2 >> 8 & 3);
+				}
+			} else { *p++ = '\t'; memcpy(p, b->buf + b->com_off[r], b->com_len[r]); p += b->com_len[r]; }
+		} else { /* correct.c:604-608; the kept stretch as worker_ec's memmove leaves it (correct.c:557-567) */
+			if (!o->keep[r]) continue;
+			*p++ = is_fq ? '@' : '>';
+			memcpy(p, b->buf + b->name_off[r], b->name_len[r]); p += b->name_len[r];
+			if (b->com_off[r] != FQ_NONE) { *p++ = '\t'; memcpy(p, b->buf + b->com_off[r], b->com_len[r]); p += b->com_len[r]; }
+			seq += o->tstart[r];
+			if (qual) qual += o->tstart[r];
+			l = (uint32_t)(o->tend[r] - o->tstart[r]);
+		}
+		*p++ = '\n';
+		memcpy(p, seq, l); p += l; *p++ = '\n';
+		if (is_fq) { *p++ = '+'; *p++ = '\n'; memcpy(p, qual, l); p += l; *p++ = '\n'; }
+	}
+	w->piece[i] = out, w->piece_len[i] = (size_t)(p - out);
+}
+
+int fq_write(FILE *fp, const fq_block_t *b, const fq_flat_t *flat, const fq_out_t *o, int n_threads)
+{
+	wr_t w;
+	int i, rc = 0;
+	if (b->n == 0) return 0;
+	memset(&w, 0, sizeof(w));
+	w.b = b, w.flat = flat, w.o = o;
+	w.n_items = n_threads < 1 ? 1 : n_threads * 4;
+	if ((int64_t)w.n_items > b->n) w.n_items = (int)b->n;
+	w.piece = (char**)calloc((size_t)w.n_items, sizeof(char*));
+	w.piece_len = (size_t*)calloc((size_t)w.n_items, sizeof(size_t));
+	kt_for(n_threads, write_worker, &w, w.n_items);
+	for (i = 0; i < w.n_items; ++i) {
+		if (!w.oom && w.piece_len[i] && fwrite(w.piece[i], 1, w.piece_len[i], fp) != w.piece_len[i]) rc = -1;
+		free(w.piece[i]);
+	}
+	free(w.piece); free(w.piece_len);
+	return w.oom ? -1 : rc;
+}

@@ -1,0 +1,77 @@
+/* fqblock.h -- block-wise FASTA/FASTQ ingest and egress for the phase drivers.
+ *
+ * Replaces, on the way in, the record-at-a-time bseq_read() (reference bseq.c:52-76 over
+ * kseq.h:185-224: one getc state machine and four mallocs per read) and, on the way out,
+ * the printf-per-read writer (reference correct.c:591-616).  Input is read in blocks of
+ * text; a block that is plain four-line FASTQ -- every record "@name[ comment]", one
+ * sequence line, "+...", one quality line of the same length, "\n" line ends -- is split
+ * by all -t threads at once (newline index, then one record per work item).  Anything
+ * else (FASTA, multi-line records, "\r\n", blank lines, a truncated tail) switches the
+ * reader, from the start of that block on, to the tolerant sequential parser in bseq.c,
+ * so the records delivered are always exactly those bseq_read() would deliver, including
+ * kseq's two quirks (sticky comments; stop at the first record whose quality length
+ * differs).  Records never get their own allocations: a block owns one text buffer and
+ * arrays of offsets into it.
+ */
+#ifndef BFC_B200_FQBLOCK_H
+#define BFC_B200_FQBLOCK_H
+
+#include <stdint.h>
+#include <stdio.h>
+#include "bfc_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FQ_NONE UINT64_MAX
+
+typedef struct {
+	char *buf;                 /* the text the offsets point into (owned) */
+	size_t buf_len;
+	int64_t n;                 /* records */
+	uint64_t *name_off, *com_off, *seq_off, *qual_off; /* com_off / qual_off = FQ_NONE: no comment / no quality */
+	uint32_t *name_len, *com_len, *seq_len;
+	uint64_t n_bases;
+	int any_qual;
+} fq_block_t;
+
+struct fq_reader_s;
+typedef struct fq_reader_s fq_reader_t;
+
+fq_reader_t *fq_open(const char *fn, int n_threads);   /* plain or gzip'd, "-" = stdin; NULL on failure */
+void fq_close(fq_reader_t *r);
+/* next block of about target_bytes of input text; 0 at end of input (blk zeroed), 1 otherwise */
+int  fq_next(fq_reader_t *r, size_t target_bytes, int keep_comment, fq_block_t *blk);
+void fq_block_free(fq_block_t *blk);
+int  fq_reader_is_fast(const fq_reader_t *r);           /* still on the parallel path (tests) */
+
+/* the flat batch of bfc_b200.h over a block: pinned buffers that are reused from batch to batch */
+typedef struct {
+	bfcg_batch_t b;            /* b.qual is NULL for a batch without any quality string */
+	uint64_t *off;
+	uint8_t *seq_buf, *qual_buf;
+	size_t cap_bytes, cap_reads;
+	int pinned;
+} fq_flat_t;
+
+int  fq_flat_fill(fq_flat_t *f, const fq_block_t *blk, int n_threads);   /* 0 ok, -1 out of memory */
+void fq_flat_free(fq_flat_t *f);
+
+/* the writer of correct.c:591-611 over a block + the (corrected / trimmed) flat batch: formats on n_threads
+ * threads, then writes the pieces in order.  aux/aux2 as packed by worker_ec (correct.c:552-553); in filter mode
+ * keep/tstart/tend give the kept stretch (aux = !keep). */
+typedef struct {
+	int filter_mode, discard, no_qual;
+	const uint32_t *aux;        /* 2 per read (normal mode) */
+	const uint8_t *keep;        /* filter mode */
+	const int32_t *tstart, *tend;
+} fq_out_t;
+
+int fq_write(FILE *fp, const fq_block_t *blk, const fq_flat_t *flat, const fq_out_t *o, int n_threads);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

@@ -1,0 +1,134 @@
+"""CPU: the block reader / writer of the phase drivers (csrc/fqblock.c) against the tolerant record-at-a-time
+reader (csrc/bseq.c, which mirrors the reference's bseq.c over kseq.h): same records on plain four-line FASTQ (the
+parallel path) and on everything else (hand-over to the tolerant parser mid-stream), sticky comments included."""
+import ctypes as C
+import gzip
+import os
+import random
+
+import pytest
+
+import bfc_b200
+
+u64p, u32p = C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)
+
+
+class Bseq1(C.Structure):
+    _fields_ = [("l_seq", C.c_int), ("aux", C.c_uint32), ("aux2", C.c_uint32), ("name", C.c_char_p),
+                ("comment", C.c_char_p), ("seq", C.c_char_p), ("qual", C.c_char_p)]
+
+
+class Block(C.Structure):
+    _fields_ = [("buf", C.POINTER(C.c_char)), ("buf_len", C.c_size_t), ("n", C.c_int64),
+                ("name_off", u64p), ("com_off", u64p), ("seq_off", u64p), ("qual_off", u64p),
+                ("name_len", u32p), ("com_len", u32p), ("seq_len", u32p), ("n_bases", C.c_uint64), ("any_qual", C.c_int)]
+
+
+NONE = (1 << 64) - 1
+
+
+@pytest.fixture(scope="module")
+def L():
+    lib = C.CDLL(bfc_b200.lib_path())
+    lib.bseq_open.restype = C.c_void_p
+    lib.bseq_open.argtypes = [C.c_char_p]
+    lib.bseq_read.restype = C.POINTER(Bseq1)
+    lib.bseq_read.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    lib.bseq_close.argtypes = [C.c_void_p]
+    lib.fq_open.restype = C.c_void_p
+    lib.fq_open.argtypes = [C.c_char_p, C.c_int]
+    lib.fq_next.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(Block)]
+    lib.fq_block_free.argtypes = [C.POINTER(Block)]
+    lib.fq_close.argtypes = [C.c_void_p]
+    lib.fq_reader_is_fast.argtypes = [C.c_void_p]
+    return lib
+
+
+def read_slow(L, path, keep_comment):
+    f = L.bseq_open(path.encode())
+    out = []
+    while True:
+        n = C.c_int(0)
+        seqs = L.bseq_read(f, 1000, keep_comment, C.byref(n))
+        if not seqs or n.value == 0:
+            break
+        for i in range(n.value):
+            s = seqs[i]
+            out.append((s.name, s.comment, s.seq, s.qual))
+    L.bseq_close(f)
+    return out
+
+
+def read_fast(L, path, keep_comment, target, threads=3):
+    f = L.fq_open(path.encode(), threads)
+    out, fast_blocks = [], 0
+    while True:
+        b = Block()
+        if not L.fq_next(f, target, keep_comment, C.byref(b)):
+            break
+        fast_blocks += L.fq_reader_is_fast(f)
+        raw = C.string_at(b.buf, b.buf_len)
+        for i in range(b.n):
+            name = raw[b.name_off[i]:b.name_off[i] + b.name_len[i]]
+            com = None if b.com_off[i] == NONE else raw[b.com_off[i]:b.com_off[i] + b.com_len[i]]
+            seq = raw[b.seq_off[i]:b.seq_off[i] + b.seq_len[i]]
+            qual = None if b.qual_off[i] == NONE else raw[b.qual_off[i]:b.qual_off[i] + b.seq_len[i]]
+            out.append((name, com, seq, qual))
+        L.fq_block_free(C.byref(b))
+    L.fq_close(f)
+    return out, fast_blocks
+
+
+def rand_fastq(n, seed, comments=0.0, first_comment=True):
+    rng = random.Random(seed)
+    recs = []
+    for i in range(n):
+        l = rng.randint(1, 180)
+        seq = "".join(rng.choice("ACGTN") for _ in range(l))
+        qual = "".join(chr(rng.randint(33, 74)) for _ in range(l))
+        if qual[0] in "@+>" and rng.random() < 0.5:
+            qual = "@" + qual[1:]  # quality lines may start with '@'
+        com = ""
+        if rng.random() < comments and (i > 0 or first_comment):
+            com = rng.choice([" ", "\t"]) + rng.choice(["ec:Z:0_0:1_0_0:0_0", "1:N:0", "", " x  y "])
+        recs.append(f"@r{i}{com}\n{seq}\n+\n{qual}\n")
+    return "".join(recs).encode()
+
+
+CASES = {
+    "plain": rand_fastq(5000, 1),
+    "comments": rand_fastq(3000, 2, comments=0.3, first_comment=False),
+    "no_final_newline": rand_fastq(500, 3)[:-1],
+    "crlf": rand_fastq(300, 4).replace(b"\n", b"\r\n"),
+    "blank_line_midway": rand_fastq(2000, 5) + b"\n" + rand_fastq(2000, 6, comments=0.2),
+    "multiline_then_plain": b"@m1 c1\nACGT\nAC\n+\nIIII\nII\n" + rand_fastq(1500, 7, comments=0.1),
+    "fasta_mixed": rand_fastq(800, 8, comments=0.2) + b">f1 hello\nACGTNN\nACG\n>f2\nAC\n" + rand_fastq(10, 9),
+    "truncated_tail": rand_fastq(1000, 10) + b"@last\nACGT\n+\nII",
+    "bad_qual_length_stops": rand_fastq(700, 11) + b"@bad\nACGT\n+\nIIIII\n" + rand_fastq(50, 12),
+    "leading_garbage": b"garbage\n\n" + rand_fastq(100, 13),
+    "empty": b"",
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("keep_comment", [0, 1])
+@pytest.mark.parametrize("target", [4096, 50_000, 10_000_000])
+def test_block_reader_equals_record_reader(L, tmp_path, name, keep_comment, target):
+    p = str(tmp_path / "in.fq")
+    with open(p, "wb") as f:
+        f.write(CASES[name])
+    want = read_slow(L, p, keep_comment)
+    got, fast_blocks = read_fast(L, p, keep_comment, target)
+    assert got == want
+    if name in ("plain", "comments", "no_final_newline"):
+        assert fast_blocks > 0  # the parallel path did the work
+
+
+def test_block_reader_gzip_and_threads(L, tmp_path):
+    p = str(tmp_path / "in.fq.gz")
+    with gzip.open(p, "wb") as f:
+        f.write(CASES["comments"])
+    want = read_slow(L, p, 1)
+    for threads in (1, 2, 7):
+        got, fast_blocks = read_fast(L, p, 1, 30_000, threads)
+        assert got == want and fast_blocks > 0
