@@ -5,18 +5,19 @@
 // The read stream of a batch window is turned into BIT PLANES (one bit per stream
 // position) and a 16-bit flag word per base; the search then works on those:
 //
-//   K0  k_enum       (enum.cuh) canonical k-mer hash of every stream position
-//   K5  k_ec_lookup  bfc_ec_kcov's one-lookup-per-k-mer (correct.c:106) for the whole
-//                    window at once (36 independent probes per thread) -> planes
-//                    B0 B1 NB Q (base bits, non-ACGT, Q >= q) and SOL HS A H (what
-//                    the search ever asks about a read k-mer's table value)
+//   K5  k_ec_lookup  bfc_ec_kcov's one-lookup-per-k-mer (correct.c:106) for the whole window at
+//                    once: the window is staged as bit planes in shared memory, the k-mer ending
+//                    at a position is cut out of them, hashed and looked up -> planes B0 B1 NB Q
+//                    (base bits, non-ACGT, Q >= q) and SOL HS A H (what the search ever asks
+//                    about a read k-mer's table value)
 //   K5b k_ec_cov     lcov / hcov thresholds (correct.c:109-112) as sliding popcounts
 //                    over SOL / HS -> the per-base flag word, and the two "jump" planes
 //                    (positions a lone search state steps over without any decision)
 //   K6a k_ec_setup   one read per thread: >5 % N, longest solid island (correct.c:119-130)
 //                    by run scanning, the rare single-edit rescue (correct.c:63-94, 405-421)
+//   K6a' k_ec_ext    the lookups past the end of every read (they depend on its last k-1 bases only)
 //   K6b k_ec_search  the heap search, one (read, direction) JOB per thread at a time,
-//                    persistent threads.  The thread is a resumable state machine whose
+//                    persistent threads, jobs handed out dynamically.  The thread is a resumable state machine whose
 //                    only table lookup sits at ONE place in the loop, so the lanes of
 //                    a warp hash and probe together whatever step each of them is in.
 //   K6c k_ec_merge   one read per warp: merge the two directions, rewrite seq / qual
@@ -183,31 +184,66 @@ __global__ void __launch_bounds__(EL_THREADS) k_ec_lookup(LookupParams p)
 // the next read: no k-mer ends on a terminator or on the first k-1 bases of a read.
 __global__ void __launch_bounds__(256) k_ec_cov(EcParams P, uint64_t n_pos, uint16_t *fl, uint64_t *pl_out)
 {
-	const uint64_t pos = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; // n_pos is a multiple of 32
+	// one thread per plane word = 32 stream positions p0 .. p0 + 31 (n_pos is a multiple of 32): everything is
+	// word arithmetic on the planes; the only per-position work is the two sliding popcounts
+	const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (w * 32 >= n_pos) return;
 	const int k = P.k;
+	const uint32_t *pl32 = (const uint32_t*)P.pl;
+	const uint64_t s32 = P.pl_words * 2, g = w + PL_PAD / 32;
+#define PLW(which, d) __ldg(pl32 + (uint64_t)(which) * s32 + g + (d))
+	const uint32_t b0 = PLW(PL_B0, 0), b1 = PLW(PL_B1, 0), nb = PLW(PL_NB, 0), q = PLW(PL_Q, 0);
+	const uint32_t s0 = PLW(PL_SOL, 0), s1 = PLW(PL_SOL, 1), s2 = PLW(PL_SOL, 2);
+	const uint32_t t0 = PLW(PL_HS, 0), t1 = PLW(PL_HS, 1), t2 = PLW(PL_HS, 2);
+	const uint32_t a0 = PLW(PL_A, 0), a1 = PLW(PL_A, 1), a2 = PLW(PL_A, 2);
+	const uint32_t h0 = PLW(PL_H, 0), h1 = PLW(PL_H, 1), h2 = PLW(PL_H, 2);
+#undef PLW
 	const uint64_t kmask = (1ULL << k) - 1;
-	uint32_t f = 4;
-	bool j0 = false, j1 = false;
-	if (pos < n_pos) {
-		const int64_t p = (int64_t)pos;
-		const int b = bit1(plane(P, PL_B0), p) | bit1(plane(P, PL_B1), p) << 1, nb = bit1(plane(P, PL_NB), p);
-		const int q = bit1(plane(P, PL_Q), p);
-		const int lc = __popcll(bits64(plane(P, PL_SOL), p) & kmask) >= P.min_cov + 1;
-		const int hc = 4 * __popcll(bits64(plane(P, PL_HS), p) & kmask) > 3 * k; // hcov > k * .75
-		const int sol = bit1(plane(P, PL_SOL), p), a = bit1(plane(P, PL_A), p), h = bit1(plane(P, PL_H), p);
-		f = (uint32_t)(nb ? 4 : b) | (q ? FL_Q : 0) | (lc ? FL_LC : 0) | (hc ? FL_HC : 0) | (sol ? FL_SOL : 0) | (a ? FL_A : 0) | (h ? FL_H : 0);
-		// a lone state whose last k-1 bases are the read's steps over this base without a decision when the
-		// base is "fixed" (correct.c:299-301) and its own k-mer costs nothing (correct.c:334-336)
-		j0 = !nb && ((q && a && lc) || hc) && sol && h;
-		// reverse direction: the k-mer ending (in search order) on this base ends k-1 positions further in the stream
-		const int sol1 = bit1(plane(P, PL_SOL), p + k - 1), a1 = bit1(plane(P, PL_A), p + k - 1), h1 = bit1(plane(P, PL_H), p + k - 1);
-		j1 = !nb && ((q && a1 && lc) || hc) && sol1 && h1;
-		fl[pos] = (uint16_t)f;
+	const uint64_t slo = s0 | (uint64_t)s1 << 32, tlo = t0 | (uint64_t)t1 << 32;
+	// lcov[p] / hcov[p] = solid (solid && high_end) k-mers ENDING in [p, p + k - 1] (correct.c:109-112)
+	int cs = __popcll(slo & kmask), ct = __popcll(tlo & kmask);
+	uint32_t lc = 0, hc = 0;
+#pragma unroll
+	for (int i = 0; i < 32; ++i) {
+		lc |= (uint32_t)(cs >= P.min_cov + 1) << i;
+		hc |= (uint32_t)(4 * ct > 3 * k) << i; // hcov > k * .75
+		const int j = i + k; // the bit entering the window; bit i leaves it
+		cs += (int)(j < 64 ? slo >> j & 1 : (uint64_t)(s2 >> (j - 64) & 1)) - (int)(slo >> i & 1);
+		ct += (int)(j < 64 ? tlo >> j & 1 : (uint64_t)(t2 >> (j - 64) & 1)) - (int)(tlo >> i & 1);
 	}
-	const uint32_t m0 = __ballot_sync(0xffffffffu, j0), m1 = __ballot_sync(0xffffffffu, j1);
-	if ((threadIdx.x & 31) == 0 && pos < n_pos) {
-		uint32_t *w = (uint32_t*)pl_out + (pos + PL_PAD) / 32;
-		w[(uint64_t)PL_J0 * P.pl_words * 2] = m0, w[(uint64_t)PL_J1 * P.pl_words * 2] = m1;
+	// a lone state whose last k-1 bases are the read's steps over a base without a decision when the base is
+	// "fixed" (correct.c:299-301) and its own k-mer costs nothing (correct.c:334-336)
+	const uint32_t fixed = ~nb & ((q & lc) | hc);
+	const uint32_t j0 = ~nb & ((q & a0 & lc) | hc) & s0 & h0;
+	// reverse direction: the k-mer ending (in search order) on a base ends k-1 positions further in the stream
+	const int sh = k - 1;
+	const uint64_t alo = a0 | (uint64_t)a1 << 32, hlo = h0 | (uint64_t)h1 << 32;
+	const uint32_t sr = sh ? (uint32_t)((slo >> sh) | ((uint64_t)s2 << (64 - sh))) : s0;
+	const uint32_t ar = sh ? (uint32_t)((alo >> sh) | ((uint64_t)a2 << (64 - sh))) : a0;
+	const uint32_t hr = sh ? (uint32_t)((hlo >> sh) | ((uint64_t)h2 << (64 - sh))) : h0;
+	const uint32_t j1 = ~nb & ((q & ar & lc) | hc) & sr & hr;
+	(void)fixed;
+	uint32_t *jw = (uint32_t*)pl_out + g;
+	jw[(uint64_t)PL_J0 * s32] = j0, jw[(uint64_t)PL_J1 * s32] = j1;
+	// the flag word of every base
+	uint4 *out = (uint4*)(fl + w * 32);
+#pragma unroll
+	for (int v = 0; v < 4; ++v) {
+		uint32_t o[4];
+#pragma unroll
+		for (int u = 0; u < 4; ++u) {
+			uint32_t pair = 0;
+#pragma unroll
+			for (int e = 0; e < 2; ++e) {
+				const int i = v * 8 + u * 2 + e;
+				const uint32_t n = nb >> i & 1;
+				const uint32_t f = (n ? 4u : (b0 >> i & 1) | (b1 >> i & 1) << 1) | (q >> i & 1 ? (uint32_t)FL_Q : 0u) | (lc >> i & 1 ? (uint32_t)FL_LC : 0u) |
+				                   (hc >> i & 1 ? (uint32_t)FL_HC : 0u) | (s0 >> i & 1 ? (uint32_t)FL_SOL : 0u) | (a0 >> i & 1 ? (uint32_t)FL_A : 0u) | (h0 >> i & 1 ? (uint32_t)FL_H : 0u);
+				pair |= f << (16 * e);
+			}
+			o[u] = pair;
+		}
+		out[v] = make_uint4(o[0], o[1], o[2], o[3]);
 	}
 }
 
@@ -1022,7 +1058,7 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 		BFCG_LAUNCH_CHECK();
 		{
 			KTime kt(KT_EC_SETUP);
-			k_ec_cov<<<(unsigned)(n_rec / 256), 256, 0, rt.stream>>>(P, n_rec, (uint16_t*)(a + o_fl), (uint64_t*)(a + o_pl));
+			k_ec_cov<<<(unsigned)((n_rec / 32 + 255) / 256), 256, 0, rt.stream>>>(P, n_rec, (uint16_t*)(a + o_fl), (uint64_t*)(a + o_pl));
 			k_ec_setup<<<(unsigned)((nr + 127) / 128), 128, 0, rt.stream>>>(P);
 		}
 		BFCG_LAUNCH_CHECK();

@@ -128,10 +128,15 @@ __global__ void __launch_bounds__(EL_THREADS) k_enum_lin(EnumLinParams p)
 __global__ void __launch_bounds__(256) k_part_bounds(const unsigned long long *y0, uint64_t n, uint64_t base, int shift, uint32_t pmask, uint32_t *start, uint32_t *end)
 {
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; // y0 points at record `base` of the array the bounds refer to
-	if (i >= n) return;
-	const uint32_t p = (uint32_t)(__ldg(y0 + i) >> shift) & pmask;
-	if (i == 0 || ((uint32_t)(__ldg(y0 + i - 1) >> shift) & pmask) != p) start[p] = (uint32_t)(base + i);
-	if (i + 1 == n || ((uint32_t)(__ldg(y0 + i + 1) >> shift) & pmask) != p) end[p] = (uint32_t)(base + i + 1);
+	const unsigned lane = threadIdx.x & 31;
+	const bool in = i < n;
+	const uint32_t p = in ? (uint32_t)(__ldg(y0 + i) >> shift) & pmask : 0;
+	uint32_t prev = __shfl_up_sync(0xffffffffu, p, 1), next = __shfl_down_sync(0xffffffffu, p, 1);
+	if (!in) return;
+	if (lane == 0 && i > 0) prev = (uint32_t)(__ldg(y0 + i - 1) >> shift) & pmask;
+	if (lane == 31 && i + 1 < n) next = (uint32_t)(__ldg(y0 + i + 1) >> shift) & pmask;
+	if (i == 0 || prev != p) start[p] = (uint32_t)(base + i);
+	if (i + 1 == n || next != p) end[p] = (uint32_t)(base + i + 1);
 }
 
 // ------------------------------------------------------------------ K3': one CTA per partition
