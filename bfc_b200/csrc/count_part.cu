@@ -29,6 +29,7 @@
 #include "common.cuh"
 #include "enum.cuh"
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <algorithm>
 #include <functional>
 
@@ -92,7 +93,19 @@ struct EnumLinParams {
 	int k, q;
 	unsigned long long *key;
 	void *val;
+	uint32_t *seg_cnt;           // k_enum_count: records per segment
+	const uint32_t *seg_off;     // k_enum_lin: first record of every segment (exclusive scan of seg_cnt)
 };
+
+// how many k-mers end in every segment (the records are written back to back, in stream order)
+__global__ void __launch_bounds__(EL_THREADS) k_enum_count(EnumLinParams p)
+{
+	__shared__ uint32_t s_nb[EL_WORDS], s_warp[EL_THREADS / 32 + 1];
+	el_stage_nb(s_nb, p.seq, p.len, (int64_t)p.emit_from + (int64_t)blockIdx.x * EL_SEG);
+	uint32_t total;
+	el_block_scan((uint32_t)__popc(el_valid_word(s_nb, threadIdx.x, p.k)), s_warp, &total);
+	if (threadIdx.x == 0) p.seg_cnt[blockIdx.x] = total;
+}
 
 // What worker_count does per base (count.c:76-88): map the character (bseq.c:9-26), restart on
 // a non-ACGT one, and once k bases are in, hash the canonical k-mer (kmer.h:79-88) with
@@ -102,24 +115,36 @@ template <typename VT, bool PACKED>
 __global__ void __launch_bounds__(EL_THREADS) k_enum_lin(EnumLinParams p)
 {
 	__shared__ uint32_t s_pl[4][EL_WORDS]; // B0, B1 (base code bits), NB (not ACGT / outside), Q (Q >= q)
+	__shared__ uint32_t s_v[EL_THREADS], s_vpre[EL_THREADS], s_warp[EL_THREADS / 32 + 1];
 	const int64_t seg0 = (int64_t)p.emit_from + (int64_t)blockIdx.x * EL_SEG;
 	el_stage_planes(s_pl, p.seq, p.qual, p.len, seg0, p.q);
 	const int k = p.k;
 	const uint64_t kmask = (1ULL << k) - 1;
-	unsigned long long *ok = p.key + (uint64_t)blockIdx.x * EL_SEG + threadIdx.x;
-	VT *ov = (VT*)p.val + (uint64_t)blockIdx.x * EL_SEG + threadIdx.x;
+	{ // where k-mers end, and how many end before every plane word: the records leave compacted
+		const uint32_t v = el_valid_word(s_pl[2], threadIdx.x, k);
+		uint32_t total;
+		s_v[threadIdx.x] = v;
+		s_vpre[threadIdx.x] = el_block_scan((uint32_t)__popc(v), s_warp, &total);
+		__syncthreads();
+	}
+	const unsigned lane = threadIdx.x & 31;
+	unsigned long long *const ok = p.key + __ldg(p.seg_off + blockIdx.x);
+	VT *const ov = (VT*)p.val + __ldg(p.seg_off + blockIdx.x);
 #pragma unroll 4
 	for (int j = 0; j < EL_ITERS; ++j) {
 		const uint32_t pp = (uint32_t)(j * EL_THREADS + threadIdx.x);   // position inside the segment
-		const uint32_t bit = pp + EL_LEAD - (uint32_t)(k - 1);          // oldest base of the k-mer ending at pp
-		// a position where no k-mer ends still gets a record (marked); its key is spread so that the
-		// partitions stay balanced
-		unsigned long long key = ((uint64_t)(seg0 + pp) * 0x9E3779B97F4A7C15ULL) >> 1;
-		VT val = Rec<VT, PACKED>::mark();
-		uint64_t y[2];
-		if (el_kmer_at(s_pl, bit, k, kmask, y)) Rec<VT, PACKED>::pack(k, y[0], y[1], (win64(s_pl[3], bit) & kmask) == kmask, key, val);
-		ok[j * EL_THREADS] = key;
-		ov[j * EL_THREADS] = val;
+		const uint32_t v = s_v[pp >> 5];
+		if (v >> lane & 1) {
+			const uint32_t bit = pp + EL_LEAD - (uint32_t)(k - 1);      // oldest base of the k-mer ending at pp
+			const uint32_t at = s_vpre[pp >> 5] + __popc(v & ((1u << lane) - 1));
+			unsigned long long key;
+			VT val;
+			uint64_t y[2];
+			el_kmer_hash_at(s_pl, bit, k, kmask, y);
+			Rec<VT, PACKED>::pack(k, y[0], y[1], (win64(s_pl[3], bit) & kmask) == kmask, key, val);
+			ok[at] = key;
+			ov[at] = val;
+		}
 	}
 }
 
@@ -490,11 +515,35 @@ static uint64_t window_positions(uint64_t n_positions, bool host, const PartGeom
 	return std::min(P, el_padded(n_positions));
 }
 
-static void launch_enum_lin(int vb, const EnumLinParams &ep, uint64_t n_rec)
+#define ENUM_SCAN_TMP (1 << 20)
+
+// bytes of scratch enumerate_window needs for n_pos (padded) positions: per-segment counts + offsets + scan scratch
+static size_t enum_scratch_bytes(uint64_t n_pos) { return 2 * align_up((n_pos / EL_SEG + 1) * 4, 256) + ENUM_SCAN_TMP; }
+
+// K0': the records of the n_pos (padded) positions described by ep, compacted, into ep.key / ep.val; *n_valid = how many
+static int enumerate_window(int vb, EnumLinParams ep, uint64_t n_pos, uint8_t *scratch, uint64_t *n_valid)
 {
 	BfcgRuntime &rt = bfcg_rt();
+	const uint64_t n_seg = n_pos / EL_SEG;
+	uint32_t *seg_cnt = (uint32_t*)scratch, *seg_off = (uint32_t*)(scratch + align_up((n_seg + 1) * 4, 256));
+	void *scan_tmp = scratch + 2 * align_up((n_seg + 1) * 4, 256);
+	size_t scan_bytes = 0;
+	uint32_t last[2];
+	ep.seg_cnt = seg_cnt, ep.seg_off = seg_off;
 	KTime kt(KT_ENUM_LIN);
-	REC_DISPATCH(vb, (k_enum_lin<VT, PK><<<(unsigned)(n_rec / EL_SEG), EL_THREADS, 0, rt.stream>>>(ep)));
+	k_enum_count<<<(unsigned)n_seg, EL_THREADS, 0, rt.stream>>>(ep);
+	BFCG_LAUNCH_CHECK();
+	BFCG_CUDA(cub::DeviceScan::ExclusiveSum((void*)0, scan_bytes, seg_cnt, seg_off, (int)n_seg, rt.stream));
+	if (scan_bytes > ENUM_SCAN_TMP) return bfcg_fail(__func__, "scan scratch too small", cudaSuccess);
+	BFCG_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, seg_cnt, seg_off, (int)n_seg, rt.stream));
+	++rt.n_launches;
+	REC_DISPATCH(vb, (k_enum_lin<VT, PK><<<(unsigned)n_seg, EL_THREADS, 0, rt.stream>>>(ep)));
+	BFCG_LAUNCH_CHECK();
+	BFCG_CUDA(cudaMemcpyAsync(&last[0], seg_cnt + n_seg - 1, 4, cudaMemcpyDeviceToHost, rt.stream));
+	BFCG_CUDA(cudaMemcpyAsync(&last[1], seg_off + n_seg - 1, 4, cudaMemcpyDeviceToHost, rt.stream));
+	BFCG_CUDA(cudaStreamSynchronize(rt.stream));
+	*n_valid = (uint64_t)last[0] + last[1];
+	return BFCG_OK;
 }
 
 int bfcg_count_part_batch(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, bfc_ch_t *ch, const bfcg_batch_t *batch, bfcg_stats_t *stats)
@@ -514,8 +563,10 @@ int bfcg_count_part_batch(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high,
 	if (host)
 		for (int b = 0; b < 2; ++b)
 			for (int j = 0; j < 2; ++j) { o_stage[b][j] = tot; tot += W; }
+	size_t o_enum;
 	o_key = tot; tot += align_up(P * 8, 256);
 	o_val = tot; tot += align_up(P * value_bytes(vb), 256);
+	o_enum = tot; tot += enum_scratch_bytes(P);
 	o_sc = tot; tot += PartScratch::bytes(P, g, vb);
 	uint8_t *a = (uint8_t*)bfcg_arena(tot);
 	if (!a) return BFCG_ERR_NOMEM;
@@ -552,10 +603,8 @@ int bfcg_count_part_batch(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high,
 			if (ce != cudaSuccess) { r = bfcg_fail(__func__, "staging copy", ce); break; }
 			ep.seq = a + o_stage[b][0], ep.qual = batch->qual ? a + o_stage[b][1] : 0;
 		} else ep.seq = batch->seq + w0, ep.qual = batch->qual ? batch->qual + w0 : 0;
-		const uint64_t n_rec = el_padded(e - s);
-		launch_enum_lin(vb, ep, n_rec);
-		++rt.n_launches;
-		{ const cudaError_t le = cudaGetLastError(); if (le != cudaSuccess) { r = bfcg_fail(__func__, "kernel launch", le); break; } }
+		uint64_t n_rec = 0;
+		if ((r = enumerate_window(vb, ep, el_padded(e - s), a + o_enum, &n_rec)) != BFCG_OK) break;
 		if (host) cudaEventRecord(rt.ev_free[b], rt.stream);
 		// the next window travels while this one is counted (issued after this window's launches: a copy from
 		// pageable memory blocks the host, and should not hold the kernels back)
@@ -564,7 +613,8 @@ int bfcg_count_part_batch(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high,
 			const cudaError_t ce = issue_copy(wi + 1);
 			return ce == cudaSuccess ? BFCG_OK : bfcg_fail("bfcg_count_part_batch", "staging copy", ce);
 		};
-		r = count_part_window(opt, bf, bf_high, ch, g, ~0ULL, vb, rec_key, rec_val, n_rec, sc, stats, &next_copy);
+		if (n_rec) r = count_part_window(opt, bf, bf_high, ch, g, ~0ULL, vb, rec_key, rec_val, n_rec, sc, stats, &next_copy);
+		else r = next_copy();
 	}
 	if (host) cudaStreamSynchronize(rt.copy_in);
 	if (r != BFCG_OK) { cudaStreamSynchronize(rt.stream); return r; }
@@ -618,6 +668,7 @@ int bfcg_enum_part_records(const bfc_opt_t *opt, const bfcg_batch_t *batch, int 
 	o_y0 = tot; tot = align_up(tot + n_rec * 8, 256);
 	o_y1 = tot; tot = align_up(tot + n_rec * 8, 256);
 	o_tmp = tot; tot = align_up(tot + temp, 256);
+	size_t o_enum = tot; tot += enum_scratch_bytes(n_rec);
 	o_bnd = tot; tot += 256;
 	uint8_t *a = (uint8_t*)bfcg_arena(tot);
 	if (!a) return BFCG_ERR_NOMEM;
@@ -630,30 +681,30 @@ int bfcg_enum_part_records(const bfc_opt_t *opt, const bfcg_batch_t *batch, int 
 		if (batch->qual) BFCG_CUDA(cudaMemcpyAsync(a + o_qual, batch->qual, nb, cudaMemcpyHostToDevice, rt.stream));
 		ep.seq = a + o_seq, ep.qual = batch->qual ? a + o_qual : 0;
 	} else ep.seq = batch->seq, ep.qual = batch->qual;
-	launch_enum_lin(0, ep, n_rec);
-	BFCG_LAUNCH_CHECK();
-	// the caller's arrays hold batch->n_bytes records: the padding (no k-mer ends there) stays behind
+	uint64_t nv = 0; // records = positions where a k-mer ends (<= batch->n_bytes, what the caller's arrays hold)
+	{ int er = enumerate_window(0, ep, n_rec, a + o_enum, &nv); if (er != BFCG_OK) return er; }
+	if (nv == 0) return BFCG_OK;
 	if (sort_bits > 0) {
 		cudaError_t se;
 		{
 			KTime kt(KT_COUNT_SORT);
-			se = sort_records(a + o_tmp, temp, 0, ep.key, (unsigned long long*)d_y0, ep.val, d_y1, nb, g.pshift, g.pshift + sort_bits);
+			se = sort_records(a + o_tmp, temp, 0, ep.key, (unsigned long long*)d_y0, ep.val, d_y1, nv, g.pshift, g.pshift + sort_bits);
 		}
 		BFCG_CUDA(se);
 		rt.n_launches += 1 + (sort_bits + 7) / 8;
 	} else {
-		BFCG_CUDA(cudaMemcpyAsync(d_y0, ep.key, nb * 8, cudaMemcpyDeviceToDevice, rt.stream));
-		BFCG_CUDA(cudaMemcpyAsync(d_y1, ep.val, nb * 8, cudaMemcpyDeviceToDevice, rt.stream));
+		BFCG_CUDA(cudaMemcpyAsync(d_y0, ep.key, nv * 8, cudaMemcpyDeviceToDevice, rt.stream));
+		BFCG_CUDA(cudaMemcpyAsync(d_y1, ep.val, nv * 8, cudaMemcpyDeviceToDevice, rt.stream));
 	}
 	uint32_t h_bnd[2 * 8];
 	memset(h_bnd, 0, sizeof(h_bnd));
 	if (owner_bits > 0) { // bucket sizes = runs of the owner bits in the sorted keys
 		uint32_t *bnd = (uint32_t*)(a + o_bnd);
 		BFCG_CUDA(cudaMemsetAsync(bnd, 0, 64, rt.stream));
-		{ KTime kt(KT_BUCKET); k_part_bounds<<<(unsigned)((nb + 255) / 256), 256, 0, rt.stream>>>((const unsigned long long*)d_y0, nb, 0, g.pshift + g.pbits, n_owners - 1, bnd, bnd + 8); }
+		{ KTime kt(KT_BUCKET); k_part_bounds<<<(unsigned)((nv + 255) / 256), 256, 0, rt.stream>>>((const unsigned long long*)d_y0, nv, 0, g.pshift + g.pbits, n_owners - 1, bnd, bnd + 8); }
 		BFCG_LAUNCH_CHECK();
 		BFCG_CUDA(cudaMemcpyAsync(h_bnd, bnd, 64, cudaMemcpyDeviceToHost, rt.stream));
-	} else h_bnd[8] = (uint32_t)nb;
+	} else h_bnd[8] = (uint32_t)nv;
 	BFCG_CUDA(cudaStreamSynchronize(rt.stream));
 	for (int o = 0; o < n_owners; ++o) counts[o] = h_bnd[8 + o] - h_bnd[o];
 	return BFCG_OK;

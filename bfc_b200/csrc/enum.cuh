@@ -85,15 +85,70 @@ __device__ __forceinline__ void el_stage_planes(uint32_t (*s_pl)[EL_WORDS], cons
 	__syncthreads();
 }
 
+// The same for the NB plane alone (what deciding WHERE k-mers end needs)
+__device__ __forceinline__ void el_stage_nb(uint32_t *s_nb, const uint8_t *seq, uint64_t len, int64_t seg0)
+{
+	const unsigned lane = threadIdx.x & 31;
+	if (threadIdx.x < 2) s_nb[EL_WORDS - 1 - threadIdx.x] = 0;
+	for (int i = threadIdx.x; i < EL_SEG + EL_LEAD; i += EL_THREADS) {
+		const int64_t pos = seg0 - EL_LEAD + i;
+		const bool not_acgt = !(pos >= 0 && (uint64_t)pos < len && base_code(__ldg(seq + pos)) < 4);
+		const uint32_t nb = __ballot_sync(0xffffffffu, not_acgt);
+		if (lane == 0) s_nb[i >> 5] = nb;
+	}
+	__syncthreads();
+}
+
+// Word w (0 .. EL_SEG/32 - 1) of the segment's "a k-mer ends here" plane: position p qualifies when none of the k
+// bases p-k+1 .. p is non-ACGT, i.e. when the NB plane dilated by k-1 positions is 0 at p.  The dilation doubles:
+// OR of shifts 0 .. k-1 of the 96 NB bits ending with this word.
+__device__ __forceinline__ uint32_t el_valid_word(const uint32_t *s_nb, int w, int k)
+{
+	uint64_t lo = s_nb[w] | (uint64_t)s_nb[w + 1] << 32, hi = s_nb[w + 2]; // plane words w .. w+2 = positions 32w-64 .. 32w+31
+	for (int covered = 1; covered < k;) {
+		const int step = covered < k - covered ? covered : k - covered;
+		hi |= (hi << step) | (lo >> (64 - step));
+		lo |= lo << step;
+		covered += step;
+	}
+	return ~(uint32_t)hi;
+}
+
+// exclusive prefix sum over the EL_THREADS values of a CTA (one per thread); *total = their sum.  Two barriers.
+__device__ __forceinline__ uint32_t el_block_scan(uint32_t v, uint32_t *s_warp /* EL_THREADS / 32 + 1 */, uint32_t *total)
+{
+	const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t inc = v;
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
+		if (lane >= (unsigned)d) inc += u;
+	}
+	if (lane == 31) s_warp[warp] = inc;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		uint32_t run = 0;
+		for (int i = 0; i < EL_THREADS / 32; ++i) { const uint32_t t = s_warp[i]; s_warp[i] = run; run += t; }
+		s_warp[EL_THREADS / 32] = run;
+	}
+	__syncthreads();
+	*total = s_warp[EL_THREADS / 32];
+	return s_warp[warp] + inc - v;
+}
+
 // The canonical k-mer hash (kmer.h:79-88) of the k bases whose oldest one is plane bit `bit`; false when one of them
 // is not ACGT.  The 4-plane k-mer (kmer.h:10-17) is cut out of the base planes: forward planes = the window
 // bit-reversed (newest base at bit 0), reverse-complement planes = the window complemented (newest base at bit k-1).
-__device__ __forceinline__ bool el_kmer_at(const uint32_t (*s_pl)[EL_WORDS], uint32_t bit, int k, uint64_t kmask, uint64_t y[2])
+__device__ __forceinline__ void el_kmer_hash_at(const uint32_t (*s_pl)[EL_WORDS], uint32_t bit, int k, uint64_t kmask, uint64_t y[2])
 {
-	if ((win64(s_pl[2], bit) & kmask) != 0) return false;
 	const uint64_t w0 = win64(s_pl[0], bit) & kmask, w1 = win64(s_pl[1], bit) & kmask;
 	const uint64_t x[4] = { __brevll(w0) >> (64 - k), __brevll(w1) >> (64 - k), ~w0 & kmask, ~w1 & kmask };
 	bfc_kmer_hash(k, x, y);
+}
+
+__device__ __forceinline__ bool el_kmer_at(const uint32_t (*s_pl)[EL_WORDS], uint32_t bit, int k, uint64_t kmask, uint64_t y[2])
+{
+	if ((win64(s_pl[2], bit) & kmask) != 0) return false;
+	el_kmer_hash_at(s_pl, bit, k, kmask, y);
 	return true;
 }
 
