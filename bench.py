@@ -458,6 +458,16 @@ def main():
                "d2h_bytes_per_step": int(2 * n * RB + 8 * n),
                "steps": e2e_steps, "split": {k_: v / e2e_steps for k_, v in split.items()} if world == 1 else None, "note": "whole job, all ranks: pinned host buffers -> bfcg_count_batch (N>1: bfcg_enum_records + "
                "all-to-all + bfcg_count_records) / bfcg_correct_batch -> host buffers; wall clock, max over ranks"}
+        # full-size consistency check (outside every timed region): the reads corrected through host batches (many
+        # windows, copies overlapped with the kernels) equal, byte for byte, those corrected while resident in HBM
+        same = True
+        if nb_mine:
+            L.bfcg_d2h(h_seq.ctypes.data, w_seq, nb_mine)
+            L.bfcg_d2h(h_qual.ctypes.data, w_qual, nb_mine)
+            d_aux_h = np.empty(2 * n_mine, dtype=np.uint32)
+            L.bfcg_d2h(d_aux_h.ctypes.data, d_aux, 8 * n_mine)
+            same = bool(np.array_equal(h_seq, ws) and np.array_equal(h_qual, wq) and np.array_equal(d_aux_h, p_aux[:2 * n_mine]))
+        e2e["equals_resident_result"] = bool(max_over_ranks(0.0 if same else 1.0) == 0.0)
         for p_ in (p_hs, p_hq, p_ws, p_wq):
             L.bfcg_host_free_pinned(p_)
 
