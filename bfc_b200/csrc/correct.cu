@@ -92,6 +92,7 @@ struct EcParams {
 	TabView tab;
 	int k, q, min_cov, win_multi_ec, max_end_ext;
 	int w_ec, w_ec_high, w_absent, w_absent_high, max_path_diff, max_heap, mode;
+	int refine;                  // -R: aux holds the earlier stats on entry (correct.c:438-442, 470)
 	EcState *pool;               // heap_cap states per thread slot
 	uint32_t *heapk;             // heap_cap keys per thread slot: tot_pen << 12 | pool slot
 	uint2 *edits;                // edit_cap entries per thread slot: (parent, pos << 3 | base), forward coordinates
@@ -131,6 +132,7 @@ struct LookupParams {
 	uint64_t *pl;
 	uint64_t pl_words;
 	int k, q, min_cov;
+	int refine;                  // -R: corrected bases are taken back from the quality string (correct.c:31)
 	unsigned long long *ctr;
 };
 
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(EL_THREADS) k_ec_lookup(LookupParams p)
 {
 	__shared__ uint32_t s_pl[4][EL_WORDS];
 	const int64_t seg0 = (int64_t)blockIdx.x * EL_SEG;
-	el_stage_planes(s_pl, p.seq, p.qual, p.n_pos, seg0, p.q);
+	el_stage_planes(s_pl, p.seq, p.qual, p.n_pos, seg0, p.q, p.refine != 0);
 	uint32_t *pl32 = (uint32_t*)p.pl;
 	const uint64_t stride32 = p.pl_words * 2, w0 = (uint64_t)(seg0 + PL_PAD) / 32;
 	// the base planes of the segment: shared-memory word 2 + t = positions seg0 + 32 t ..
@@ -833,7 +835,17 @@ __global__ void __launch_bounds__(256) k_ec_merge(EcParams P)
 			const int bad = r0.x < 0 ? r0.x : r1.x < 0 ? r1.x : 0; // the reference stops at the first failing direction
 			if (bad < 0) ec_code = bad == -2 ? 4 : bad == -3 ? 5 : 1;
 		}
-		uint32_t n_ec = 0, n_ec_high = 0;
+		uint32_t n_ec = 0, n_ec_high = 0, rf_code = P.refine ? 1u : 0u;
+		if (P.refine && ec_code == 0) { // correct.c:438-442: more absent k-mers than the earlier round left => keep that one
+			const uint32_t oa = P.aux[2 * r], oa2 = P.aux[2 * r + 1];
+			if ((oa & 7) == 0 && (uint32_t)(r0.x + r1.x) > oa2 >> 10) {
+				__syncwarp();
+				if (lane == 0) P.aux[2 * r + 1] = (oa2 & ~(3u << 8)) | 2u << 8; // aux[2r] stays: the earlier stats, rf_code 2
+				continue;
+			}
+			rf_code = 3; // correct.c:470
+		}
+		__syncwarp(); // (every lane has read the earlier stats before lane 0 overwrites them)
 		if (ec_code == 0) {
 			uint8_t *seq = P.seq + ob0;
 			uint8_t *qual = P.qual && n > 0 && P.qual[ob0] != 0xFF ? P.qual + ob0 : 0;
@@ -865,7 +877,7 @@ __global__ void __launch_bounds__(256) k_ec_merge(EcParams P)
 		}
 		if (lane == 0) { // correct.c:552-553
 			P.aux[2 * r] = (n_ec & 0x3fff) << 18 | (n_ec_high & 0x3fff) << 4 | brute << 3 | ec_code;
-			P.aux[2 * r + 1] = (n_absent & 0x3fffff) << 10 | 0u << 8 | (mh & 0xff);
+			P.aux[2 * r + 1] = (n_absent & 0x3fffff) << 10 | rf_code << 8 | (mh & 0xff);
 		}
 	}
 }
@@ -911,8 +923,8 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 	int r;
 	if ((r = bfcg_rt_init()) != BFCG_OK) return r;
 	BfcgRuntime &rt = bfcg_rt();
-	if (!opt || !ch || !batch || !aux || !batch->off || bfc_ch_get_k(ch) != opt->k || opt->refine_ec || opt->max_heap < 1 || opt->max_heap > 4000)
-		return bfcg_fail(__func__, "invalid arguments (refine mode -R is not supported)", cudaSuccess), BFCG_ERR_ARG;
+	if (!opt || !ch || !batch || !aux || !batch->off || bfc_ch_get_k(ch) != opt->k || opt->max_heap < 1 || opt->max_heap > 4000)
+		return bfcg_fail(__func__, "invalid arguments", cudaSuccess), BFCG_ERR_ARG;
 	if (batch->n_reads == 0) return BFCG_OK;
 	const bool host = batch->where == BFCG_HOST;
 	const int64_t n = batch->n_reads;
@@ -1004,6 +1016,7 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 		if ((ce = cudaMemcpyAsync(a + o_seq[b], batch->seq + b0, nb, cudaMemcpyHostToDevice, rt.copy_in)) != cudaSuccess) return ce;
 		if (batch->qual && (ce = cudaMemcpyAsync(a + o_qual[b], batch->qual + b0, nb, cudaMemcpyHostToDevice, rt.copy_in)) != cudaSuccess) return ce;
 		if ((ce = cudaMemcpyAsync(a + o_off[b], batch->off + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, rt.copy_in)) != cudaSuccess) return ce;
+		if (opt->refine_ec && (ce = cudaMemcpyAsync(a + o_aux[b], aux + 2 * r0, nr * 8, cudaMemcpyHostToDevice, rt.copy_in)) != cudaSuccess) return ce; // earlier stats in
 		return cudaEventRecord(rt.ev_in[b], rt.copy_in);
 	};
 
@@ -1042,7 +1055,7 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 		P.tab = tab_view(ch);
 		P.k = opt->k, P.q = opt->q, P.min_cov = opt->min_cov, P.win_multi_ec = opt->win_multi_ec, P.max_end_ext = opt->max_end_ext;
 		P.w_ec = opt->w_ec, P.w_ec_high = opt->w_ec_high, P.w_absent = opt->w_absent, P.w_absent_high = opt->w_absent_high;
-		P.max_path_diff = opt->max_path_diff, P.max_heap = opt->max_heap, P.mode = mode;
+		P.max_path_diff = opt->max_path_diff, P.max_heap = opt->max_heap, P.mode = mode, P.refine = opt->refine_ec != 0;
 		P.pool = (EcState*)(a + o_pool), P.heapk = (uint32_t*)(a + o_heapk), P.edits = (uint2*)(a + o_edits);
 		P.heap_cap = heap_cap, P.edit_cap = edit_cap;
 		P.overflow = (uint32_t*)(a + o_ovf), P.ctr = (unsigned long long*)(a + o_ctr);
@@ -1053,7 +1066,7 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 		const uint8_t *w_qual = host ? (batch->qual ? a + o_qual[ib] : 0) : (batch->qual ? batch->qual + b0 : 0);
 		LookupParams lp;
 		lp.tab = P.tab, lp.seq = w_seq, lp.qual = w_qual, lp.n_pos = nb;
-		lp.pl = (uint64_t*)(a + o_pl), lp.pl_words = pl_words, lp.k = opt->k, lp.q = opt->q, lp.min_cov = opt->min_cov, lp.ctr = P.ctr;
+		lp.pl = (uint64_t*)(a + o_pl), lp.pl_words = pl_words, lp.k = opt->k, lp.q = opt->q, lp.min_cov = opt->min_cov, lp.refine = opt->refine_ec != 0, lp.ctr = P.ctr;
 		{ KTime kt(KT_EC_LOOKUP); k_ec_lookup<<<(unsigned)(n_rec / EL_SEG), EL_THREADS, 0, rt.stream>>>(lp); }
 		BFCG_LAUNCH_CHECK();
 		{

@@ -19,6 +19,7 @@ typedef struct {
 	const bfc_ch_t *ch;
 	int mode;
 	long n_batches;
+	uint32_t ori[2];        /* -R: the stats of the latest tagged read (e->ori_st of the reference, correct.c:176, 543) */
 	fq_flat_t flat[N_FLAT];
 	bfcg_stats_t stats;
 } ec_shared_t;
@@ -33,19 +34,55 @@ typedef struct {
 
 static size_t batch_text_bytes(const bfc_opt_t *opt) { return (size_t)opt->chunk_size * 10; }
 
+/* parse_stats (reference correct.c:517-531) over the text after "ec:Z:", packed as worker_ec packs the result
+ * (correct.c:552-553): numbers separated by one character each; what is missing counts as 0 */
+static void parse_ec_tag(const char *s, size_t l, uint32_t ori[2])
+{
+	long v[6] = {0, 0, 0, 0, 0, 0};
+	size_t i = 0;
+	int f;
+	for (f = 0; f < 6 && i < l; ++f) {
+		int neg = 0;
+		if (f) ++i; /* the separator */
+		if (i < l && s[i] == '-') neg = 1, ++i;
+		while (i < l && s[i] >= '0' && s[i] <= '9') v[f] = v[f] * 10 + (s[i++] - '0');
+		if (neg) v[f] = -v[f];
+		if (f == 0 && v[0] != 0) break; /* the other fields are only read for ec_code 0 */
+	}
+	if (v[0] != 0) ori[0] = (uint32_t)v[0] & 7, ori[1] = 0;
+	else {
+		ori[0] = ((uint32_t)v[4] & 0x3fff) << 18 | ((uint32_t)v[5] & 0x3fff) << 4 | ((uint32_t)v[3] & 1) << 3;
+		ori[1] = ((uint32_t)v[1] & 0x3fffff) << 10 | 1u << 8 | ((uint32_t)v[2] & 0xff);
+	}
+}
+
 static void ec_step1(ec_shared_t *es, ec_step_t *data)
 {
 	const bfc_opt_t *opt = es->opt;
 	const size_t n = (size_t)data->blk.n;
-	int rc;
+	uint8_t *skip = 0;
+	int rc = BFCG_OK;
 	data->flat = &es->flat[es->n_batches++ % N_FLAT];
-	if (fq_flat_fill(data->flat, &data->blk, opt->n_threads) < 0) {
+	if (!opt->filter_mode) data->aux = (uint32_t*)malloc((n ? n : 1) * 2 * sizeof(uint32_t));
+	if (opt->refine_ec && !opt->filter_mode) { /* worker_ec's refine branch (correct.c:542-550), in read order */
+		const fq_block_t *b = &data->blk;
+		size_t r, m = 0;
+		skip = (uint8_t*)calloc(n ? n : 1, 1);
+		for (r = 0; r < n; ++r) {
+			if (b->com_off[r] != FQ_NONE && b->com_len[r] >= 5 && memcmp(b->buf + b->com_off[r], "ec:Z:", 5) == 0) {
+				parse_ec_tag(b->buf + b->com_off[r] + 5, b->com_len[r] - 5, es->ori);
+				skip[r] = (es->ori[0] & 7) == 0 && (es->ori[1] & 0xff) < 50; /* fine as it is */
+			}
+			if (!skip[r]) data->aux[2 * m] = es->ori[0], data->aux[2 * m + 1] = es->ori[1], ++m; /* in: the earlier stats */
+		}
+	}
+	if (fq_flat_fill(data->flat, &data->blk, skip, opt->n_threads) < 0) {
 		fprintf(stderr, "[E::%s] out of host memory\n", "bfc_correct");
 		exit(1);
 	}
+	free(skip);
 	if (!opt->filter_mode) {
-		data->aux = (uint32_t*)malloc((n ? n : 1) * 2 * sizeof(uint32_t));
-		rc = bfcg_correct_batch(opt, es->ch, es->mode, &data->flat->b, data->aux, &es->stats);
+		if (data->flat->b.n_reads) rc = bfcg_correct_batch(opt, es->ch, es->mode, &data->flat->b, data->aux, &es->stats);
 	} else {
 		data->keep = (uint8_t*)malloc(n ? n : 1);
 		data->ts = (int32_t*)malloc((n ? n : 1) * 4), data->te = (int32_t*)malloc((n ? n : 1) * 4);
@@ -78,6 +115,7 @@ static void *ec_cb(void *shared, int step, void *_data)
 		fq_out_t o;
 		memset(&o, 0, sizeof(o));
 		o.filter_mode = es->opt->filter_mode, o.discard = es->opt->discard, o.no_qual = es->opt->no_qual;
+		o.refine = es->opt->refine_ec && !es->opt->filter_mode;
 		o.aux = data->aux, o.keep = data->keep, o.tstart = data->ts, o.tend = data->te;
 		if (fq_write(stdout, &data->blk, data->flat, &o, es->opt->n_threads) < 0) {
 			fprintf(stderr, "[E::%s] writing the output failed\n", "bfc_correct");
@@ -98,10 +136,6 @@ void bfc_correct(const char *fn, const bfc_opt_t *opt, const void *ptr)
 	if (bfc_verbose >= 3)
 		fprintf(stderr, "[M::%s @%.1f*%.1f%%] Starting...\n", __func__, realtime() - bfc_real_time,
 				100. * cputime() / (realtime() - bfc_real_time + 1e-6));
-	if (opt->refine_ec) {
-		fprintf(stderr, "[E::%s] refine mode (-R) is not part of the GPU path yet\n", __func__);
-		exit(1);
-	}
 	if (!opt->filter_mode) {
 		uint64_t hist[256], hist_high[64];
 		int i;

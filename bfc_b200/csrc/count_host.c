@@ -36,7 +36,7 @@ static void *count_cb(void *shared, int step, void *_data)
 	} else if (step == 1) {
 		fq_block_t *blk = (fq_block_t*)_data;
 		double rt, eff;
-		if (fq_flat_fill(&cs->flat, blk, cs->opt->n_threads) < 0 ||
+		if (fq_flat_fill(&cs->flat, blk, 0, cs->opt->n_threads) < 0 ||
 			bfcg_count_batch(cs->opt, cs->bf, cs->bf_high, cs->ch, &cs->flat.b, &cs->stats) != BFCG_OK) {
 			fprintf(stderr, "[E::%s] GPU count failed: %s\n", "bfc_count", bfcg_last_error());
 			exit(1);

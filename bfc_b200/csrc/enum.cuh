@@ -67,7 +67,10 @@ __device__ __forceinline__ uint64_t win64(const uint32_t *pl, uint32_t bit)
 // Stage EL_LEAD + EL_SEG stream positions starting at seg0 - EL_LEAD as four bit planes in shared memory: B0, B1
 // (base code bits, bseq.c:9-26), NB (not ACGT, or outside [0, len)), Q (an ACGT base with Q >= q; every ACGT base
 // when qual == 0).  Bit i of a plane = position seg0 - EL_LEAD + i.  Ends with a __syncthreads().
-__device__ __forceinline__ void el_stage_planes(uint32_t (*s_pl)[EL_WORDS], const uint8_t *seq, const uint8_t *qual, uint64_t len, int64_t seg0, int q_min)
+// b_from_q (refine mode, correct.c:31): a base whose quality is <= 5 was corrected by an earlier round, which left the
+// ORIGINAL base in the quality string as 34 + base -- that is the base to start from again.
+__device__ __forceinline__ void el_stage_planes(uint32_t (*s_pl)[EL_WORDS], const uint8_t *seq, const uint8_t *qual, uint64_t len, int64_t seg0, int q_min,
+                                                bool b_from_q = false)
 {
 	const unsigned lane = threadIdx.x & 31;
 	if (threadIdx.x < 8) s_pl[threadIdx.x & 3][EL_WORDS - 1 - (threadIdx.x >> 2)] = 0;
@@ -75,8 +78,11 @@ __device__ __forceinline__ void el_stage_planes(uint32_t (*s_pl)[EL_WORDS], cons
 		const int64_t pos = seg0 - EL_LEAD + i;
 		uint32_t c = 4, q = 0;
 		if (pos >= 0 && (uint64_t)pos < len) {
-			c = base_code(__ldg(seq + pos));
-			q = c < 4 && (qual == 0 || (int)__ldg(qual + pos) - 33 >= q_min);
+			const uint8_t sc = __ldg(seq + pos);
+			const int qv = qual ? (int)__ldg(qual + pos) : 0xFF; // 0xFF = this read has no quality string (bfc_b200.h)
+			c = base_code(sc);
+			if (b_from_q && qual && qv != 0xFF && sc != 0 && qv - 33 <= 5) { c = (uint32_t)(qv - 34) & 7; if (c > 3) c = 4; } // (3-bit field)
+			q = c < 4 && (qual == 0 || qv - 33 >= q_min);
 		}
 		const uint32_t b0 = __ballot_sync(0xffffffffu, c & 1), b1 = __ballot_sync(0xffffffffu, c & 2);
 		const uint32_t nb = __ballot_sync(0xffffffffu, c > 3), bq = __ballot_sync(0xffffffffu, q);

@@ -312,8 +312,10 @@ static void fill_worker(void *data, long i, int tid)
 	int64_t r, r1 = (i + 1) * (int64_t)REC_PER_ITEM < b->n ? (i + 1) * (int64_t)REC_PER_ITEM : b->n;
 	(void)tid;
 	for (r = i * (int64_t)REC_PER_ITEM; r < r1; ++r) {
-		const uint64_t o = f->off[r];
 		const uint32_t l = b->seq_len[r];
+		uint64_t o;
+		if (f->flat_idx[r] < 0) continue;
+		o = f->off[f->flat_idx[r]];
 		memcpy(f->b.seq + o, b->buf + b->seq_off[r], l);
 		f->b.seq[o + l] = 0;
 		if (f->b.qual) {
@@ -348,10 +350,11 @@ static int flat_cache_put(uint8_t *seq, uint8_t *qual, size_t cap)
 	return 0;
 }
 
-int fq_flat_fill(fq_flat_t *f, const fq_block_t *b, int n_threads)
+int fq_flat_fill(fq_flat_t *f, const fq_block_t *b, const uint8_t *skip, int n_threads)
 {
 	const size_t need = (size_t)(b->n_bases + (uint64_t)b->n) + 1;
-	int64_t r;
+	int64_t r, m = 0;
+	int any_qual = 0;
 	uint64_t tot = 0;
 	fill_t ft;
 	if (need > f->cap_bytes) { /* grow-only, reused from batch to batch: pinning memory is expensive */
@@ -371,15 +374,21 @@ int fq_flat_fill(fq_flat_t *f, const fq_block_t *b, int n_threads)
 		if (f->seq_buf == 0 || f->qual_buf == 0) return -1;
 	}
 	if ((size_t)b->n + 1 > f->cap_reads) {
-		free(f->off);
+		free(f->off); free(f->flat_idx);
 		f->cap_reads = (size_t)b->n + 1 + (size_t)b->n / 8;
 		f->off = (uint64_t*)malloc(f->cap_reads * 8);
-		if (f->off == 0) return -1;
+		f->flat_idx = (int64_t*)malloc(f->cap_reads * 8);
+		if (f->off == 0 || f->flat_idx == 0) return -1;
 	}
-	for (r = 0; r < b->n; ++r) { f->off[r] = tot; tot += (uint64_t)b->seq_len[r] + 1; }
-	f->off[b->n] = tot;
-	f->b.n_reads = b->n, f->b.n_bytes = tot, f->b.where = BFCG_HOST, f->b.off = f->off;
-	f->b.seq = f->seq_buf, f->b.qual = b->any_qual ? f->qual_buf : 0;
+	for (r = 0; r < b->n; ++r) {
+		if (skip && skip[r]) { f->flat_idx[r] = -1; continue; }
+		f->flat_idx[r] = m, f->off[m++] = tot;
+		tot += (uint64_t)b->seq_len[r] + 1;
+		any_qual |= b->qual_off[r] != FQ_NONE;
+	}
+	f->off[m] = tot;
+	f->b.n_reads = m, f->b.n_bytes = tot, f->b.where = BFCG_HOST, f->b.off = f->off;
+	f->b.seq = f->seq_buf, f->b.qual = any_qual ? f->qual_buf : 0;
 	ft.f = f, ft.b = b;
 	kt_for(n_threads, fill_worker, &ft, (long)((b->n + REC_PER_ITEM - 1) / REC_PER_ITEM));
 	return 0;
@@ -390,7 +399,7 @@ void fq_flat_free(fq_flat_t *f)
 	if (f->pinned && f->seq_buf && flat_cache_put(f->seq_buf, f->qual_buf, f->cap_bytes)) {}
 	else if (f->pinned) { bfcg_host_free_pinned(f->seq_buf); bfcg_host_free_pinned(f->qual_buf); }
 	else { free(f->seq_buf); free(f->qual_buf); }
-	free(f->off);
+	free(f->off); free(f->flat_idx);
 	memset(f, 0, sizeof(*f));
 }
 
@@ -430,17 +439,23 @@ static void write_worker(void *data, long i, int tid)
 	out = p = (char*)malloc(cap);
 	if (out == 0) { w->oom = 1; w->piece[i] = 0, w->piece_len[i] = 0; return; }
 	for (r = r0; r < r1; ++r) {
-		const uint64_t fo = w->flat->b.off[r];
-		const int has_qual = b->qual_off[r] != FQ_NONE && w->flat->b.qual != 0;
+		const int64_t j = w->flat->flat_idx[r]; /* index in the batch; < 0: the record was left out of it */
+		const uint64_t fo = j >= 0 ? w->flat->b.off[j] : 0;
+		const int has_qual = b->qual_off[r] != FQ_NONE && (j < 0 || w->flat->b.qual != 0);
 		const int is_fq = has_qual && !o->no_qual;
-		const uint8_t *seq = w->flat->b.seq + fo, *qual = has_qual ? w->flat->b.qual + fo : 0;
+		const uint8_t *seq = j >= 0 ? w->flat->b.seq + fo : (const uint8_t*)b->buf + b->seq_off[r];
+		const uint8_t *qual = !has_qual ? 0 : j >= 0 ? w->flat->b.qual + fo : (const uint8_t*)b->buf + b->qual_off[r];
 		uint32_t l = b->seq_len[r];
-		if (!o->filter_mode) { /* correct.c:596-603 */
-			const uint32_t aux = o->aux[2 * r], aux2 = o->aux[2 * r + 1];
+		if (j < 0) { /* -R: untouched, comment kept (correct.c:544-545, 602) */
+			*p++ = is_fq ? '@' : '>';
+			memcpy(p, b->buf + b->name_off[r], b->name_len[r]); p += b->name_len[r];
+			if (b->com_off[r] != FQ_NONE) { *p++ = '\t'; memcpy(p, b->buf + b->com_off[r], b->com_len[r]); p += b->com_len[r]; }
+		} else if (!o->filter_mode) { /* correct.c:596-603 */
+			const uint32_t aux = o->aux[2 * j], aux2 = o->aux[2 * j + 1];
 			if (o->discard && (aux & 7)) continue;
 			*p++ = is_fq ? '@' : '>';
 			memcpy(p, b->buf + b->name_off[r], b->name_len[r]); p += b->name_len[r];
-			if (b->com_off[r] == FQ_NONE) {
+			if (o->refine || b->com_off[r] == FQ_NONE) {
 				memcpy(p, "\tec:Z:", 6); p += 6;
 				p = put_uint(p, aux & 7);
 				if ((aux & 7) == 0) {

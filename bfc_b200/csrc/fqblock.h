@@ -50,12 +50,14 @@ int  fq_reader_is_fast(const fq_reader_t *r);           /* still on the parallel
 typedef struct {
 	bfcg_batch_t b;            /* b.qual is NULL for a batch without any quality string */
 	uint64_t *off;
+	int64_t *flat_idx;         /* per record of the block: its index in the batch, -1 = left out (fq_flat_fill's skip) */
 	uint8_t *seq_buf, *qual_buf;
 	size_t cap_bytes, cap_reads;
 	int pinned;
 } fq_flat_t;
 
-int  fq_flat_fill(fq_flat_t *f, const fq_block_t *blk, int n_threads);   /* 0 ok, -1 out of memory */
+/* skip: NULL, or one byte per record, non-zero = the record does not go into the batch.  0 ok, -1 out of memory */
+int  fq_flat_fill(fq_flat_t *f, const fq_block_t *blk, const uint8_t *skip, int n_threads);
 void fq_flat_free(fq_flat_t *f);
 
 /* the writer of correct.c:591-611 over a block + the (corrected / trimmed) flat batch: formats on n_threads
@@ -63,7 +65,9 @@ void fq_flat_free(fq_flat_t *f);
  * keep/tstart/tend give the kept stretch (aux = !keep). */
 typedef struct {
 	int filter_mode, discard, no_qual;
-	const uint32_t *aux;        /* 2 per read (normal mode) */
+	int refine;                 /* -R: records left out of the batch are written as they came (comment included, correct.c:544-545);
+	                               the others lose their comment and get a fresh tag (correct.c:547-550) */
+	const uint32_t *aux;        /* 2 per read OF THE BATCH (normal mode) */
 	const uint8_t *keep;        /* filter mode */
 	const int32_t *tstart, *tend;
 } fq_out_t;

@@ -81,7 +81,12 @@ int bfcg_count_batch(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, bfc_
 /* correct: bfc_ec1 on every read (correct.c:388-472).  seq/qual are rewritten in
  * place exactly as there (untouched on failure); aux[2*i] = s->aux, aux[2*i+1] =
  * s->aux2 as packed by worker_ec (correct.c:552-553).  `mode` is the return value
- * of bfc_ch_hist.  aux lives where the batch lives (host or device). */
+ * of bfc_ch_hist.  aux lives where the batch lives (host or device).
+ * Refine mode (opt->refine_ec, `bfc -R`): aux is IN/OUT -- on entry aux[2*i], aux[2*i+1] hold the read's earlier
+ * stats in the same packing (what parse_stats reads from the ec:Z: tag into e->ori_st, correct.c:517-531, 543);
+ * bases an earlier round corrected are taken back from the quality string (correct.c:31), and a read whose new
+ * search leaves more absent k-mers than the earlier one keeps its bytes and its earlier stats with rf_code 2
+ * (correct.c:438-442).  Which reads are left out altogether (correct.c:544-545) is the caller's business. */
 int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int mode,
                        bfcg_batch_t *batch, uint32_t *aux, bfcg_stats_t *stats);
 

@@ -89,7 +89,7 @@ orc_ecbuf_t *orc_ecbuf_new(const orc_opt_t *opt, const orc_ch_t *ch, int mode);
 void         orc_ecbuf_free(orc_ecbuf_t *e);
 /* edits seq/qual in place exactly as bfc_ec1 does; returns aux | (uint64_t)aux2 << 32
  * packed like worker_ec (correct.c:552-553) */
-uint64_t orc_ec1(orc_ecbuf_t *e, char *seq, char *qual);
+uint64_t orc_ec1(orc_ecbuf_t *e, char *seq, char *qual, const uint32_t *ori /* refine mode: earlier aux, aux2 */);
 /* counters accumulated over orc_ec1 calls: [0] table lookups, [1] heap pops, [2] max stack */
 const uint64_t *orc_ecbuf_counters(const orc_ecbuf_t *e);
 /* whole batch, sequentially; seq/qual are edited in place; aux[2*i], aux[2*i+1] per read */

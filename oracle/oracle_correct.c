@@ -380,15 +380,18 @@ static uint64_t best_island(int k, const oseq_t *s)
 }
 
 /* reference correct.c:388-472 (bfc_ec1) + the packing of correct.c:552-553.
- * refine mode (-R, correct.c:438-442) is outside this round's scope: refine_ec must be 0. */
-uint64_t orc_ec1(orc_ecbuf_t *e, char *seq, char *qual)
+ * Refine mode (-R): `ori` = the read's earlier stats (e->ori_st in the reference, correct.c:176, 543) packed like
+ * the result: ori[0] = aux, ori[1] = aux2.  Bases that an earlier round corrected are taken back from the quality
+ * string (correct.c:31); if this round leaves more absent k-mers than the earlier one the earlier stats come back
+ * with rf_code 2 and the read stays as it is (correct.c:438-442), else rf_code is 3 (correct.c:470). */
+uint64_t orc_ec1(orc_ecbuf_t *e, char *seq, char *qual, const uint32_t *ori)
 {
 	const orc_opt_t *o = e->opt;
 	int i, start = 0, end = 0, n_n = 0, rv[2], max_heap[2], n;
-	uint32_t ec_code = 1, brute = 0, n_ec = 0, n_ec_high = 0, n_absent = 0, mh = 0, rf_code = 0;
+	uint32_t ec_code = 1, brute = 0, n_ec = 0, n_ec_high = 0, n_absent = 0, mh = 0, rf_code = o->refine_ec ? 1 : 0;
 	uint64_t r;
 
-	seq_convert(seq, qual, o->q, &e->seq, 0);
+	seq_convert(seq, qual, o->q, &e->seq, o->refine_ec);
 	n = (int)e->seq.n;
 	for (i = 0; i < n; ++i) n_n += e->seq.a[i].ob > 3;
 	if (n_n > n * .05) { ec_code = 2; goto done; }
@@ -422,6 +425,8 @@ uint64_t orc_ec1(orc_ecbuf_t *e, char *seq, char *qual)
 	ec_code = 0, n_absent = rv[0] + rv[1];
 	seq_revcomp(&e->ec[1]);
 	seq_revcomp(&e->seq);
+	if (o->refine_ec && ori && (ori[0] & 7) == 0 && n_absent > ori[1] >> 10) /* correct.c:438-442 */
+		return (uint64_t)((ori[1] & ~(3u << 8)) | 2u << 8) << 32 | ori[0];
 	for (i = 0; i < n; ++i) {
 		obase_t *c = &e->seq.a[i];
 		int f = e->ec[0].a[i].b, g = e->ec[1].a[i].b;
@@ -437,6 +442,7 @@ uint64_t orc_ec1(orc_ecbuf_t *e, char *seq, char *qual)
 		seq[i] = (diff ? "acgtn" : "ACGTN")[c->b];
 		if (qual) qual[i] = diff ? 34 + c->ob : "+?"[c->q];
 	}
+	if (o->refine_ec) rf_code = 3; /* correct.c:470 */
 done:
 	{
 		uint32_t aux = (n_ec & 0x3fff) << 18 | (n_ec_high & 0x3fff) << 4 | brute << 3 | ec_code;
@@ -453,7 +459,7 @@ void orc_correct_batch(const orc_opt_t *opt, const orc_ch_t *ch, int mode, int64
 	for (i = 0; i < n_reads; ++i) {
 		int len = (int)(off[i + 1] - off[i] - 1);
 		char *q = qual && (len == 0 || qual[off[i]] != 0) ? (char*)qual + off[i] : 0;
-		uint64_t r = orc_ec1(e, (char*)seq + off[i], q);
+		uint64_t r = orc_ec1(e, (char*)seq + off[i], q, opt->refine_ec ? aux + 2 * i : 0); /* refine: aux is in/out */
 		aux[2 * i] = (uint32_t)r, aux[2 * i + 1] = (uint32_t)(r >> 32);
 	}
 	if (counters) memcpy(counters, e->counters, sizeof(e->counters));

@@ -20,6 +20,9 @@ class Case:
         self.fastq = gzip.open(os.path.join(d, "in.fq.gz")).read()
         self.corrected = gzip.open(os.path.join(d, "corrected.fq.gz")).read()
         self.trimmed = gzip.open(os.path.join(d, "trimmed.fq.gz")).read()
+        self.refined = gzip.open(os.path.join(d, "refined.fq.gz")).read()                 # `bfc -R` over corrected
+        self.refine_forced_in = gzip.open(os.path.join(d, "refine_forced_in.fq.gz")).read()  # tags rewritten: every read re-run
+        self.refined_forced = gzip.open(os.path.join(d, "refined_forced.fq.gz")).read()
         t = np.load(os.path.join(d, "table.npz"))
         self.sub, self.key = t["sub"], t["key"]
         self.recs = orc.parse_fastx(self.fastq)

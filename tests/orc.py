@@ -224,6 +224,59 @@ def format_corrected(recs, seq: np.ndarray, qual, off: np.ndarray, aux: np.ndarr
     return b"".join(out)
 
 
+def parse_ec_tag(comment: bytes):
+    """parse_stats (reference correct.c:517-531) -> (aux, aux2) as worker_ec packs them (correct.c:552-553)."""
+    import re
+    v = [int(x) for x in re.findall(rb"-?\d+", comment[5:])] + [0] * 6
+    ec_code = v[0]
+    if ec_code != 0:
+        return ec_code & 7, 0
+    n_absent, max_heap, brute, n_ec, n_ec_high = v[1:6]
+    return (n_ec & 0x3fff) << 18 | (n_ec_high & 0x3fff) << 4 | (brute & 1) << 3, (n_absent & 0x3fffff) << 10 | 1 << 8 | (max_heap & 0xff)
+
+
+def refine_plan(recs):
+    """worker_ec's refine branch (correct.c:542-550) under -t1.  Returns (comments, skip, ori): the comment every record
+    carries (kseq's sticky comment), which records are left alone (earlier round fine and max_heap < 50), and for the
+    others the earlier stats e->ori_st holds when they are corrected -- those of the latest tagged record so far."""
+    comments, skip, ori = [], [], []
+    sticky, cur = None, (0, 0)
+    for r in recs:
+        if r[1] is not None:
+            sticky = r[1]
+        comments.append(sticky)
+        sk = False
+        if sticky is not None and sticky.startswith(b"ec:Z:"):
+            cur = parse_ec_tag(sticky)
+            sk = (cur[0] & 7) == 0 and (cur[1] & 0xff) < 50
+        skip.append(sk)
+        ori.append(cur)
+    return comments, skip, ori
+
+
+def format_refined(recs, comments, skip, seq, qual, off, aux, no_qual=False) -> bytes:
+    """The step-2 printer in -R mode: skipped records keep their comment and their bytes; the others (whose corrected
+    bytes and stats are the i-th entries of seq / qual / off / aux, in order) get a fresh tag."""
+    out, j = [], 0
+    for i, r in enumerate(recs):
+        is_fq = r[3] is not None and not no_qual
+        if skip[i]:
+            out.append((b"@" if is_fq else b">") + r[0] + b"\t" + comments[i] + b"\n" + r[2] + b"\n")
+            if is_fq:
+                out.append(b"+\n" + r[3] + b"\n")
+            continue
+        o, e = int(off[j]), int(off[j + 1]) - 1
+        a, a2 = int(aux[2 * j]), int(aux[2 * j + 1])
+        tag = b"\tec:Z:%d" % (a & 7)
+        if (a & 7) == 0:
+            tag += b"_%d:%d_%d_%d:%d_%d" % (a2 >> 10, a2 & 0xff, a >> 3 & 1, a >> 18 & 0x3fff, a >> 4 & 0x3fff, a2 >> 8 & 3)
+        out.append((b"@" if is_fq else b">") + r[0] + tag + b"\n" + seq[o:e].tobytes() + b"\n")
+        if is_fq:
+            out.append(b"+\n" + qual[o:e].tobytes() + b"\n")
+        j += 1
+    return b"".join(out)
+
+
 def format_trimmed(recs, seq, qual, off, keep, tstart, tend, no_qual=False) -> bytes:
     """The step-2 printer of the reference in `-1` mode (correct.c:605-611)."""
     out = []
@@ -330,12 +383,13 @@ class OracleRun:
         mode = self.L.orc_ch_hist(self.ch, as_u64p(cnt), as_u64p(high))
         return mode, cnt, high
 
-    def correct(self, seq, qual, off):
-        """Returns (seq', qual', aux[2n], counters[3]); inputs are not modified."""
+    def correct(self, seq, qual, off, ori=None):
+        """Returns (seq', qual', aux[2n], counters[3]); inputs are not modified.  Refine mode (opt.refine_ec): `ori` =
+        the earlier stats, 2 words per read (aux is in/out in the C call)."""
         s = seq.copy()
         q = qual.copy() if qual is not None else None
         n = len(off) - 1
-        aux = np.zeros(2 * n, dtype=np.uint32)
+        aux = np.zeros(2 * n, dtype=np.uint32) if ori is None else np.array(ori, dtype=np.uint32).reshape(-1).copy()
         counters = np.zeros(3, dtype=np.uint64)
         mode, _, _ = self.hist()
         self.L.orc_correct_batch(C.byref(self.opt), self.ch, mode, n, as_u64p(off), as_u8p(s),

@@ -132,3 +132,69 @@ def test_block_reader_gzip_and_threads(L, tmp_path):
     for threads in (1, 2, 7):
         got, fast_blocks = read_fast(L, p, 1, 30_000, threads)
         assert got == want and fast_blocks > 0
+
+
+class Batch(C.Structure):
+    _fields_ = [("n_reads", C.c_int64), ("n_bytes", C.c_uint64), ("where", C.c_int), ("off", u64p),
+                ("seq", C.POINTER(C.c_uint8)), ("qual", C.POINTER(C.c_uint8))]
+
+
+class Flat(C.Structure):
+    _fields_ = [("b", Batch), ("off", u64p), ("flat_idx", C.POINTER(C.c_int64)), ("seq_buf", C.c_void_p), ("qual_buf", C.c_void_p),
+                ("cap_bytes", C.c_size_t), ("cap_reads", C.c_size_t), ("pinned", C.c_int)]
+
+
+class Out(C.Structure):
+    _fields_ = [("filter_mode", C.c_int), ("discard", C.c_int), ("no_qual", C.c_int), ("refine", C.c_int),
+                ("aux", u32p), ("keep", C.POINTER(C.c_uint8)), ("tstart", C.POINTER(C.c_int32)), ("tend", C.POINTER(C.c_int32))]
+
+
+@pytest.mark.parametrize("refine", [0, 1])
+def test_writer_with_records_left_out_of_the_batch(L, tmp_path, refine):
+    """fq_flat_fill(skip) + fq_write: the -R writer (records left alone keep comment and bytes, the others get a fresh
+    tag from aux) and the plain writer, against the printers of tests/orc.py (which mirror correct.c:591-611)."""
+    import gzip as gz
+    import numpy as np
+    import orc
+    from golden_util import Case
+    c = Case("k33_rep")
+    data = c.refine_forced_in if refine else gz.open(os.path.join(os.path.dirname(__file__), "golden", "k33_rep", "in.fq.gz")).read()
+    p = str(tmp_path / "in.fq")
+    open(p, "wb").write(data)
+    recs = orc.parse_fastx(data)
+    comments, skip, ori = orc.refine_plan(recs)
+    if refine:
+        skip = [i % 3 == 0 for i in range(len(recs))]   # leave every third record out, whatever its tag says
+    else:
+        skip = [False] * len(recs)
+    L.fq_flat_fill.argtypes = [C.POINTER(Flat), C.POINTER(Block), C.POINTER(C.c_uint8), C.c_int]
+    L.fq_write.argtypes = [C.c_void_p, C.POINTER(Block), C.POINTER(Flat), C.POINTER(Out), C.c_int]
+    L.fq_flat_free.argtypes = [C.POINTER(Flat)]
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+    f = L.fq_open(p.encode(), 3)
+    b, flat = Block(), Flat()
+    assert L.fq_next(f, 1 << 30, 1 if refine else 0, C.byref(b)) and b.n == len(recs)
+    sk = (C.c_uint8 * len(recs))(*[1 if s else 0 for s in skip])
+    assert L.fq_flat_fill(C.byref(flat), C.byref(b), sk if refine else None, 3) == 0
+    m = flat.b.n_reads
+    assert m == sum(1 for s in skip if not s)
+    rng = np.random.default_rng(5)
+    aux = rng.integers(0, 1 << 32, size=2 * m, dtype=np.uint32)
+    aux[0::2] &= ~np.uint32(6)  # ec_code 0 or 1
+    o = Out(0, 0, 0, refine, aux.ctypes.data_as(u32p), None, None, None)
+    outp = str(tmp_path / "out.fq")
+    fp = libc.fopen(outp.encode(), b"wb")
+    assert L.fq_write(fp, C.byref(b), C.byref(flat), C.byref(o), 3) == 0
+    libc.fclose(fp)
+    n_bytes = flat.b.n_bytes
+    seq = np.ctypeslib.as_array(flat.b.seq, shape=(n_bytes,)).copy()
+    qual = np.ctypeslib.as_array(flat.b.qual, shape=(n_bytes,)).copy()
+    off = np.ctypeslib.as_array(flat.b.off, shape=(m + 1,)).copy()
+    want = orc.format_refined(recs, comments, skip, seq, qual, off, aux)
+    assert open(outp, "rb").read() == want
+    L.fq_flat_free(C.byref(flat))
+    L.fq_block_free(C.byref(b))
+    L.fq_close(f)

@@ -309,3 +309,54 @@ def test_device_batches_and_many_windows(bfc, monkeypatch, path):
         for p in (d_seq, d_qual, d_off, d_aux):
             L.bfcg_dev_free(p)
         eh.close(); ed.close(); o.close()
+
+
+@pytest.mark.parametrize("k,b,repeat", [(33, 24, 0.3), (21, 20, 0.5), (55, 24, 0.2)])
+def test_refine_mode_against_oracle(bfc, k, b, repeat):
+    """-R through the C ABI (aux carries the earlier stats in, the new ones out): bases taken back from the quality
+    string, the n_absent comparison (rf_code 2 / 3), failures (rf_code 1) -- equal to the oracle, which is pinned to
+    the reference's `bfc -R` by tests/test_oracle_golden.py."""
+    seq, qual, off = synth_batch(40000, 9000, 120, seed=k + 3, err=0.02, repeat=repeat)
+    n = len(off) - 1
+    o1 = orc.OracleRun(orc.make_opt(k=k, bf_shift=b))
+    o2 = orc.OracleRun(orc.make_opt(k=k, bf_shift=b, refine_ec=1))
+    e1 = bfc.Engine(bfc.make_opt(k=k, bf_shift=b))
+    e2 = bfc.Engine(bfc.make_opt(k=k, bf_shift=b, refine_ec=1))
+    try:
+        o1.count(seq, qual, off)
+        e1.count(seq, qual, off)
+        s1, q1, a1 = e1.correct(seq, qual, off)        # first round
+        # earlier stats as a second round would read them from the tags; every other read claims 0 absent k-mers
+        ori = a1.copy().reshape(-1, 2)
+        ori[:, 1] = (ori[:, 1] & ~np.uint32(3 << 8)) | np.uint32(1 << 8)
+        ori[::2, 1] &= np.uint32(0x3ff)
+        o2.ch, keep_o = o1.ch, o2.ch
+        e2.ch, keep_e = e1.ch, e2.ch
+        so, qo, ao, _ = o2.correct(s1, q1, off, ori=ori)
+        aux = ori.reshape(-1).copy()
+        sg, qg = s1.copy(), q1.copy()
+        e2.correct_batch(bfc.api.host_batch(sg, qg, off), aux.ctypes.data)
+        assert np.array_equal(aux, ao) and np.array_equal(sg, so) and np.array_equal(qg, qo)
+        rf = (aux.reshape(-1, 2)[:, 1] >> 8) & 3
+        assert (rf == 2).any() and (rf == 3).any()
+        assert n == len(rf)
+    finally:
+        o2.ch, e2.ch = keep_o, keep_e
+        for x in (o1, o2, e1, e2):
+            x.close()
+
+
+def test_cli_refine_matches_reference_golden(bfc, tmp_path):
+    """`bfc -R` end to end (tag parsing, reads left alone, sticky e->ori_st, fresh tags) against the reference's stdout."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(bfc.lib_path()), "bfc")
+    for name in ("k31_edge", "k33_rep", "k63_h7"):
+        c = Case(name)
+        fq = tmp_path / (name + ".fq")
+        fq.write_bytes(c.fastq)
+        args = ["-k", str(c.meta["k"]), "-b", str(c.meta["b"])] + c.meta["extra_args"]
+        for data, want in ((c.corrected, c.refined), (c.refine_forced_in, c.refined_forced)):
+            c1 = tmp_path / (name + ".c1.fq")
+            c1.write_bytes(data)
+            out = subprocess.run([exe, "-R"] + args + ["-t", "3", str(fq), str(c1)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True).stdout
+            assert out == want

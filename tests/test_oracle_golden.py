@@ -86,3 +86,27 @@ def test_trim_golden(oracle, name):
     keep, ts, te = o.trim(c.seq, c.off)
     assert orc.format_trimmed(c.recs, c.seq, c.qual, c.off, keep, ts, te) == c.trimmed
     o.close()
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("which", ["refined", "refined_forced"])
+def test_oracle_refine_mode(oracle, name, which):
+    """`bfc -R` (second round over tagged reads): the oracle + the host rules of worker_ec's refine branch against
+    the reference's stdout -- over its own first-round output, and over the same with every tag rewritten so that
+    every read is re-run and both outcomes of the n_absent comparison occur (tools/make_golden_refine.py)."""
+    c = Case(name)
+    data = c.corrected if which == "refined" else c.refine_forced_in
+    recs = orc.parse_fastx(data)
+    o = orc.OracleRun(c.opt())
+    r = orc.OracleRun(c.opt(refine_ec=1))
+    try:
+        o.count(c.seq, c.qual, c.off)                 # counted from the original reads
+        r.ch, r_ch = o.ch, r.ch                       # the refine run corrects against that table
+        comments, skip, ori = orc.refine_plan(recs)
+        todo = [x for x, sk in zip(recs, skip) if not sk]
+        seq, qual, off = orc.batch_from_records(todo)
+        s, q, aux, _ = r.correct(seq, qual, off, ori=[v for v, sk in zip(ori, skip) if not sk]) if todo else (seq, qual, np.zeros(0, np.uint32), None)
+        assert orc.format_refined(recs, comments, skip, s, q, off, aux) == (c.refined if which == "refined" else c.refined_forced)
+    finally:
+        r.ch = r_ch
+        o.close(); r.close()
