@@ -262,11 +262,15 @@ def test_sharded_count_kernels_emulated_on_one_gpu(bfc, monkeypatch, world, k, b
         o.close()
 
 
-@pytest.mark.parametrize("path", ["part", "probe"])
+@pytest.mark.parametrize("path", ["part", "probe", "part-wire-noext"])
 def test_device_batches_and_many_windows(bfc, monkeypatch, path):
     """What bench.py runs: batches resident in HBM (BFCG_DEVICE), and host batches cut into many count /
     correct windows (the double-buffered copy streams cycle several times); both equal the oracle."""
     import ctypes as C
+    if path == "part-wire-noext":  # the A/B switches: 16-byte records inside the count, no end-of-read lookup memo
+        path = "part"
+        monkeypatch.setenv("BFC_B200_COUNT_WIRE", "1")
+        monkeypatch.setenv("BFC_B200_EC_NOEXT", "1")
     monkeypatch.setenv("BFC_B200_COUNT", path)
     monkeypatch.setenv("BFC_B200_EC_BATCH", "150000")
     monkeypatch.setenv("BFC_B200_COUNT_WINDOW", "65536")
