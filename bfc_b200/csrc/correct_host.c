@@ -101,6 +101,7 @@ static void *ec_cb(void *shared, int step, void *_data)
 		ec_step_t *ret = (ec_step_t*)calloc(1, sizeof(ec_step_t));
 		const int keep_comment = (es->opt->filter_mode || es->opt->refine_ec);
 		const int ok = fq_next(es->ks, batch_text_bytes(es->opt), keep_comment, &ret->blk);
+		if (ok < 0) { fprintf(stderr, "[E::%s] out of host memory while reading\n", "bfc_correct"); exit(1); }
 		fprintf(stderr, "[M::%s] read %ld sequences\n", "bfc_ec_cb", (long)ret->blk.n);
 		if (ok) return ret;
 		free(ret);

@@ -30,6 +30,7 @@ static void *count_cb(void *shared, int step, void *_data)
 	if (step == 0) {
 		fq_block_t *blk = (fq_block_t*)calloc(1, sizeof(fq_block_t));
 		const int ok = fq_next(cs->ks, batch_text_bytes(cs->opt), 0, blk);
+		if (ok < 0) { fprintf(stderr, "[E::%s] out of host memory while reading\n", "bfc_count"); exit(1); }
 		fprintf(stderr, "[M::%s] read %ld sequences\n", "bfc_count_cb", (long)blk->n);
 		if (ok) return blk;
 		free(blk);

@@ -273,7 +273,7 @@ int fq_next(fq_reader_t *rd, size_t target, int keep_comment, fq_block_t *b)
 		char *data = (char*)malloc(carry0 + target + 1);
 		size_t len = carry0, used = 0;
 		int rc;
-		if (data == 0) return 0;
+		if (data == 0) return -1;
 		if (carry0) memcpy(data, rd->carry, carry0);
 		free(rd->carry); rd->carry = 0, rd->carry_len = 0;
 		while (!rd->eof && len < carry0 + target) {
@@ -291,13 +291,13 @@ int fq_next(fq_reader_t *rd, size_t target, int keep_comment, fq_block_t *b)
 			}
 			return 1;
 		}
-		if (rc < 0) { free(data); return 0; }
+		if (rc < 0) { free(data); return -1; }
 		/* not plain four-line FASTQ: the tolerant parser takes the stream over, starting with this block's text */
 		rd->fast = 0;
 		if (rd->fd >= 0) gzseek(rd->fp, (z_off_t)rd->pos, SEEK_SET); /* the stream goes on where the pread()s stopped */
 		rd->slow = bseq_open_from(rd->fp, (unsigned char*)data, len, rd->last_comment);
 	}
-	return slow_block(rd, target, keep_comment, b) == 1;
+	return slow_block(rd, target, keep_comment, b); /* 1, 0 at end of input, -1 out of memory */
 }
 
 /* ---------------------------------------------------------------- flat batch */

@@ -41,7 +41,7 @@ typedef struct fq_reader_s fq_reader_t;
 
 fq_reader_t *fq_open(const char *fn, int n_threads);   /* plain or gzip'd, "-" = stdin; NULL on failure */
 void fq_close(fq_reader_t *r);
-/* next block of about target_bytes of input text; 0 at end of input (blk zeroed), 1 otherwise */
+/* next block of about target_bytes of input text: 1, 0 at end of input (blk zeroed), -1 out of memory */
 int  fq_next(fq_reader_t *r, size_t target_bytes, int keep_comment, fq_block_t *blk);
 void fq_block_free(fq_block_t *blk);
 int  fq_reader_is_fast(const fq_reader_t *r);           /* still on the parallel path (tests) */

@@ -64,7 +64,9 @@ def read_fast(L, path, keep_comment, target, threads=3):
     out, fast_blocks = [], 0
     while True:
         b = Block()
-        if not L.fq_next(f, target, keep_comment, C.byref(b)):
+        rc = L.fq_next(f, target, keep_comment, C.byref(b))
+        assert rc >= 0
+        if rc == 0:
             break
         fast_blocks += L.fq_reader_is_fast(f)
         raw = C.string_at(b.buf, b.buf_len)
@@ -176,7 +178,7 @@ def test_writer_with_records_left_out_of_the_batch(L, tmp_path, refine):
     libc.fclose.argtypes = [C.c_void_p]
     f = L.fq_open(p.encode(), 3)
     b, flat = Block(), Flat()
-    assert L.fq_next(f, 1 << 30, 1 if refine else 0, C.byref(b)) and b.n == len(recs)
+    assert L.fq_next(f, 1 << 30, 1 if refine else 0, C.byref(b)) == 1 and b.n == len(recs)
     sk = (C.c_uint8 * len(recs))(*[1 if s else 0 for s in skip])
     assert L.fq_flat_fill(C.byref(flat), C.byref(b), sk if refine else None, 3) == 0
     m = flat.b.n_reads
