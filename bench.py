@@ -367,7 +367,7 @@ def main():
     value = n * args.steps / (ms / 1e3) / 1e6
     if world > 1:  # whole-job counters for the roofline arithmetic and the stats block
         import torch
-        keys = ["n_kmers", "n_pass", "n_pending", "n_conflict", "n_lookups", "n_redo", "n_launches"]
+        keys = ["n_kmers", "n_pass", "n_pending", "n_conflict", "n_lookups", "n_search_lookups", "n_redo", "n_launches"]
         t = torch.tensor([st[k_] for k_ in keys], dtype=torch.int64, device="cuda")
         dist.all_reduce(t)
         launches_rank0 = st["n_launches"]
@@ -381,9 +381,12 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     count_bytes = 2 * n * RB * args.steps + 64 * st["n_kmers"] + 16 * st["n_pass"]
-    correct_bytes = 32 * st["n_lookups"] + 4 * n * RB * args.steps
+    # k_ec_search: a 32-byte sector per lookup it makes itself + 4 B per base of flags / planes in and edits out;
+    # k_ec_lookup: one lookup per k-mer of every read (bfc_ec_kcov) + seq and qual in + a byte of planes out per position
+    correct_bytes = 32 * st["n_search_lookups"] + 4 * n * RB * args.steps
+    lookup_bytes = 32 * st["n_kmers"] + 3 * n * RB * args.steps
     kern = {}
-    for name, alg in (("count_probe", count_bytes), ("count_part", count_bytes), ("correct", correct_bytes)):
+    for name, alg in (("count_probe", count_bytes), ("count_part", count_bytes), ("correct", correct_bytes), ("ec_lookup", lookup_bytes)):
         t_ms, launches = kt.get(name, (0.0, 0))
         if launches:
             kern[name] = {"ms": t_ms, "launches": launches, "algorithmic_bytes": alg, "GBps": alg / (t_ms / 1e3) / 1e9,
@@ -397,7 +400,8 @@ def main():
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(dom, {}).get("dram_bytes_per_launch")
     d = kern.get(dom, {"GBps": 0.0, "launches": 1, "algorithmic_bytes": 0})
-    roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": d["GBps"], "peak": peak, "unit": "GB/s",
+    kernel_name = {"count_probe": "k_count_probe", "count_part": "k_count_part", "correct": "k_ec_search"}[dom]
+    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": d["GBps"], "peak": peak, "unit": "GB/s",
                 "frac": d["GBps"] / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": d["algorithmic_bytes"] / max(1, d["launches"]),
                 "kernels": kern}
@@ -491,7 +495,8 @@ def main():
                 "stats": {"kmers_per_step": st["n_kmers"] // args.steps, "f_pass": st["n_pass"] / max(1, st["n_kmers"]),
                           "pending_frac": st["n_pending"] / max(1, st["n_kmers"]),
                           "conflict_frac": st["n_conflict"] / max(1, st["n_kmers"]),
-                          "lookups_per_read": st["n_lookups"] / max(1, n * args.steps), "redo": st["n_redo"]}}
+                          "lookups_per_read": st["n_lookups"] / max(1, n * args.steps),
+                          "search_lookups_per_read": st["n_search_lookups"] / max(1, n * args.steps), "redo": st["n_redo"]}}
         print(json.dumps(line))
     if world == 1:
         eng.close()

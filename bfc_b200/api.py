@@ -48,7 +48,7 @@ class Batch(C.Structure):
 class Stats(C.Structure):
     """bfcg_stats_t."""
     _fields_ = [(n, C.c_uint64) for n in ("n_kmers", "n_pass", "n_pending", "n_conflict", "n_lookups",
-                                           "n_redo", "n_launches")] + [("kernel_ms", C.c_double)]
+                                           "n_redo", "n_launches")] + [("kernel_ms", C.c_double), ("n_search_lookups", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

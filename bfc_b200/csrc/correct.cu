@@ -100,7 +100,7 @@ struct EcParams {
 	const uint32_t *redo;        // when set: thread job list (job = read * 2 + dir); n_jobs = its length
 	int64_t n_jobs;
 	uint32_t *overflow;          // jobs whose edit list overflowed
-	unsigned long long *ctr;     // [0] n_overflow, [1] n_lookups, [2] next job to hand out
+	unsigned long long *ctr;     // [0] n_overflow, [1] n_lookups, [2] next job to hand out, [3] lookups of k_ec_search
 };
 
 __device__ __forceinline__ int comp_b(int b) { return b < 4 ? 3 - b : 4; }
@@ -815,6 +815,7 @@ __global__ void __launch_bounds__(EC_THREADS, EC_CTAS_PER_SM) k_ec_search(EcPara
 		}
 	}
 	block_add(P.ctr + 1, n_lookups);
+	block_add(P.ctr + 3, n_lookups);
 }
 
 // ------------------------------------------------------------------ K6c: merge + rewrite, one read per warp
@@ -1087,7 +1088,7 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 			if (ce != cudaSuccess) { rc = bfcg_fail(__func__, "staging copy", ce); break; }
 		}
 		if (host && w >= 1) drain_aux(w - 1);
-		unsigned long long c[2];
+		unsigned long long c[4];
 		BFCG_CUDA(cudaMemcpyAsync(c, P.ctr, sizeof(c), cudaMemcpyDeviceToHost, rt.stream));
 		BFCG_CUDA(cudaStreamSynchronize(rt.stream));
 		// jobs whose edit list outgrew the scratch: same kernel, fewer threads, larger lists
@@ -1115,7 +1116,7 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 		cudaFree(redo); cudaFree(big);
 		{ KTime kt(KT_EC_MERGE); k_ec_merge<<<(unsigned)std::min<int64_t>((nr + 7) / 8, (int64_t)rt.sm_count * 16), 256, 0, rt.stream>>>(P); }
 		BFCG_LAUNCH_CHECK();
-		if (stats) stats->n_lookups += c[1];
+		if (stats) stats->n_lookups += c[1], stats->n_search_lookups += c[3];
 		if (host) { // the corrected window leaves on the copy-out stream while the next one is searched
 			cudaError_t ce = cudaEventRecord(rt.ev_done[ib], rt.stream);
 			if (ce == cudaSuccess) ce = cudaStreamWaitEvent(rt.copy_out, rt.ev_done[ib], 0);

@@ -52,6 +52,7 @@ typedef struct {
 	uint64_t n_redo;         /* reads re-run with a larger search scratch                   */
 	uint64_t n_launches;     /* kernels launched                                            */
 	double   kernel_ms;      /* device time of those kernels (CUDA events), when timing on  */
+	uint64_t n_search_lookups; /* of n_lookups: those made inside the search kernel (k_ec_search) */
 } bfcg_stats_t;
 
 /* device selection / info ------------------------------------------------------- */
