@@ -72,12 +72,14 @@ static inline int rd_getc(bseq_file_t *f)
  * *dret = the delimiter that ended the token, 0 at end of input. */
 static long rd_until(bseq_file_t *f, int line, str_t *str, int *dret, int append)
 {
+	int gotany = 0;
 	if (dret) *dret = 0;
 	if (!append) str->l = 0;
 	if (f->begin >= f->end && f->eof && f->pre_pos >= f->pre_len) return -1;
 	for (;;) {
 		int i;
 		if (f->begin >= f->end && !rd_fill(f)) break;
+		gotany = 1;
 		if (line) {
 			unsigned char *nl = (unsigned char*)memchr(f->buf + f->begin, '\n', f->end - f->begin);
 			i = nl ? (int)(nl - f->buf) : f->end;
@@ -91,6 +93,7 @@ static long rd_until(bseq_file_t *f, int line, str_t *str, int *dret, int append
 			break;
 		}
 	}
+	if (!gotany) return -1; /* the input ended before this token began (kseq.h: !gotany && ks_eof) */
 	str_reserve(str, str->l + 2);
 	if (line && str->l > 1 && str->s[str->l - 1] == '\r') --str->l;
 	str->s[str->l] = 0;
@@ -156,6 +159,9 @@ bseq_file_t *bseq_open_from(void *gz, unsigned char *pre, size_t pre_len, const 
 	return f;
 }
 
+/* nothing left to read (an empty batch from bseq_read() otherwise means "stopped at a malformed record") */
+int bseq_at_eof(const bseq_file_t *f) { return f->begin >= f->end && f->eof && f->pre_pos >= f->pre_len; }
+
 void bseq_close(bseq_file_t *f)
 {
 	if (f == 0) return;
@@ -185,7 +191,7 @@ bseq1_t *bseq_read(bseq_file_t *f, int chunk_size, int keep_comment, int *n_)
 		}
 		s = &seqs[n++];
 		s->name = dup_n(f->name.s, f->name.l);
-		s->comment = f->comment_seen && keep_comment ? dup_n(f->comment.s, strlen(f->comment.s)) : 0;
+		s->comment = f->comment.s && f->comment_seen && keep_comment ? dup_n(f->comment.s, strlen(f->comment.s)) : 0; /* (bseq.c:66 tests the pointer) */
 		s->seq = dup_n(f->seq.s, f->seq.l);
 		s->qual = f->qual.l ? dup_n(f->qual.s, f->qual.l) : 0;
 		s->l_seq = (int)f->seq.l;

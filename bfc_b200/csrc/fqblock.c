@@ -11,6 +11,7 @@
 #include "fqblock.h"
 
 bseq_file_t *bseq_open_from(void *gz, unsigned char *pre, size_t pre_len, const char *comment); /* bseq.c */
+int bseq_at_eof(const bseq_file_t *f);
 
 struct fq_reader_s {
 	gzFile fp;
@@ -240,10 +241,18 @@ static int slow_block(fq_reader_t *rd, size_t target, int keep_comment, fq_block
 {
 	int n = 0, i;
 	const long chunk = target > 0x7fffffffUL / 2 ? 0x7fffffff / 2 : (long)(target / 2 + 1); /* bases ~ half of the text */
-	bseq1_t *seqs = bseq_read(rd->slow, (int)chunk, keep_comment, &n);
+	bseq1_t *seqs = 0;
 	size_t tot = 0, at = 0;
 	memset(b, 0, sizeof(*b));
-	if (seqs == 0 || n == 0) { free(seqs); return 0; }
+	/* bseq_read() ends a batch at a record whose quality length is wrong (kseq's -2) and goes on behind it on the next
+	 * call; a batch that is empty for that reason is not the end of the input (the reference, whose batches are 100 M
+	 * bases, would only stop there if the bad record happened to be the first of a batch) */
+	for (;;) {
+		seqs = bseq_read(rd->slow, (int)chunk, keep_comment, &n);
+		if (seqs && n > 0) break;
+		free(seqs);
+		if (bseq_at_eof(rd->slow)) return 0;
+	}
 	for (i = 0; i < n; ++i)
 		tot += strlen(seqs[i].name) + 1 + (seqs[i].comment ? strlen(seqs[i].comment) + 1 : 0) + (size_t)seqs[i].l_seq * (seqs[i].qual ? 2 : 1) + 2;
 	if (blk_alloc(b, n) < 0 || (b->buf = (char*)malloc(tot + 1)) == 0) { fq_block_free(b); return -1; }

@@ -35,6 +35,7 @@ def L():
     lib.bseq_read.restype = C.POINTER(Bseq1)
     lib.bseq_read.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]
     lib.bseq_close.argtypes = [C.c_void_p]
+    lib.bseq_at_eof.argtypes = [C.c_void_p]
     lib.fq_open.restype = C.c_void_p
     lib.fq_open.argtypes = [C.c_char_p, C.c_int]
     lib.fq_next.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(Block)]
@@ -51,7 +52,9 @@ def read_slow(L, path, keep_comment):
         n = C.c_int(0)
         seqs = L.bseq_read(f, 1000, keep_comment, C.byref(n))
         if not seqs or n.value == 0:
-            break
+            if L.bseq_at_eof(f):
+                break
+            continue  # the batch ended at a record with a wrong quality length (kseq's -2): reading goes on behind it
         for i in range(n.value):
             s = seqs[i]
             out.append((s.name, s.comment, s.seq, s.qual))
@@ -200,3 +203,74 @@ def test_writer_with_records_left_out_of_the_batch(L, tmp_path, refine):
     L.fq_flat_free(C.byref(flat))
     L.fq_block_free(C.byref(b))
     L.fq_close(f)
+
+
+def mutate(rng, base: bytearray) -> bytes:
+    for _ in range(rng.randint(0, 6)):
+        if not base:
+            break
+        k = rng.randint(0, len(base) - 1)
+        op = rng.randint(0, 5)
+        if op == 0:
+            base[k:k + 1] = b""
+        elif op == 1:
+            base[k:k] = rng.choice([b"\n", b"@", b"+", b">", b"\r", b" ", b"\n\n", b"\t"])
+        elif op == 2:
+            base[k] = rng.choice(b"@+>\nACGT !\r")
+        elif op == 3:
+            del base[k:k + rng.randint(1, 300)]
+        elif op == 4:
+            base[k:k] = base[max(0, k - rng.randint(1, 200)):k]
+        else:
+            base = base[:k]
+    return bytes(base)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_fuzz_block_reader_equals_record_reader(L, tmp_path, seed):
+    """Randomly damaged FASTQ (deleted / inserted / duplicated stretches, stray '@' '+' '>' CR and blank lines,
+    truncation): whatever the tolerant reader makes of it, the block reader delivers the same records."""
+    rng = random.Random(seed)
+    p = str(tmp_path / "f.fq")
+    for it in range(60):
+        data = mutate(rng, bytearray(rand_fastq(rng.randint(1, 300), rng.randint(0, 1 << 30), comments=rng.choice([0, 0.3]))))
+        with open(p, "wb") as f:
+            f.write(data)
+        for keep in (0, 1):
+            want = read_slow(L, p, keep)
+            for target in (4096, 20_000, 1 << 22):
+                got, _ = read_fast(L, p, keep, target, threads=rng.choice([1, 3]))
+                assert got == want, (seed, it, keep, target)
+
+
+REF_LIB = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libbfcref.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_LIB), reason="oracle/_ref (the unmodified reference, built where /root/reference exists) is absent")
+@pytest.mark.parametrize("seed", [11, 12])
+def test_fuzz_record_reader_equals_the_reference_reader(L, tmp_path, seed):
+    """csrc/bseq.c against the UNMODIFIED reference's bseq_read (kseq.h underneath) on the same damaged inputs, one
+    batch each: same records, same stops, same sticky comments."""
+    R = C.CDLL(REF_LIB)
+    R.bseq_open.restype = C.c_void_p
+    R.bseq_open.argtypes = [C.c_char_p]
+    R.bseq_read.restype = C.POINTER(Bseq1)
+    R.bseq_read.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    R.bseq_close.argtypes = [C.c_void_p]
+
+    def one_batch(lib, path, keep):
+        f = lib.bseq_open(path.encode())
+        n = C.c_int(0)
+        seqs = lib.bseq_read(f, 1 << 30, keep, C.byref(n))
+        out = [(seqs[i].name, seqs[i].comment, seqs[i].seq, seqs[i].qual) for i in range(n.value)]
+        lib.bseq_close(f)
+        return out
+
+    rng = random.Random(seed)
+    p = str(tmp_path / "f.fq")
+    for it in range(150):
+        data = mutate(rng, bytearray(rand_fastq(rng.randint(1, 300), rng.randint(0, 1 << 30), comments=rng.choice([0, 0.3]))))
+        with open(p, "wb") as f:
+            f.write(data)
+        for keep in (0, 1):
+            assert one_batch(L, p, keep) == one_batch(R, p, keep), (seed, it, keep)
