@@ -122,6 +122,7 @@ def lib():
                                      C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Stats)]
     L.bfcg_bf_init_shard.restype = C.POINTER(BF)
     L.bfcg_bf_init_shard.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.bfcg_ch_set_shard.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.bfcg_ch_export_device.restype = C.c_uint64
     L.bfcg_ch_export_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.bfcg_ch_import_device.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]

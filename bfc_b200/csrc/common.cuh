@@ -106,6 +106,15 @@ struct bfc_ch_s {
 	uint64_t def_cap;
 	uint64_t prev_new;        // distinct keys added by the previous count window (growth estimate of the next one)
 	int have_prev;
+	// One shard of N (sharded counting): the owner bits of a k-mer are the top bits of its Bloom
+	// block index, which tab_region turns into the TOP own_bits bits of the region index -- so a shard only ever touches
+	// the regions whose top bits equal own_val, and only those 2^(l_pre - own_bits) regions are allocated.  When the
+	// geometry does not allow that (block index not a bit field of the sub-table index) the shard keeps every region and
+	// `skew` = N tells the growth policy that 1/N of them take all the keys.
+	int req_owners, req_owner; // what bfcg_ch_set_shard asked for (applied by bfcg_tab_align_to_filter, table empty)
+	int own_bits;
+	uint32_t own_val;
+	int skew;
 };
 
 // ------------------------------------------------------------------ device views
@@ -122,6 +131,7 @@ struct TabView {
 	unsigned long long *deferred;
 	unsigned long long def_cap;
 	int k, l_pre, rbits, rot;
+	uint32_t rmask;   // region index bits kept by this table (all l_pre of them unless it is a shard)
 };
 
 static inline BloomView bloom_view(const bfc_bf_t *b)
@@ -136,6 +146,7 @@ static inline TabView tab_view(const bfc_ch_s *c)
 	TabView v;
 	v.slots = c->slots, v.counters = c->counters, v.deferred = c->deferred, v.def_cap = c->def_cap;
 	v.k = c->k, v.l_pre = c->l_pre, v.rbits = c->rbits, v.rot = c->rot;
+	v.rmask = (1u << (c->l_pre - c->own_bits)) - 1;
 	return v;
 }
 
@@ -145,6 +156,10 @@ int bfcg_tab_reserve(bfc_ch_s *ch, uint64_t extra);
 int bfcg_tab_align_to_filter(bfc_ch_s *ch, int x);
 // re-apply inserts that found their region full (after growing); htab.cu
 int bfcg_tab_drain_deferred(bfc_ch_s *ch);
+// double the slots of every region
+int bfcg_tab_grow(bfc_ch_s *ch);
+// slots of the table (a shard holds 2^(l_pre - own_bits) regions)
+static inline uint64_t bfcg_tab_capacity(const bfc_ch_s *ch) { return 1ULL << (ch->l_pre - ch->own_bits + ch->rbits); }
 
 // the partitioned count path (count_part.cu); count.cu dispatches to it when it applies
 bool bfcg_count_part_usable(const bfc_opt_t *opt, int n_shift, int owner_bits);
@@ -256,6 +271,12 @@ __host__ __device__ __forceinline__ uint32_t tab_region_inv(int l_pre, int rot, 
 	return rot ? ((reg << rot) | (reg >> (l_pre - rot))) & ((1u << l_pre) - 1) : reg;
 }
 
+// first slot of the region of sub-table `sub` inside this table's allocation
+__device__ __forceinline__ unsigned long long *tab_region_ptr(const TabView &t, uint32_t sub)
+{
+	return t.slots + ((uint64_t)(tab_region(t.l_pre, t.rot, sub) & t.rmask) << t.rbits);
+}
+
 __device__ __forceinline__ uint64_t tab_mix(uint64_t key)
 {
 	key ^= key >> 29;
@@ -270,12 +291,13 @@ __device__ __forceinline__ uint64_t tab_mix(uint64_t key)
 // Probing: 4-slot (32-byte, one DRAM sector) buckets, linear over buckets inside the
 // key's region.  Returns 1 = new key stored, 0 = existing key updated, -1 = region
 // full (insert parked in the deferred list and re-applied after the table has grown).
-__device__ __forceinline__ int tab_upsert(const TabView &t, uint64_t y0, uint64_t y1, int is_high)
+template <bool PARK>
+__device__ __forceinline__ int tab_upsert_t(const TabView &t, uint64_t y0, uint64_t y1, int is_high)
 {
 	uint32_t sub; uint64_t key;
 	tab_subkey(t.k, t.l_pre, y0, y1, sub, key);
 	const uint64_t R = 1ULL << t.rbits;
-	unsigned long long *reg = t.slots + ((uint64_t)tab_region(t.l_pre, t.rot, sub) << t.rbits);
+	unsigned long long *reg = tab_region_ptr(t, sub);
 	uint64_t h = tab_mix(key) & (R - 1) & ~3ULL;
 	const unsigned long long fresh = key << 14 | (unsigned long long)(is_high ? 1 : 0) << 8 | 1ULL;
 	for (uint64_t n = 0; n < R; n += 4, h = (h + 4) & (R - 1)) {
@@ -304,19 +326,22 @@ __device__ __forceinline__ int tab_upsert(const TabView &t, uint64_t y0, uint64_
 			}
 		}
 	}
-	const unsigned long long idx = atomicAdd(t.counters + 1, 1ULL);
-	if (idx < t.def_cap) {
-		t.deferred[2 * idx] = y0 | (unsigned long long)(is_high ? 1 : 0) << 63;
-		t.deferred[2 * idx + 1] = y1;
+	if (PARK) {
+		const unsigned long long idx = atomicAdd(t.counters + 1, 1ULL);
+		if (idx < t.def_cap) {
+			t.deferred[2 * idx] = y0 | (unsigned long long)(is_high ? 1 : 0) << 63;
+			t.deferred[2 * idx + 1] = y1;
+		}
 	}
 	return -1;
 }
+__device__ __forceinline__ int tab_upsert(const TabView &t, uint64_t y0, uint64_t y1, int is_high) { return tab_upsert_t<true>(t, y0, y1, is_high); }
 
 // store a ready-made slot value (restore / rehash); the key must not be present yet
 __device__ __forceinline__ bool tab_put_raw(const TabView &t, uint32_t sub, unsigned long long slot)
 {
 	const uint64_t R = 1ULL << t.rbits;
-	unsigned long long *reg = t.slots + ((uint64_t)tab_region(t.l_pre, t.rot, sub) << t.rbits);
+	unsigned long long *reg = tab_region_ptr(t, sub);
 	uint64_t h = tab_mix(slot >> 14) & (R - 1) & ~3ULL;
 	for (uint64_t n = 0; n < R; ++n) {
 		const uint64_t i = (h + n) & (R - 1);
@@ -331,7 +356,7 @@ __device__ __forceinline__ int tab_get(const TabView &t, uint64_t y0, uint64_t y
 	uint32_t sub; uint64_t key;
 	tab_subkey(t.k, t.l_pre, y0, y1, sub, key);
 	const uint64_t R = 1ULL << t.rbits;
-	const unsigned long long *reg = t.slots + ((uint64_t)tab_region(t.l_pre, t.rot, sub) << t.rbits);
+	const unsigned long long *reg = tab_region_ptr(t, sub);
 	uint64_t h = tab_mix(key) & (R - 1) & ~3ULL;
 	for (uint64_t n = 0; n < R; n += 4, h = (h + 4) & (R - 1)) {
 		const ulonglong2 v01 = __ldg((const ulonglong2*)(reg + h));

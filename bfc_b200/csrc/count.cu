@@ -479,6 +479,7 @@ extern "C" int bfcg_count_records(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *
 		return bfcg_fail(__func__, "invalid arguments", cudaSuccess), BFCG_ERR_ARG;
 	if (n_rec == 0) return BFCG_OK;
 	if (bfcg_count_part_usable(opt, bf->n_shift, owner_bits)) return bfcg_count_part_records(opt, bf, bf_high, ch, n_rec, d_y0, d_y1, owner_bits, stats);
+	if (ch && (r = bfcg_tab_align_to_filter(ch, bf->n_shift - BFC_BLK_SHIFT)) != BFCG_OK) return r; // (settles a shard request)
 	const uint64_t sub = std::min<uint64_t>(sub_batch_positions(opt), 1ULL << 31);
 	const uint64_t rec_max = std::min<uint64_t>(sub, n_rec);
 	CountScratch sc;

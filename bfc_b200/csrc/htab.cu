@@ -9,11 +9,12 @@ static const uint64_t TAB_DEF_CAP = 1 << 20; // parked inserts per kernel before
 
 // ------------------------------------------------------------------ kernels
 
-__global__ void k_tab_rehash(const unsigned long long *old_slots, int old_rbits, int old_rot, uint64_t old_n, TabView nt, unsigned long long *fail)
+// reg_hi = the region index bits a shard leaves out (own_val << (l_pre - own_bits)), same for the old and the new table
+__global__ void k_tab_rehash(const unsigned long long *old_slots, int old_rbits, int old_rot, uint32_t reg_hi, uint64_t old_n, TabView nt, unsigned long long *fail)
 {
 	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < old_n; i += (uint64_t)gridDim.x * blockDim.x) {
 		const unsigned long long s = old_slots[i];
-		if (s && !tab_put_raw(nt, tab_region_inv(nt.l_pre, old_rot, (uint32_t)(i >> old_rbits)), s)) atomicAdd(fail, 1ULL);
+		if (s && !tab_put_raw(nt, tab_region_inv(nt.l_pre, old_rot, reg_hi | (uint32_t)(i >> old_rbits)), s)) atomicAdd(fail, 1ULL);
 	}
 }
 
@@ -72,14 +73,14 @@ __global__ void k_tab_hist(const unsigned long long *slots, uint64_t n, unsigned
 		if (s_h[i]) atomicAdd(hist + i, (unsigned long long)s_h[i]);
 }
 
-__global__ void k_tab_export(const unsigned long long *slots, int rbits, int l_pre, int rot, uint64_t n, uint32_t *sub, unsigned long long *key,
+__global__ void k_tab_export(const unsigned long long *slots, int rbits, int l_pre, int rot, uint32_t reg_hi, uint64_t n, uint32_t *sub, unsigned long long *key,
                              unsigned long long *cursor)
 {
 	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
 		const unsigned long long s = __ldg(slots + i);
 		if (s) {
 			const unsigned long long at = atomicAdd(cursor, 1ULL);
-			sub[at] = tab_region_inv(l_pre, rot, (uint32_t)(i >> rbits));
+			sub[at] = tab_region_inv(l_pre, rot, reg_hi | (uint32_t)(i >> rbits));
 			key[at] = s;
 		}
 	}
@@ -87,7 +88,8 @@ __global__ void k_tab_export(const unsigned long long *slots, int rbits, int l_p
 
 // ------------------------------------------------------------------ growth
 
-static inline uint64_t tab_capacity(const bfc_ch_s *ch) { return 1ULL << (ch->l_pre + ch->rbits); }
+static inline uint64_t tab_capacity(const bfc_ch_s *ch) { return bfcg_tab_capacity(ch); }
+static inline uint32_t tab_reg_hi(const bfc_ch_s *ch) { return ch->own_bits ? ch->own_val << (ch->l_pre - ch->own_bits) : 0; }
 
 static int tab_read_counters(const bfc_ch_s *ch, unsigned long long c[2])
 {
@@ -102,16 +104,16 @@ static int tab_resize(bfc_ch_s *ch, int new_rbits, int new_rot = -1)
 	if (new_rot < 0) new_rot = ch->rot;
 	BfcgRuntime &rt = bfcg_rt();
 	unsigned long long *ns = 0, *fail = ch->counters + 2, h_fail = 0; // own scratch word: callers may hold the arena
-	const uint64_t new_cap = 1ULL << (ch->l_pre + new_rbits);
+	const uint64_t new_cap = 1ULL << (ch->l_pre - ch->own_bits + new_rbits);
 	if (bfc_verbose >= 4)
-		fprintf(stderr, "[M::%s] growing the k-mer table: 2^%d -> 2^%d slots\n", __func__, ch->l_pre + ch->rbits, ch->l_pre + new_rbits);
+		fprintf(stderr, "[M::%s] growing the k-mer table: 2^%d -> 2^%d slots\n", __func__, ch->l_pre - ch->own_bits + ch->rbits, ch->l_pre - ch->own_bits + new_rbits);
 	if (cudaMalloc(&ns, new_cap * 8) != cudaSuccess)
 		return bfcg_fail(__func__, "cudaMalloc(larger k-mer table)", cudaErrorMemoryAllocation);
 	BFCG_CUDA(cudaMemsetAsync(ns, 0, new_cap * 8, rt.stream));
 	BFCG_CUDA(cudaMemsetAsync(fail, 0, 8, rt.stream));
 	TabView nt = tab_view(ch);
 	nt.slots = ns, nt.rbits = new_rbits, nt.rot = new_rot;
-	{ KTime kt(KT_TAB_REHASH); k_tab_rehash<<<rt.sm_count * 8, 256, 0, rt.stream>>>(ch->slots, ch->rbits, ch->rot, tab_capacity(ch), nt, fail); }
+	{ KTime kt(KT_TAB_REHASH); k_tab_rehash<<<rt.sm_count * 8, 256, 0, rt.stream>>>(ch->slots, ch->rbits, ch->rot, tab_reg_hi(ch), tab_capacity(ch), nt, fail); }
 	BFCG_LAUNCH_CHECK();
 	BFCG_CUDA(cudaMemcpyAsync(&h_fail, fail, 8, cudaMemcpyDeviceToHost, rt.stream));
 	BFCG_CUDA(cudaStreamSynchronize(rt.stream));
@@ -124,12 +126,37 @@ static int tab_resize(bfc_ch_s *ch, int new_rbits, int new_rot = -1)
 // The low x bits of y0 are the Bloom block index (when x <= k); sub-table index bit j is y0 bit j + k - l_pre
 // (htab.c:45-58; for k <= 32 and l_pre > k it is y0 bit j - (l_pre - k)).  Rotating the sub-table index right by the
 // number of its bits that lie below y0 bit x makes them the top bits of the region index.
+// A shard request (bfcg_ch_set_shard) is settled here, while the table is still empty: the owner bits are the top
+// owner_bits bits of the block index = y0 bits [x - owner_bits, x) = the top bits of the region index after the
+// rotation, provided they are sub-table bits at all (rot >= owner_bits).
 int bfcg_tab_align_to_filter(bfc_ch_s *ch, int x)
 {
 	int rot = x - (ch->k - ch->l_pre);
 	if (x > ch->k || rot <= 0 || rot >= ch->l_pre) rot = 0;
-	if (rot == ch->rot) return BFCG_OK;
-	if (bfc_ch_count(ch) == 0) { ch->rot = rot; return BFCG_OK; }
+	int own_bits = 0, skew = 1;
+	if (ch->req_owners > 1) {
+		int ob = 0;
+		while ((1 << ob) < ch->req_owners) ++ob;
+		if (rot >= ob) own_bits = ob;
+		else skew = ch->req_owners;
+	}
+	if (rot == ch->rot && own_bits == ch->own_bits) { ch->skew = skew; return BFCG_OK; }
+	if (bfc_ch_count(ch) == 0) {
+		if (own_bits != ch->own_bits) { // another number of regions: a fresh, empty array
+			BfcgRuntime &rt = bfcg_rt();
+			unsigned long long *ns = 0;
+			const uint64_t cap = 1ULL << (ch->l_pre - own_bits + ch->rbits);
+			if (cudaMalloc(&ns, cap * 8) != cudaSuccess) return bfcg_fail(__func__, "cudaMalloc(k-mer table)", cudaErrorMemoryAllocation);
+			BFCG_CUDA(cudaMemsetAsync(ns, 0, cap * 8, rt.stream));
+			BFCG_CUDA(cudaStreamSynchronize(rt.stream));
+			cudaFree(ch->slots);
+			ch->slots = ns;
+		}
+		ch->rot = rot, ch->own_bits = own_bits, ch->own_val = own_bits ? (uint32_t)ch->req_owner : 0, ch->skew = skew;
+		return BFCG_OK;
+	}
+	if (own_bits != ch->own_bits) return bfcg_fail(__func__, "the shard geometry of a non-empty k-mer table cannot change", cudaSuccess);
+	ch->skew = skew;
 	return tab_resize(ch, ch->rbits, rot);
 }
 
@@ -139,9 +166,12 @@ int bfcg_tab_reserve(bfc_ch_s *ch, uint64_t extra)
 	int r;
 	if ((r = tab_read_counters(ch, c)) != BFCG_OK) return r;
 	int rbits = ch->rbits;
-	while (2 * (c[0] + extra) > (1ULL << (ch->l_pre + rbits))) ++rbits;
+	const uint64_t skew = ch->skew > 1 ? (uint64_t)ch->skew : 1; // a shard that keeps every region fills 1/skew of them
+	while (2 * (c[0] + extra) * skew > (1ULL << (ch->l_pre - ch->own_bits + rbits))) ++rbits;
 	return rbits != ch->rbits ? tab_resize(ch, rbits) : BFCG_OK;
 }
+
+int bfcg_tab_grow(bfc_ch_s *ch) { return tab_resize(ch, ch->rbits + 1); }
 
 int bfcg_tab_drain_deferred(bfc_ch_s *ch)
 {
@@ -190,7 +220,8 @@ bfc_ch_t *bfc_ch_init(int k, int l_pre)
 	if (bfcg_rt_init() != BFCG_OK) return 0;
 	BfcgRuntime &rt = bfcg_rt();
 	bfc_ch_s *ch = (bfc_ch_s*)calloc(1, sizeof(bfc_ch_s));
-	ch->k = k, ch->l_pre = l_pre, ch->rbits = TAB_MIN_RBITS, ch->def_cap = TAB_DEF_CAP;
+	ch->k = k, ch->l_pre = l_pre, ch->rbits = TAB_MIN_RBITS, ch->def_cap = TAB_DEF_CAP, ch->skew = 1;
+	{ const char *dc = getenv("BFC_B200_TAB_DEFCAP"); if (dc && atoll(dc) >= 16) ch->def_cap = (uint64_t)atoll(dc); } // tests: a small parking list
 	const char *e = getenv("BFC_B200_TAB_LOG2"); // optional pre-sizing: log2(slots)
 	if (e && atoi(e) - l_pre > ch->rbits && atoi(e) <= 36) ch->rbits = atoi(e) - l_pre;
 	if (cudaMalloc(&ch->slots, tab_capacity(ch) * 8) != cudaSuccess ||
@@ -303,7 +334,17 @@ int bfc_ch_hist(const bfc_ch_t *ch, uint64_t cnt[256], uint64_t high[64])
 
 int bfc_ch_get_k(const bfc_ch_t *ch) { return ch->k; }
 int bfcg_ch_l_pre(const bfc_ch_t *ch) { return ch->l_pre; }
-int bfcg_ch_capacity_log2(const bfc_ch_t *ch) { return ch->l_pre + ch->rbits; }
+int bfcg_ch_capacity_log2(const bfc_ch_t *ch) { return ch->l_pre - ch->own_bits + ch->rbits; }
+
+// this table is shard `owner` of `n_owners` (1, 2, 4, 8) of a sharded count; must be called while it is empty
+int bfcg_ch_set_shard(bfc_ch_t *ch, int n_owners, int owner)
+{
+	if (!ch || n_owners < 1 || n_owners > 8 || (n_owners & (n_owners - 1)) || owner < 0 || owner >= n_owners)
+		return bfcg_fail(__func__, "invalid arguments", cudaSuccess), BFCG_ERR_ARG;
+	if (bfc_ch_count(ch) != 0) return bfcg_fail(__func__, "the table is not empty", cudaSuccess), BFCG_ERR_ARG;
+	ch->req_owners = n_owners, ch->req_owner = owner;
+	return BFCG_OK;
+}
 
 int bfcg_ch_clear(bfc_ch_t *ch)
 {
@@ -335,7 +376,7 @@ uint64_t bfcg_ch_export(const bfc_ch_t *ch, uint32_t *sub, uint64_t *key)
 	unsigned long long *d_key = (unsigned long long*)a, *cursor = (unsigned long long*)(a + n * 8);
 	uint32_t *d_sub = (uint32_t*)(a + n * 8 + 256);
 	cudaMemsetAsync(cursor, 0, 8, rt.stream);
-	k_tab_export<<<rt.sm_count * 8, 256, 0, rt.stream>>>(ch->slots, ch->rbits, ch->l_pre, ch->rot, tab_capacity(ch), d_sub, d_key, cursor);
+	k_tab_export<<<rt.sm_count * 8, 256, 0, rt.stream>>>(ch->slots, ch->rbits, ch->l_pre, ch->rot, tab_reg_hi(ch), tab_capacity(ch), d_sub, d_key, cursor);
 	++rt.n_launches;
 	std::vector<uint32_t> hs(n);
 	std::vector<uint64_t> hk(n);
@@ -361,7 +402,7 @@ uint64_t bfcg_ch_export_device(const bfc_ch_t *ch, uint32_t *d_sub, uint64_t *d_
 	if (d_sub == 0 || d_key == 0 || c[0] == 0) return c[0];
 	unsigned long long *cursor = ch->counters + 3;
 	cudaMemsetAsync(cursor, 0, 8, rt.stream);
-	k_tab_export<<<rt.sm_count * 8, 256, 0, rt.stream>>>(ch->slots, ch->rbits, ch->l_pre, ch->rot, tab_capacity(ch), d_sub, (unsigned long long*)d_key, cursor);
+	k_tab_export<<<rt.sm_count * 8, 256, 0, rt.stream>>>(ch->slots, ch->rbits, ch->l_pre, ch->rot, tab_reg_hi(ch), tab_capacity(ch), d_sub, (unsigned long long*)d_key, cursor);
 	++rt.n_launches;
 	if (cudaStreamSynchronize(rt.stream) != cudaSuccess) { bfcg_fail(__func__, "kernel", cudaGetLastError()); return 0; }
 	return c[0];
@@ -427,14 +468,21 @@ bfc_ch_t *bfc_ch_restore(const char *fn)
 	if (ch == 0 || (int)t[1] != ch->l_pre) { fclose(fp); bfc_ch_destroy(ch); return 0; }
 	std::vector<uint32_t> sub;
 	std::vector<uint64_t> key;
+	bool whole = true; // a short read anywhere = a truncated or corrupt dump: no table (the reference asserts, htab.c:161-170)
 	for (uint32_t s = 0; s < 1u << ch->l_pre; ++s) {
-		if (fread(t, 4, 2, fp) != 2) break;
+		if (fread(t, 4, 2, fp) != 2) { whole = false; break; }
 		const size_t at = key.size();
+		if (t[1] > t[0] || at + t[1] > (1ULL << 40)) { whole = false; break; } // more keys than buckets
 		key.resize(at + t[1]);
 		sub.resize(at + t[1], s);
-		if (t[1] && fread(&key[at], 8, t[1], fp) != t[1]) break;
+		if (t[1] && fread(&key[at], 8, t[1], fp) != t[1]) { whole = false; break; }
 	}
 	fclose(fp);
+	if (!whole) {
+		fprintf(stderr, "[E::%s] '%s' is truncated or not a k-mer table dump\n", __func__, fn);
+		bfc_ch_destroy(ch);
+		return 0;
+	}
 	const uint64_t n = key.size();
 	BfcgRuntime &rt = bfcg_rt();
 	if (n) {

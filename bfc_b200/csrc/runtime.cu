@@ -15,10 +15,20 @@ int bfcg_fail(const char *func, const char *what, cudaError_t e)
 	return e == cudaErrorMemoryAllocation ? BFCG_ERR_NOMEM : BFCG_ERR_CUDA;
 }
 
+// Every public entry point comes through here.  The GPU steps of bfc_count / bfc_correct run on kt_pipeline worker
+// threads, and a host thread's current CUDA device defaults to 0: make the engine's device current on whichever thread
+// calls (once per thread).
+static thread_local int tl_dev = -1;
+
 int bfcg_rt_init()
 {
+	if (g_rt.ready && tl_dev == g_rt.dev) return BFCG_OK;
 	std::lock_guard<std::mutex> lock(g_rt_mutex);
-	if (g_rt.ready) return BFCG_OK;
+	if (g_rt.ready) {
+		BFCG_CUDA(cudaSetDevice(g_rt.dev));
+		tl_dev = g_rt.dev;
+		return BFCG_OK;
+	}
 	int n = 0;
 	cudaError_t e = cudaGetDeviceCount(&n);
 	if (e != cudaSuccess || n == 0)
@@ -48,6 +58,7 @@ int bfcg_rt_init()
 		BFCG_CUDA(cudaEventCreateWithFlags(&g_rt.ev_out[i], cudaEventDisableTiming));
 	}
 	g_rt.ready = true;
+	tl_dev = g_rt.dev;
 	return BFCG_OK;
 }
 

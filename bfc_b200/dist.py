@@ -140,7 +140,7 @@ class ShardedCount:
 class CudaBackend:
     """The C ABI of libbfc_b200.so (include/bfc_b200.h) behind the ShardedCount backend interface."""
 
-    def __init__(self, opt, world: int, device_index: int = 0):
+    def __init__(self, opt, world: int, device_index: int = 0, rank: int | None = None):
         from . import api
         self.api, self.L, self.opt, self.world = api, api.lib(), opt, world
         self.filter_mode = bool(opt.filter_mode)
@@ -152,6 +152,8 @@ class CudaBackend:
         self.ch = None if self.filter_mode else L.bfc_ch_init(opt.k, opt.l_pre)
         if not self.bf or (self.filter_mode and not self.bf_high) or (not self.filter_mode and not self.ch):
             raise api.BfcError("allocation failed: " + L.bfcg_last_error().decode())
+        if self.ch and world > 1 and rank is not None:  # only 1/world of the sub-table regions can receive keys
+            self._check(L.bfcg_ch_set_shard(self.ch, world, rank), "bfcg_ch_set_shard")
         self.full_ch = None          # complete table after gather()
         self.full_bf_high = None     # complete bf_high (torch tensor keeps the memory) after gather()
         self._bf_high_view = None

@@ -119,6 +119,9 @@ int bfcg_count_records(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, bf
 int bfcg_count_record_runs(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, bfc_ch_t *ch, int n_runs, const uint64_t *run_counts,
                            uint64_t *d_y0, uint64_t *d_y1, int n_owners, bfcg_stats_t *stats);
 bfc_bf_t *bfcg_bf_init_shard(int n_shift, int n_hashes, int n_owners);   /* 2^(n_shift-3) / n_owners bytes */
+/* declare an EMPTY table to be shard `owner` of `n_owners`: it then allocates (and sizes itself for) only the 1/n_owners
+ * of the sub-table regions its k-mers can fall into (the owner bits are sub-table index bits, htab.c:45-58) */
+int bfcg_ch_set_shard(bfc_ch_t *ch, int n_owners, int owner);
 /* table exchange: entries as (sub-table index, key50<<14 | val14) in DEVICE arrays, unsorted; returns n
  * (pass NULLs to get n); import adds entries that are not present yet (shards are disjoint) */
 uint64_t bfcg_ch_export_device(const bfc_ch_t *ch, uint32_t *d_sub, uint64_t *d_key);

@@ -29,7 +29,7 @@ def _worker(rank, world, port, k, b, trim, chunk, out):
         seq, qual = synth.make_reads(genome, 24000, 120, k + b)
         n = len(seq)
         opt = bfc_b200.make_opt(k=k, bf_shift=b, filter_mode=1 if trim else 0)
-        be = CudaBackend(opt, world, rank)
+        be = CudaBackend(opt, world, rank, rank=rank)
         sc = ShardedCount(be, rank, world)
         mine = []
         for lo in range(0, n, chunk):

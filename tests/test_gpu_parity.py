@@ -223,7 +223,7 @@ def test_sharded_count_kernels_emulated_on_one_gpu(bfc, monkeypatch, world, k, b
     N = len(off) - 1
     opt = bfc.make_opt(k=k, bf_shift=b, filter_mode=1 if trim else 0)
     o = orc.OracleRun(orc.make_opt(k=k, bf_shift=b, filter_mode=1 if trim else 0))
-    ranks = [CudaBackend(opt, world) for _ in range(world)]
+    ranks = [CudaBackend(opt, world, 0, rank=r) for r in range(world)]
     try:
         o.count(seq, qual, off)
         chunk = 5000
