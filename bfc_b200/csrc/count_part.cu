@@ -193,6 +193,38 @@ __device__ __forceinline__ int bloom_test_set_smem(uint32_t *w, int h1, int h2, 
 	return cnt;
 }
 
+// ---- the slice travels as ONE bulk copy each way (TMA engine, SASS UBLKCP): no per-thread LDG / STG loop, the LSU and
+// the registers stay with the replay
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void bulk_load_slice(uint32_t *s_dst, const uint32_t *g_src, uint32_t bytes, uint64_t *mbar)
+{
+	if (threadIdx.x == 0) {
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(mbar)));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(mbar)), "r"(bytes) : "memory");
+		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		             :: "r"(smem_u32(s_dst)), "l"(g_src), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
+	}
+}
+
+__device__ __forceinline__ void bulk_load_wait(uint64_t *mbar)
+{
+	asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+	             :: "r"(smem_u32(mbar)) : "memory");
+}
+
+// after a __syncthreads(): the CTA's writes to the slice become visible to the async proxy, one thread sends it
+__device__ __forceinline__ void bulk_store_slice(uint32_t *g_dst, const uint32_t *s_src, uint32_t bytes)
+{
+	if (threadIdx.x == 0) {
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+		asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(g_dst), "r"(smem_u32(s_src)), "r"(bytes) : "memory");
+		asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+		asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // shared memory must outlive the read
+	}
+}
+
 // One round = CP_THREADS consecutive records of the partition.  Records whose bits are all set pass whatever the
 // order and write nothing.  Of the others, the EARLIEST of every block (shared-memory atomicMin claim) applies the
 // reference's test-then-set at once -- different blocks, disjoint words.  The few that lost a claim (a later
@@ -202,7 +234,8 @@ __device__ __forceinline__ int bloom_test_set_smem(uint32_t *w, int h1, int h2, 
 template <typename VT, bool PACKED>
 __global__ void __launch_bounds__(CP_THREADS, CP_MIN_CTAS) k_count_part(PartParams p)
 {
-	extern __shared__ __align__(16) uint32_t s_w[];  // the partition's slice of the filter: blocks_per_part x 16 words
+	extern __shared__ __align__(128) uint32_t s_w[]; // the partition's slice of the filter: blocks_per_part x 16 words
+	__shared__ __align__(8) uint64_t s_mbar;
 	__shared__ uint32_t s_claim[1 << CP_SLOG2];      // per block: lowest thread with a pending occurrence this round
 	__shared__ uint32_t s_info[CP_THREADS];          // losers: block << 18 | h1 << 9 | h2
 	__shared__ uint32_t s_lose[CP_THREADS / 32], s_res[CP_THREADS / 32]; // bitmaps over the round's threads
@@ -213,21 +246,22 @@ __global__ void __launch_bounds__(CP_THREADS, CP_MIN_CTAS) k_count_part(PartPara
 		for (uint32_t r = 0; r < p.n_runs; ++r) any |= __ldg(p.start + (uint64_t)r * p.n_parts + part) < __ldg(p.end + (uint64_t)r * p.n_parts + part);
 		if (!any) return;
 	}
-	uint4 *const g4 = (uint4*)(p.bf.w + ((uint64_t)part * nb << 4));
-	uint4 *const s4 = (uint4*)s_w;
-	for (uint32_t i = tid; i < nb * 4; i += CP_THREADS) s4[i] = __ldcs(g4 + i);
+	uint32_t *const g_slice = p.bf.w + ((uint64_t)part * nb << 4);
+	bulk_load_slice(s_w, g_slice, nb * CP_BLK_BYTES, &s_mbar);
 	for (uint32_t i = tid; i < nb; i += CP_THREADS) s_claim[i] = ~0u;
 	if (tid < CP_THREADS / 32) s_lose[tid] = 0, s_res[tid] = 0;
 	const int H = p.bf.n_hashes;
 	const bool mark = p.bf_high.w == 0;
 	VT *const vals = (VT*)p.val;
 	unsigned long long n_k = 0, n_pass = 0, n_wait = 0;
-	__syncthreads();
+	__syncthreads();          // (the barrier's initialisation is visible to every thread)
+	bool loaded = false;
 	for (uint32_t run = 0; run < p.n_runs; ++run) {
 		const uint64_t beg = __ldg(p.start + (uint64_t)run * p.n_parts + part), end = __ldg(p.end + (uint64_t)run * p.n_parts + part);
 		unsigned long long key = 0;
 		VT val = R::mark();
 		if (beg + tid < end) val = __ldg(vals + beg + tid), key = __ldg(p.key + beg + tid);
+		if (!loaded) { bulk_load_wait(&s_mbar); loaded = true; } // the first records were requested while the slice travelled
 		for (uint64_t base = beg; base < end; base += CP_THREADS) {
 			const unsigned long long ckey = key;
 			const VT cval = val;
@@ -293,7 +327,7 @@ __global__ void __launch_bounds__(CP_THREADS, CP_MIN_CTAS) k_count_part(PartPara
 		}
 	}
 	__syncthreads();
-	for (uint32_t i = tid; i < nb * 4; i += CP_THREADS) __stcs(g4 + i, s4[i]);
+	bulk_store_slice(g_slice, s_w, nb * CP_BLK_BYTES);
 	block_add(p.ctr + 1, n_k);
 	block_add(p.ctr + 2, n_pass);
 	block_add(p.ctr + 3, n_wait);

@@ -208,7 +208,85 @@ def test_cli_matches_reference_golden(bfc, tmp_path):
 
 
 @pytest.mark.parametrize("path", ["part", "probe"])
-@pytest.mark.parametrize("world,k,b,trim", [(4, 31, 22, False), (2, 33, 20, True), (8, 55, 24, False), (2, 33, 30, False)])
+@pytest.mark.parametrize("b", [12, 20])
+def test_table_grows_when_regions_fill(bfc, monkeypatch, b, path):
+    """A saturated (too small) first filter lets nearly every occurrence through, so a window adds far more keys than
+    the growth estimate reserved and whole table regions fill up: the inserts that found no room are applied again
+    after the table has grown, however many there are (the reference only slows down here).  The parking list of the
+    probe path is cut to 16 entries to make sure nothing depends on its size."""
+    monkeypatch.setenv("BFC_B200_COUNT", path)
+    monkeypatch.setenv("BFC_B200_TAB_DEFCAP", "16")
+    monkeypatch.setenv("BFC_B200_COUNT_WINDOW", str(1 << 19))
+    monkeypatch.setenv("BFC_B200_SUBBATCH", str(1 << 19))
+    seq, qual, off = synth_batch(400000, 30000, 100, seed=b, repeat=0.0)
+    o = orc.OracleRun(orc.make_opt(k=31, bf_shift=b))
+    e = bfc.Engine(bfc.make_opt(k=31, bf_shift=b))
+    try:
+        o.count(seq, qual, off)
+        e.count(seq, qual, off)
+        assert np.array_equal(e.bloom_bytes(), o.bloom_bytes())
+        assert int(e.stats.n_pass) == int(o.stats[1])
+        so, ko = o.table()
+        se, ke = e.table()
+        assert len(ke) == e.n_distinct() > 100000
+        assert np.array_equal(se, so) and np.array_equal(ke, ko)
+    finally:
+        e.close()
+        o.close()
+
+
+def test_truncated_dump_is_rejected(bfc, tmp_path):
+    """bfc_ch_restore on a dump cut short returns NULL (the reference asserts, htab.c:161-170) instead of a partial table."""
+    seq, qual, off = synth_batch(20000, 4000, 100, seed=3, repeat=0.0)
+    e = bfc.Engine(bfc.make_opt(k=31, bf_shift=22))
+    L = bfc.lib()
+    try:
+        e.count(seq, qual, off)
+        full = tmp_path / "full.dump"
+        assert L.bfc_ch_dump(e.ch, str(full).encode()) == 0
+        raw = full.read_bytes()
+        ch = L.bfc_ch_restore(str(full).encode())
+        assert ch and int(L.bfc_ch_count(ch)) == e.n_distinct()
+        L.bfc_ch_destroy(ch)
+        for cut in (4, len(raw) // 2, len(raw) - 8):
+            part = tmp_path / f"cut{cut}.dump"
+            part.write_bytes(raw[:cut])
+            assert not L.bfc_ch_restore(str(part).encode())
+    finally:
+        e.close()
+
+
+def test_reference_accepts_gpu_dump(bfc, tmp_path):
+    """A table counted on the GPU and dumped by this library is read back by the UNMODIFIED reference: `bfc -r dump`
+    corrects to the reference's own golden output, and hash2cnt (hash2cnt.c:37-64) reports the same number of keys."""
+    import subprocess
+    ref = os.path.join(orc.ROOT, "oracle", "_ref")
+    if not os.path.exists(os.path.join(ref, "bfc")):
+        pytest.skip("oracle/_ref is not built on this box")
+    exe = os.path.join(os.path.dirname(bfc.lib_path()), "bfc")
+    for name in ("k31_edge", "k33_rep"):
+        c = Case(name)
+        fq = tmp_path / (name + ".fq")
+        fq.write_bytes(c.fastq)
+        args = ["-k", str(c.meta["k"]), "-b", str(c.meta["b"])] + c.meta["extra_args"]
+        dump = tmp_path / (name + ".dump")
+        subprocess.run([exe] + args + ["-E", "-d", str(dump), str(fq)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True)
+        out = subprocess.run([os.path.join(ref, "bfc")] + args + ["-t1", "-r", str(dump), str(fq)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True).stdout
+        assert out == c.corrected
+        # hash2cnt -h: the count / high-count histograms of the dump = bfc_ch_hist of the reference's own table
+        h = subprocess.run([os.path.join(ref, "hash2cnt"), "-h", str(dump)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True).stdout
+        rows = [ln.split() for ln in h.decode().splitlines()]
+        cnt = np.array([int(r[1]) for r in rows], dtype=np.uint64)
+        high = np.array([int(r[2]) for r in rows[:64]], dtype=np.uint64)
+        assert np.array_equal(cnt, np.bincount((c.key & 0xff).astype(np.int64), minlength=256).astype(np.uint64))
+        assert np.array_equal(high, np.bincount((c.key >> 8 & 0x3f).astype(np.int64), minlength=64).astype(np.uint64))
+        # hash2cnt's default listing inverts the hash back to k-mer strings (k <= 37): one line per key
+        lst = subprocess.run([os.path.join(ref, "hash2cnt"), str(dump)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True).stdout
+        assert lst.count(b"\n") == len(c.key)
+
+
+@pytest.mark.parametrize("path", ["part", "probe"])
+@pytest.mark.parametrize("world,k,b,trim", [(4, 31, 22, False), (2, 33, 20, True), (8, 55, 24, False), (2, 33, 30, False), (8, 33, 26, False)])
 def test_sharded_count_kernels_emulated_on_one_gpu(bfc, monkeypatch, world, k, b, trim, path):
     """The sharded count path (bfcg_enum_records -> bucket exchange -> bfcg_count_records on 1/N filters) with
     the N ranks emulated one after the other on one GPU: the shards concatenate to the oracle's filter and the
@@ -219,6 +297,7 @@ def test_sharded_count_kernels_emulated_on_one_gpu(bfc, monkeypatch, world, k, b
     monkeypatch.setenv("BFC_B200_COUNT", path)
     monkeypatch.setenv("BFC_B200_SUBBATCH", str(1 << 17))
     monkeypatch.setenv("BFC_B200_COUNT_WINDOW", str(1 << 17))
+    monkeypatch.setenv("BFC_B200_TAB_DEFCAP", "64")  # (round 1's N = 8 failure: a shard's keys fall into 1/N of the regions)
     seq, qual, off = synth_batch(60000, 16000, 120, seed=k + world, repeat=0.2)
     N = len(off) - 1
     opt = bfc.make_opt(k=k, bf_shift=b, filter_mode=1 if trim else 0)

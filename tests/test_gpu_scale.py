@@ -77,3 +77,83 @@ def test_count_paths_and_batch_kinds_agree_at_scale(monkeypatch):
             e.close()
         for p in (d_gen, d_seq, d_qual, d_off):
             L.bfcg_dev_free(p)
+
+
+def test_eight_shards_at_full_filter_size():
+    """Round 1's N = 8 failure, reproduced on one GPU: a shard of 8 receives all its keys in 1/8 of the table's
+    sub-table regions (the owner bits are sub-table index bits), so a table sized for uniform use of every region
+    overflowed at the first 16 M-read chunk of the bench (k = 33, Bloom 2^37 bits).  Here the 8 ranks of one such chunk
+    are run one after the other on one GPU through the same calls bench.py makes (bfcg_enum_records -> exchange ->
+    bfcg_count_record_runs on 1/8 filters and shard tables); the union of the shard tables must equal the table of
+    the single-GPU count of the same reads, and the shard filters its filter."""
+    import torch
+    import bfc_b200
+    from bfc_b200 import api
+    from bfc_b200.dist import CudaBackend, piece_bounds
+    L = api.lib()
+    world, n, k, b = 8, 16_000_000, 33, 37
+    RB = L_READ + 1
+    G = n * L_READ // 30
+    nb = n * RB
+    d_gen, d_seq, d_qual, d_off = L.bfcg_dev_alloc(G), L.bfcg_dev_alloc(nb), L.bfcg_dev_alloc(nb), L.bfcg_dev_alloc(8 * (n + 1))
+    assert d_gen and d_seq and d_qual and d_off
+    assert L.bfcg_synth_genome(d_gen, G, 11) == 0
+    assert L.bfcg_synth_reads(d_gen, G, 11, 0, n, L_READ, 0.01, 2e-4, d_seq, d_qual, d_off) == 0
+    opt = bfc_b200.make_opt(k=k, bf_shift=b)
+    ranks = [CudaBackend(opt, world, 0, rank=r) for r in range(world)]
+    single = None
+    try:
+        sent = []
+        for r in range(world):
+            p0, p1 = piece_bounds(0, n, r, world)
+            pb = api.Batch()
+            pb.n_reads, pb.n_bytes, pb.where = p1 - p0, (p1 - p0) * RB, api.DEVICE
+            pb.off = C.cast(d_off, api.u64p)
+            pb.seq, pb.qual = C.cast(d_seq + p0 * RB, api.u8p), C.cast(d_qual + p0 * RB, api.u8p)
+            y0, y1, counts = ranks[r].enum_records(pb, world)
+            starts = np.concatenate([[0], np.cumsum(counts)])
+            sent.append([(y0[int(starts[d]):int(starts[d + 1])].clone(), y1[int(starts[d]):int(starts[d + 1])].clone()) for d in range(world)])
+            ranks[r]._buf.clear()
+        for d in range(world):
+            r0 = torch.cat([sent[r][d][0] for r in range(world)])
+            r1 = torch.cat([sent[r][d][1] for r in range(world)])
+            ranks[d].count_record_runs(r0, r1, [int(sent[r][d][0].numel()) for r in range(world)], world)
+            del r0, r1
+        del sent
+        parts = [ranks[r].export_table() for r in range(world)]
+        sizes = [int(s.numel()) for s, _ in parts]
+        assert min(sizes) > 0.8 * max(sizes) > 1_000_000       # every shard took its share of the keys ...
+        cap = [int(L.bfcg_ch_capacity_log2(ranks[r].ch)) for r in range(world)]
+        assert max(cap) <= 29, cap                              # ... in a table of its own size, not the whole job's
+        key = torch.cat([kk for _, kk in parts]); sub = torch.cat([ss for ss, _ in parts])
+        order = torch.argsort(key); key, sub = key[order], sub[order]
+        order = torch.argsort(sub, stable=True); key, sub = key[order].cpu().numpy(), sub[order].cpu().numpy()
+        bloom = torch.cat([ranks[r].bf_shard() for r in range(world)])
+        n_k, n_p = sum(int(r.stats.n_kmers) for r in ranks), sum(int(r.stats.n_pass) for r in ranks)
+        for r in ranks:
+            r.close()
+        ranks = []
+        del parts, order
+        single = bfc_b200.Engine(opt)
+        fb = api.Batch()
+        fb.n_reads, fb.n_bytes, fb.where = n, nb, api.DEVICE
+        fb.off, fb.seq, fb.qual = C.cast(d_off, api.u64p), C.cast(d_seq, api.u8p), C.cast(d_qual, api.u8p)
+        single.count_batch(fb)
+        assert int(single.stats.n_kmers) == n_k and int(single.stats.n_pass) == n_p
+        m = int(L.bfcg_ch_export_device(single.ch, None, None))
+        s1, k1 = torch.empty(m, dtype=torch.int32, device="cuda"), torch.empty(m, dtype=torch.int64, device="cuda")
+        assert int(L.bfcg_ch_export_device(single.ch, C.c_void_p(s1.data_ptr()), C.c_void_p(k1.data_ptr()))) == m == len(key)
+        order = torch.argsort(k1); k1, s1 = k1[order], s1[order]
+        order = torch.argsort(s1, stable=True); k1, s1 = k1[order].cpu().numpy(), s1[order].cpu().numpy()
+        assert np.array_equal(s1, sub) and np.array_equal(k1, key)
+        full = torch.empty(1 << (b - 3), dtype=torch.uint8, device="cuda")
+        cudart = C.CDLL("libcudart.so.12")
+        assert cudart.cudaMemcpy(C.c_void_p(full.data_ptr()), C.c_void_p(single.bf.contents.b), C.c_size_t(full.numel()), 3) == 0
+        assert bool(torch.equal(full, bloom))
+    finally:
+        for r in ranks:
+            r.close()
+        if single:
+            single.close()
+        for p in (d_gen, d_seq, d_qual, d_off):
+            L.bfcg_dev_free(p)
