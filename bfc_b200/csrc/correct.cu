@@ -818,6 +818,446 @@ __global__ void __launch_bounds__(EC_THREADS, EC_CTAS_PER_SM) k_ec_search(EcPara
 	block_add(P.ctr + 3, n_lookups);
 }
 
+// ------------------------------------------------------------------ K6b': the search, several lookups per round
+//
+// Same search, same results as k_ec_search; what changes is how often a thread has to come round to the lookup site.
+// k_ec_search makes ONE table lookup per pass of its stage loop, so a position that tries the three other bases costs
+// four passes, and the k-1 positions after an edit (whose k-mers contain the new base, so K5 never fetched them) cost
+// one pass each -- and a pass is expensive, because the 32 lanes of a warp are at 32 different places of the search.
+// Here a pass ends with up to EC_RQ lookups per thread:
+//   * the alternatives of a position (correct.c:318-333) are looked up together, and together with the position's own
+//     k-mer whenever the per-base flags alone already rule out "fixed" (correct.c:299-301);
+//   * while the path follows the read after an edit, the own k-mers of the NEXT positions are looked up ahead (they
+//     only depend on the read's bases) and kept in a 4-entry cache that stays valid for as long as the state keeps
+//     taking the read's base; any other base, or another state popped from the heap, drops it.
+// Every result is reduced at once to the three bits the search ever asks of a table value (occ_code).
+// The push / pop / heap logic below the step is k_ec_search's, statement for statement.
+
+#define EC_RQ 4
+#ifndef EC2_CTAS_PER_SM
+#define EC2_CTAS_PER_SM 5
+#endif
+
+// bit 0: in the table with cnt >= min_cov (solid); bit 1: (os & 0xff) >= min_cov + 1 with os = -1 counting as 255
+// (correct.c:299-300); bit 2: in the table with high count >= min_cov
+__device__ __forceinline__ uint32_t occ_code(int res, int min_cov)
+{
+	return (res >= 0 && (res & 0xff) >= min_cov ? 1u : 0u) | ((res & 0xff) >= min_cov + 1 ? 2u : 0u) | (res >= 0 && (res >> 8 & 0xff) >= min_cov ? 4u : 0u);
+}
+__device__ __forceinline__ int code_flags(uint32_t c) { return (c & 1 ? FL_SOL : 0) | (c & 2 ? FL_A : 0) | (c & 4 ? FL_H : 0); }
+
+enum { P2_NEWJOB = 0, P2_POP, P2_STEP, P2_RES, P2_FINISH, P2_EXIT };
+
+__global__ void __launch_bounds__(EC_THREADS, EC2_CTAS_PER_SM) k_ec_search2(EcParams P)
+{
+	const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	EcState *const pool = P.pool + slot * P.heap_cap;
+	__shared__ uint32_t s_hk[HK_SMEM][EC_THREADS];
+	KeyHeap heapk;
+	heapk.sm = &s_hk[0][threadIdx.x], heapk.gl = P.heapk + slot * P.heap_cap;
+	uint2 *const edits = P.edits + slot * P.edit_cap;
+	const int k = P.k;
+
+	// job context
+	int64_t job = 0, o = 0;
+	int jid = 0, n = 0, dir = 0, bp = -1, bb = 0;
+	bool memo_dir = false;
+	uint64_t ext = 0;
+	// search context (reference bfc_ec1dir locals)
+	EcState z;
+	int heap_n = 0, n_init = 0, n_edits = 0, max_heap = 0, n_fail = 0, n_paths = 0, rvl = -1;
+	int best_pen = INT_MAX, best_edit = -1, best_absent = 0;
+	bool top_valid = false, have_best = false;
+	int z_id = -1;
+	// step context
+	int cb = -1, cob = -1, ff = 0, osf = 0, other_ext = 0;
+	uint32_t cand = 0, alt_mask = 0;
+	bool has_c = false, fixed = false, own_pend = false, allowed = true;
+	// this round's requests and their results
+	uint32_t rq_cur = 0;                 // bases to try at the current position (appended to z.x)
+	uint32_t rq_done = 0;                // ... that have been looked up for this position so far
+	uint32_t rbits = 0;                  // occ_code of base b at the current position: bits 3b .. 3b+2
+	uint32_t ch_len = 0, ch_skip = 0, ch_bases = 0; // chain along the read from z.i: 2-bit bases; the first ch_skip are cached
+	// look-ahead cache: own k-mers of positions la_pos .. la_pos + 3 of the path that keeps taking the read's bases
+	int la_pos = INT_MIN;
+	uint32_t la_valid = 0, la_code = 0;  // entry j: bit j of la_valid, bits 3j .. 3j+2 of la_code
+	int pc = P2_NEWJOB;
+	unsigned long long n_lookups = 0;
+	z.tot_pen = z.i = z.n_absent = z.clean = 0, z.edit = -1;
+	z.x[0] = z.x[1] = z.x[2] = z.x[3] = 0;
+#pragma unroll
+	for (int t = 0; t < BFC_EC_HIST; ++t) z.ecpos[t] = -1;
+#pragma unroll
+	for (int t = 0; t < BFC_EC_HIST_HIGH; ++t) z.ecpos_high[t] = -1;
+
+	for (;;) {
+		bool yield = false;
+		{
+			bool job_done = false;
+			// ---------------- the lookups of the last round are in
+			if (pc == P2_RES) {
+				if (ch_len > ch_skip) la_valid = (1u << ch_len) - 1; // the chain's results went straight into the cache
+				pc = P2_FINISH;
+				if (own_pend) { // correct.c:299-301, 334-337 with the own k-mer's value
+					own_pend = false;
+					osf = code_flags(la_code & 7);
+					if (((ff & FL_Q) && (osf & FL_A) && (ff & FL_LC)) || (ff & FL_HC)) fixed = true;
+					cand |= (1u | ((osf & FL_SOL) ? 0u : 8u) | ((osf & FL_H) ? 0u : 16u)) << (8 * cb);
+					alt_mask = !fixed && allowed ? 0xFu & ~(1u << cb) : 0u;
+					const uint32_t need = alt_mask & ~rq_done;
+					if (need) { rq_cur = need, ch_len = ch_skip = 0; pc = P2_RES; yield = true; } // the flags left "fixed" open and the k-mer closed it: second round
+				}
+				if (pc == P2_FINISH) { // correct.c:320-333
+					const uint32_t ec = has_c && cb < 4 ? 1u : 0u;
+					for (uint32_t m = alt_mask; m; m &= m - 1) {
+						const int b = __ffs(m) - 1;
+						const uint32_t c = rbits >> (3 * b) & 7;
+						if (c & 1) {
+							cand |= (1u | ec << 1 | (ec && (ff & FL_Q) ? 4u : 0u) | ((c & 4) ? 0u : 16u)) << (8 * b);
+							++other_ext;
+						}
+					}
+				}
+			}
+			if (pc == P2_FINISH) {
+				const int n_added = (int)((cand & 1) + (cand >> 8 & 1) + (cand >> 16 & 1) + (cand >> 24 & 1));
+				pc = P2_POP;
+				if (!fixed && other_ext == 0) ++n_fail;
+				if (n_fail > n * 2) { rvl = -3; job_done = true; } // correct.c:342-347
+				else if (has_c || n_added == 1) {
+					uint32_t push = cand;
+					if (n_added > 1 && heap_n > P.max_heap) { // keep only the cheapest extension, first on ties (correct.c:349-355)
+						int min = INT_MAX, min_b = -1;
+#pragma unroll
+						for (int b = 0; b < 4; ++b)
+							if (cand >> (8 * b) & 1) {
+								const int t = cand_weight(P, cand >> (8 * b) & 0xff);
+								if (min > t) min = t, min_b = b;
+							}
+						push = cand & (0xffu << (8 * min_b));
+					}
+					const uint32_t pm = push & 0x01010101u;
+					if (pm != 0 && (pm & (pm - 1)) == 0) {
+						// a single successor replaces z in registers (see k_ec_search)
+						const int b = (__ffs(pm) - 1) >> 3;
+						const uint32_t c = push >> (8 * b) & 0xff;
+						const int zi = z.i;
+						if (has_c && b != cb) {
+							if (n_edits >= P.edit_cap) { rvl = EC_OVERFLOW; job_done = true; }
+							else {
+								const int f = dir ? n - 1 - zi : zi;
+								edits[n_edits] = make_uint2((uint32_t)z.edit, (uint32_t)f << 3 | (uint32_t)(dir ? 3 - b : b));
+								z.edit = n_edits++;
+							}
+						}
+						if (b != cb) la_valid = 0; // off the read: the k-mers looked up ahead are not this path's
+						z.i = zi + 1;
+						z.tot_pen += cand_weight(P, c);
+						if (c & 4) z.ecpos_high[1] = z.ecpos_high[0], z.ecpos_high[0] = zi;
+						if (c & 2) {
+#pragma unroll
+							for (int t = BFC_EC_HIST - 1; t > 0; --t) z.ecpos[t] = z.ecpos[t - 1];
+							z.ecpos[0] = zi;
+						}
+						z.clean = b == cob ? z.clean + 1 : 0;
+						if (has_c) z.n_absent += (int)(c >> 3 & 1);
+						bfc_kmer_append(k, z.x, b);
+						if (heap_n == 0) top_valid = true;
+						else if (heap_n <= 3 && (uint32_t)z.tot_pen <= hk_pen(heapk.get(0))) {
+							if (heap_n == 2) {
+								const uint32_t k0 = heapk.get(0), k1 = heapk.get(1);
+								if (hk_pen(k0) == hk_pen(k1)) heapk.set(0, k1), heapk.set(1, k0);
+							}
+							top_valid = true;
+						} else if (!job_done) {
+							uint32_t id;
+							if (heap_n < n_init) id = heapk.get(heap_n) & 0xfff;
+							else id = (uint32_t)n_init++;
+							heapk.set(heap_n++, (uint32_t)z.tot_pen << 12 | id);
+							heapk_up(heapk, heap_n);
+							z_id = (int)id;
+						}
+					} else {
+						for (int b = 0; b < 4 && !job_done; ++b) { // buf_update (correct.c:198-230), in base order
+							const uint32_t c = push >> (8 * b) & 0xff;
+							if (!(c & 1)) continue;
+							EcState s = z;
+							s.i = z.i + 1;
+							s.tot_pen = z.tot_pen + cand_weight(P, c);
+							if (c & 4) s.ecpos_high[0] = z.i, s.ecpos_high[1] = z.ecpos_high[0];
+							if (c & 2) {
+								s.ecpos[0] = z.i;
+#pragma unroll
+								for (int t = 1; t < BFC_EC_HIST; ++t) s.ecpos[t] = z.ecpos[t - 1];
+							}
+							s.clean = b == cob ? z.clean + 1 : 0;
+							if (has_c) {
+								s.n_absent = z.n_absent + (int)(c >> 3 & 1);
+								if (b != cb) {
+									if (n_edits >= P.edit_cap) { rvl = EC_OVERFLOW; job_done = true; break; }
+									const int f = dir ? n - 1 - z.i : z.i;
+									edits[n_edits] = make_uint2((uint32_t)z.edit, (uint32_t)f << 3 | (uint32_t)(dir ? 3 - b : b));
+									s.edit = n_edits++;
+								}
+							}
+							bfc_kmer_append(k, s.x, b);
+							uint32_t id;
+							if (heap_n < n_init) id = heapk.get(heap_n) & 0xfff;
+							else id = (uint32_t)n_init++;
+							pool[id] = s;
+							heapk.set(heap_n++, (uint32_t)s.tot_pen << 12 | id);
+							heapk_up(heapk, heap_n);
+						}
+					}
+				} else { // past the end of the read with 0 or >= 2 extensions: the path ends here (correct.c:360-372)
+					const int fin = z.tot_pen + (n_added == 0 ? P.w_absent * (P.max_end_ext - (z.i - n)) : 0);
+					if (fin < best_pen) best_pen = fin, best_edit = z.edit, best_absent = z.n_absent, have_best = true;
+					if (++n_paths == BFC_MAX_PATHS) job_done = true;
+				}
+			}
+			if (pc == P2_POP && !job_done) {
+				const int hs = heap_n + (top_valid ? 1 : 0);
+				max_heap = max_heap > 255 ? 255 : max_heap > hs ? max_heap : hs; // correct.c:276
+				if (hs == 0) { rvl = -2; job_done = true; }
+				else {
+					if (top_valid) top_valid = false;
+					else {
+						const uint32_t key = heapk.get(0);
+						--heap_n;
+						heapk.set(0, heapk.get(heap_n));
+						heapk.set(heap_n, key);
+						if (heap_n > 1) heapk_down(heapk, heap_n);
+						if ((int)(key & 0xfff) != z_id) {
+							if (z_id >= 0) pool[z_id] = z;
+							z = pool[key & 0xfff];
+							la_valid = 0; // another path
+						}
+						z_id = -1;
+					}
+					if (have_best && z.tot_pen > best_pen + P.max_path_diff) job_done = true; // correct.c:288
+					else if (z.i - n > P.max_end_ext) { // correct.c:289, 366-372; then the next pop
+						if (z.tot_pen < best_pen) best_pen = z.tot_pen, best_edit = z.edit, best_absent = z.n_absent, have_best = true;
+						if (++n_paths == BFC_MAX_PATHS) job_done = true;
+					} else pc = P2_STEP;
+				}
+			}
+			if (job_done) {
+				if (rvl == EC_OVERFLOW) P.overflow[atomicAdd(P.ctr, 1ULL)] = (uint32_t)jid;
+				else {
+					int rv = rvl;
+					if (n_paths > 0) { // buf_backtrack (correct.c:232-247): only the changed bases need recording
+						uint32_t *ev = (uint32_t*)(P.pl + (uint64_t)(dir ? PL_E1V : PL_E0V) * P.pl_words);
+						const uint64_t s32 = P.pl_words * 2;
+						for (int e = best_edit; e >= 0;) {
+							const uint2 ed = edits[e];
+							const uint64_t pos = (uint64_t)(o + (int64_t)(ed.y >> 3) + PL_PAD);
+							const uint32_t bit = 1u << (pos & 31), b = ed.y & 7;
+							uint32_t *w = ev + (pos >> 5);
+							atomicOr(w, bit);
+							if (b & 1) atomicOr(w + s32, bit);
+							if (b & 2) atomicOr(w + 2 * s32, bit);
+							e = (int)ed.x;
+						}
+						rv = best_absent;
+					}
+					P.res[jid] = make_int2(rv, max_heap);
+				}
+				pc = P2_NEWJOB;
+			}
+			if (pc == P2_NEWJOB) {
+				const unsigned am = __activemask(), ln = threadIdx.x & 31;
+				const int leader = __ffs(am) - 1;
+				unsigned long long first = 0;
+				if ((int)ln == leader) first = atomicAdd(P.ctr + 2, (unsigned long long)__popc(am));
+				first = __shfl_sync(am, first, leader);
+				job = (int64_t)(first + __popc(am & ((1u << ln) - 1)));
+				if (job >= P.n_jobs) pc = P2_EXIT;
+				else {
+					jid = P.redo ? (int)P.redo[job] : (int)job;
+					const int4 jr = P.jobs[jid];
+					if (jr.z >= 0) { // else: nothing to search for this read
+						dir = jid & 1;
+						o = (int64_t)(uint32_t)jr.x;
+						n = jr.y;
+						bp = jr.w >= 0 ? jr.w >> 2 : -1, bb = jr.w & 3;
+						memo_dir = dir == 0 || (k & 1) != 0; // the reverse-complement k-mer hashes like the forward one only for odd k (kmer.h:81)
+						ext = P.ext ? __ldg(P.ext + jid) : 0;
+						const int start = jr.z;
+						heap_n = n_init = n_edits = 0, max_heap = 0, n_fail = 0, n_paths = 0, rvl = -1, z_id = -1;
+						best_pen = INT_MAX, best_edit = -1, best_absent = 0, have_best = false;
+						la_valid = 0;
+						z.i = start + k - 1; // seed: the k-1 bases before position z.i (correct.c:260-267)
+						z.tot_pen = 0, z.edit = -1, z.n_absent = 0;
+#pragma unroll
+						for (int t = 0; t < BFC_EC_HIST; ++t) z.ecpos[t] = -1;
+#pragma unroll
+						for (int t = 0; t < BFC_EC_HIST_HIGH; ++t) z.ecpos_high[t] = -1;
+						if (start < 0 || z.i >= n) { P.res[jid] = make_int2(-1, 0); } // the reference asserts
+						else {
+							extract_kmer(P, o, n, dir, z.i - 1, k - 1, bp, bb, z.x);
+							z.clean = k - 1;
+							if (bp >= 0) { // bases after the rescue edit are the original ones
+								const int ib = dir ? n - 1 - bp : bp;
+								if (ib >= start && ib <= z.i - 1) z.clean = z.i - 1 - ib;
+							}
+							top_valid = true;
+							pc = P2_POP;
+						}
+					}
+				}
+			}
+			if (pc == P2_STEP) {
+				bool memo = false, own_known = false;
+				int f = 0;
+				for (;;) { // repeats only after stepping over decision-free bases
+					// Step over every decision-free base at once (see k_ec_search): possible while the path's last k-1
+					// bases are the read's own, which is what the jump planes were computed for
+					if (z.i < n && memo_dir && z.clean >= k - 1 && heap_n <= 3) {
+						const int fz = dir ? n - 1 - z.i : z.i;
+						int run;
+						if (!dir) { const uint64_t w = ~bits64(plane(P, PL_J0), o + fz); run = w ? __ffsll((long long)w) - 1 : 64; }
+						else { const uint64_t w = ~bits64(plane(P, PL_J1), o + fz - 63); run = w ? __clzll((long long)w) : 64; }
+						if (bp >= 0) { // the rescued base is not the original one: stop in front of it
+							const int ib = dir ? n - 1 - bp : bp;
+							if (ib >= z.i && ib < z.i + run) run = ib - z.i;
+						}
+						if (run > 0) {
+							const int hs = heap_n + 1;
+							max_heap = max_heap > 255 ? 255 : max_heap > hs ? max_heap : hs;
+							if (heap_n == 2 && (run & 1)) {
+								const uint32_t k0 = heapk.get(0), k1 = heapk.get(1);
+								if (hk_pen(k0) == hk_pen(k1)) heapk.set(0, k1), heapk.set(1, k0);
+							}
+							z.i += run, z.clean += run;
+							extract_kmer(P, o, n, dir, z.i - 1, k - 1, -1, 0, z.x);
+						}
+					}
+					has_c = z.i < n;
+					cb = cob = -1, ff = 0, osf = 0, allowed = true, memo = own_known = false;
+					if (!has_c) break;
+					f = dir ? n - 1 - z.i : z.i;
+					ff = __ldg(P.fl + o + f);
+					const int ob = FL_OB(ff), cur = f == bp ? bb : ob;
+					cb = dir ? comp_b(cur) : cur, cob = dir ? comp_b(ob) : ob;
+					if (cb > 3) break;
+					memo = memo_dir && z.clean >= k - 1 && cb == cob; // the read's own k-mer: K5 fetched it
+					if (memo) { osf = __ldg(P.fl + o + (dir ? f + k - 1 : f)) & (FL_SOL | FL_A | FL_H); own_known = true; break; }
+					// looked up ahead?  Entry 0 of the cache becomes this position.
+					const int d = z.i - la_pos;
+					if (la_valid && d > 0 && d < 4) la_valid >>= d, la_code >>= 3 * d;
+					else if (d != 0) la_valid = 0;
+					if (!la_valid) la_code = 0;
+					la_pos = z.i;
+					if (!(la_valid & 1)) break;
+					osf = code_flags(la_code & 7), own_known = true;
+					// A lone successor at no cost -- the base is "fixed" (correct.c:299-301) and its k-mer solid with a solid
+					// high count (correct.c:334-337) -- is pushed and popped right back, exactly as in a jump: only z moves
+					if (heap_n > 3 || !(osf & FL_SOL) || !(osf & FL_H) || !(((ff & FL_Q) && (osf & FL_A) && (ff & FL_LC)) || (ff & FL_HC))) break;
+					{
+						const int hs = heap_n + 1;
+						max_heap = max_heap > 255 ? 255 : max_heap > hs ? max_heap : hs;
+						if (heap_n == 2) {
+							const uint32_t k0 = heapk.get(0), k1 = heapk.get(1);
+							if (hk_pen(k0) == hk_pen(k1)) heapk.set(0, k1), heapk.set(1, k0);
+						}
+						z.clean = cb == cob ? z.clean + 1 : 0;
+						bfc_kmer_append(k, z.x, cb);
+						++z.i;
+					}
+				}
+				cand = 0, other_ext = 0, alt_mask = 0;
+				rq_cur = rq_done = rbits = 0, ch_len = ch_skip = 0, own_pend = false;
+				fixed = z.i > n; // correct.c:295 with end == n
+				pc = P2_FINISH;
+				if (has_c) {
+					// correct.c:316-317
+					if ((ff & FL_Q) && z.ecpos_high[BFC_EC_HIST_HIGH - 1] >= 0 && z.i - z.ecpos_high[BFC_EC_HIST_HIGH - 1] < P.win_multi_ec) allowed = false;
+					if (z.ecpos[BFC_EC_HIST - 1] >= 0 && z.i - z.ecpos[BFC_EC_HIST - 1] < P.win_multi_ec) allowed = false;
+					if (cb < 4) {
+						if (own_known) {
+							if (((ff & FL_Q) && (osf & FL_A) && (ff & FL_LC)) || (ff & FL_HC)) fixed = true; // correct.c:299-301
+							cand |= (1u | ((osf & FL_SOL) ? 0u : 8u) | ((osf & FL_H) ? 0u : 16u)) << (8 * cb); // correct.c:334-337
+							alt_mask = !fixed && allowed ? 0xFu & ~(1u << cb) : 0u;
+							rq_cur = alt_mask;
+						} else {
+							own_pend = true;
+							// the flags alone already rule out "fixed": the alternatives go along with the own k-mer
+							if (allowed && !(ff & FL_HC) && !((ff & FL_Q) && (ff & FL_LC))) rq_cur = 0xFu & ~(1u << cb);
+						}
+						if (!memo) {
+							// the chain: own k-mers of z.i, z.i + 1, ... for as long as the path would keep the read's bases,
+							// the next position is not K5's again, and this round has lookups to spare
+							const int c1 = cb == cob ? z.clean + 1 : 0;
+							int len = n - z.i < 4 ? n - z.i : 4;
+							if (memo_dir && k - c1 < len) len = k - c1 < 1 ? 1 : k - c1;
+							ch_skip = (uint32_t)__ffs(~la_valid) - 1; // cached entries come first
+							const int room = EC_RQ - __popc(rq_cur);
+							if ((int)ch_skip + room < len) len = (int)ch_skip + room;
+							ch_bases = (uint32_t)cb;
+							int m = 1;
+							for (; m < len; ++m) {
+								const int fj = dir ? f - m : f + m;
+								if (fj == bp) break;
+								const int obj = FL_OB(__ldg(P.fl + o + fj));
+								if (obj > 3) break;
+								ch_bases |= (uint32_t)(dir ? 3 - obj : obj) << (2 * m);
+							}
+							ch_len = (uint32_t)m;
+							if (ch_len <= ch_skip) ch_len = ch_skip = 0; // nothing new to look up
+						}
+					} else { // a non-ACGT read base has no own candidate
+						alt_mask = allowed ? 0xFu : 0u;
+						rq_cur = alt_mask;
+					}
+				} else if ((ext >> 63) && z.clean >= k - 1) {
+					// past the end with the read's own last k-1 bases: k_ec_ext made the four lookups of this position
+					const uint32_t m8 = (uint32_t)(ext >> (8 * (z.i - n))) & 0xff;
+#pragma unroll
+					for (int b = 0; b < 4; ++b)
+						if (m8 >> b & 1) cand |= (1u | ((m8 >> (4 + b) & 1) ? 16u : 0u)) << (8 * b), ++other_ext;
+					const uint32_t sol = m8 & 15;
+					cob = sol != 0 && (sol & (sol - 1)) == 0 ? __ffs(sol) - 1 : -1; // the base k_ec_ext went on with
+				} else { // past the end: all four bases (correct.c:318-333)
+					alt_mask = 0xFu;
+					rq_cur = alt_mask;
+				}
+				if (rq_cur | (ch_len > ch_skip ? 1u : 0u)) { pc = P2_RES; yield = true; }
+			}
+		}
+		if (pc == P2_EXIT) break;
+		// ---------------- the lookup site: this round's requests of every lane, one after the other
+		if (yield) {
+			uint64_t xr[4] = { z.x[0], z.x[1], z.x[2], z.x[3] };
+			uint32_t m = rq_cur, cj = 0;
+			rq_done |= rq_cur;
+			for (; cj < ch_skip; ++cj) bfc_kmer_append(k, xr, (int)(ch_bases >> (2 * cj) & 3));
+			while (m | (cj < ch_len ? 1u : 0u)) {
+				uint64_t x[4];
+				uint32_t sh;
+				if (m) {
+					const int b = __ffs(m) - 1;
+					m &= m - 1;
+					x[0] = z.x[0], x[1] = z.x[1], x[2] = z.x[2], x[3] = z.x[3];
+					bfc_kmer_append(k, x, b);
+					sh = 3 * b;
+				} else {
+					bfc_kmer_append(k, xr, (int)(ch_bases >> (2 * cj) & 3));
+					x[0] = xr[0], x[1] = xr[1], x[2] = xr[2], x[3] = xr[3];
+					sh = 16 + 3 * cj;
+					++cj;
+				}
+				const uint32_t c = occ_code(tab_kmer_occ(P.tab, x), P.min_cov);
+				++n_lookups;
+				if (sh < 16) rbits |= c << sh;
+				else la_code |= c << (sh - 16);
+			}
+			rq_cur = 0;
+		}
+	}
+	block_add(P.ctr + 1, n_lookups);
+	block_add(P.ctr + 3, n_lookups);
+}
+
 // ------------------------------------------------------------------ K6c: merge + rewrite, one read per warp
 
 __global__ void __launch_bounds__(256) k_ec_merge(EcParams P)
@@ -958,8 +1398,9 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 		for (uint64_t i = 0; i < h[0]; ++i) cut_r.push_back(h[1 + 2 * i]), cut_b.push_back(h[2 + 2 * i]);
 	}
 	const int threads = EC_THREADS;
-	int ctas = EC_CTAS_PER_SM;
-	{ const char *e = getenv("BFC_B200_EC_CTAS"); if (e && atoi(e) >= 1 && atoi(e) <= EC_CTAS_PER_SM) ctas = atoi(e); }
+	const bool search_v1 = getenv("BFC_B200_EC_V1") != 0; // A/B: the one-lookup-per-round search kernel
+	int ctas = search_v1 ? EC_CTAS_PER_SM : EC2_CTAS_PER_SM;
+	{ const char *e = getenv("BFC_B200_EC_CTAS"); if (e && atoi(e) >= 1 && atoi(e) <= ctas) ctas = atoi(e); }
 	const int64_t max_slots = (int64_t)rt.sm_count * ctas * threads; // persistent threads: exactly what is resident
 	const int heap_cap = opt->max_heap + 6; // the search never holds more than max_heap + 4 states
 	const int edit_cap = edit_cap0();
@@ -1081,7 +1522,11 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 			{ KTime kt(KT_EC_EXT); k_ec_ext<<<(unsigned)((2 * nr + 255) / 256), 256, 0, rt.stream>>>(P); }
 			BFCG_LAUNCH_CHECK();
 		}
-		{ KTime kt(KT_CORRECT); k_ec_search<<<(unsigned)(slots / threads), threads, 0, rt.stream>>>(P); }
+		{
+			KTime kt(KT_CORRECT);
+			if (search_v1) k_ec_search<<<(unsigned)(slots / threads), threads, 0, rt.stream>>>(P);
+			else k_ec_search2<<<(unsigned)(slots / threads), threads, 0, rt.stream>>>(P);
+		}
 		BFCG_LAUNCH_CHECK();
 		if (host && w + 1 < n_win) { // the next window travels while this one is searched (issued after the launches:
 			const cudaError_t ce = issue_copy_in(w + 1); // a copy from pageable memory blocks the host, not the GPU)
@@ -1108,7 +1553,11 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 			BFCG_CUDA(cudaMemsetAsync(P.ctr + 2, 0, 8, rt.stream));
 			EcParams Q = P;
 			Q.redo = redo, Q.n_jobs = (int64_t)n_redo, Q.edits = big, Q.edit_cap = cap;
-			{ KTime kt(KT_CORRECT_REDO); k_ec_search<<<(unsigned)(rs / 32), 32, 0, rt.stream>>>(Q); }
+			{
+				KTime kt(KT_CORRECT_REDO);
+				if (search_v1) k_ec_search<<<(unsigned)(rs / 32), 32, 0, rt.stream>>>(Q);
+				else k_ec_search2<<<(unsigned)(rs / 32), 32, 0, rt.stream>>>(Q);
+			}
 			BFCG_LAUNCH_CHECK();
 			BFCG_CUDA(cudaMemcpyAsync(c, P.ctr, sizeof(c), cudaMemcpyDeviceToHost, rt.stream));
 			BFCG_CUDA(cudaStreamSynchronize(rt.stream));

@@ -231,7 +231,7 @@ __device__ __forceinline__ void bulk_store_slice(uint32_t *g_dst, const uint32_t
 // occurrence of the same block in the same round) are replayed afterwards by warp 0 in stream order: lane l walks
 // the losers' bitmap in ascending order and handles the blocks with index = l mod 32, so one block is always
 // replayed sequentially and different blocks in parallel.
-template <typename VT, bool PACKED>
+template <typename VT, bool PACKED, bool BULK>
 __global__ void __launch_bounds__(CP_THREADS, CP_MIN_CTAS) k_count_part(PartParams p)
 {
 	extern __shared__ __align__(128) uint32_t s_w[]; // the partition's slice of the filter: blocks_per_part x 16 words
@@ -247,7 +247,8 @@ __global__ void __launch_bounds__(CP_THREADS, CP_MIN_CTAS) k_count_part(PartPara
 		if (!any) return;
 	}
 	uint32_t *const g_slice = p.bf.w + ((uint64_t)part * nb << 4);
-	bulk_load_slice(s_w, g_slice, nb * CP_BLK_BYTES, &s_mbar);
+	if (BULK) bulk_load_slice(s_w, g_slice, nb * CP_BLK_BYTES, &s_mbar);
+	else for (uint32_t i = tid; i < nb * 4; i += CP_THREADS) ((uint4*)s_w)[i] = __ldcs((const uint4*)g_slice + i);
 	for (uint32_t i = tid; i < nb; i += CP_THREADS) s_claim[i] = ~0u;
 	if (tid < CP_THREADS / 32) s_lose[tid] = 0, s_res[tid] = 0;
 	const int H = p.bf.n_hashes;
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(CP_THREADS, CP_MIN_CTAS) k_count_part(PartPara
 		unsigned long long key = 0;
 		VT val = R::mark();
 		if (beg + tid < end) val = __ldg(vals + beg + tid), key = __ldg(p.key + beg + tid);
-		if (!loaded) { bulk_load_wait(&s_mbar); loaded = true; } // the first records were requested while the slice travelled
+		if (BULK && !loaded) { bulk_load_wait(&s_mbar); loaded = true; } // the first records were requested while the slice travelled
 		for (uint64_t base = beg; base < end; base += CP_THREADS) {
 			const unsigned long long ckey = key;
 			const VT cval = val;
@@ -327,7 +328,8 @@ __global__ void __launch_bounds__(CP_THREADS, CP_MIN_CTAS) k_count_part(PartPara
 		}
 	}
 	__syncthreads();
-	bulk_store_slice(g_slice, s_w, nb * CP_BLK_BYTES);
+	if (BULK) bulk_store_slice(g_slice, s_w, nb * CP_BLK_BYTES);
+	else for (uint32_t i = tid; i < nb * 4; i += CP_THREADS) __stcs((uint4*)g_slice + i, ((const uint4*)s_w)[i]);
 	block_add(p.ctr + 1, n_k);
 	block_add(p.ctr + 2, n_pass);
 	block_add(p.ctr + 3, n_wait);
@@ -336,26 +338,19 @@ __global__ void __launch_bounds__(CP_THREADS, CP_MIN_CTAS) k_count_part(PartPara
 // bfc_ch_insert (htab.c:60-82) for every record that passed, in partition order: a warp's 32 records belong to one
 // partition, whose sub-tables are neighbours in the table (tab_region), so the probes stay in L2.  Latency-bound (a
 // load, then a CAS, per record): as many threads as the register file takes.
-// A record that finds its region full sets its bit in `retry` (n bits, zero on entry) and is applied again after the
-// table has grown (RETRY = true: only the records whose bit is set, clearing it on success) -- however many there are.
-template <typename VT, bool PACKED, bool RETRY>
-__global__ void __launch_bounds__(256, 8) k_tab_apply_marked(TabView t, const unsigned long long *key, const VT *val, uint64_t n, uint32_t *retry, unsigned long long *n_failed)
+template <typename VT, bool PACKED>
+__global__ void __launch_bounds__(256, 8) k_tab_apply_marked(TabView t, const unsigned long long *key, const VT *val, uint64_t n)
 {
-	unsigned long long added = 0, failed = 0;
+	unsigned long long added = 0;
 	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-		if (RETRY && !(__ldcg(retry + (i >> 5)) >> (i & 31) & 1)) continue;
 		const VT v = __ldg(val + i);
 		if (Rec<VT, PACKED>::valid(v)) {
 			unsigned long long y0f, y1;
 			Rec<VT, PACKED>::unpack(t.k, __ldg(key + i), v, y0f, y1);
-			const int r = tab_upsert_t<false>(t, y0f & ~(1ULL << 63), y1, (int)(y0f >> 63));
-			added += r == 1;
-			if (r < 0) { ++failed; if (!RETRY) atomicOr(retry + (i >> 5), 1u << (i & 31)); }
-			else if (RETRY) atomicAnd(retry + (i >> 5), ~(1u << (i & 31)));
+			added += tab_upsert(t, y0f & ~(1ULL << 63), y1, (int)(y0f >> 63)) == 1;
 		}
 	}
 	block_add(t.counters, added);
-	block_add(n_failed, failed);
 }
 
 // ------------------------------------------------------------------ host side
@@ -411,12 +406,11 @@ struct PartScratch {
 	uint8_t *tmp;
 	size_t tmp_bytes;
 	uint32_t *bounds;          // start[n_parts], end[n_parts]
-	uint32_t *retry;           // one bit per record: its table region was full (k_tab_apply_marked)
 	unsigned long long *ctr;
 	static size_t bytes(uint64_t n, const PartGeom &g, int vb)
 	{
 		return align_up(n * 8, 256) + align_up(n * value_bytes(vb), 256) + align_up(sort_temp_bytes(vb, n, g.pshift, g.pshift + g.pbits), 256) +
-		       align_up((size_t)g.n_parts * 8, 256) + align_up(n / 8 + 8, 256) + 256;
+		       align_up((size_t)g.n_parts * 8, 256) + 256;
 	}
 	void carve(uint8_t *a, uint64_t n, const PartGeom &g, int vb)
 	{
@@ -426,7 +420,6 @@ struct PartScratch {
 		tmp_bytes = sort_temp_bytes(vb, n, g.pshift, g.pshift + g.pbits);
 		tmp = a + o; o += align_up(tmp_bytes, 256);
 		bounds = (uint32_t*)(a + o); o += align_up((size_t)g.n_parts * 8, 256);
-		retry = (uint32_t*)(a + o); o += align_up(n / 8 + 8, 256);
 		ctr = (unsigned long long*)(a + o);
 	}
 };
@@ -455,7 +448,8 @@ static int tab_after_window(bfc_ch_t *ch, unsigned long long before)
 // The values are overwritten (marks).  `bounds` has room for 2 * n_runs * n_parts words.
 static int count_part_sorted(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, bfc_ch_t *ch, const PartGeom &g, uint64_t blk_mask, int vb,
                              const unsigned long long *key, void *val, int n_runs, const uint64_t *run_off,
-                             uint32_t *bounds, uint32_t *retry, unsigned long long *ctr, bfcg_stats_t *stats, const std::function<int()> *launched)
+                             uint32_t *bounds, unsigned long long *ctr, bfcg_stats_t *stats, const std::function<int()> *launched,
+                             unsigned long long n_before /* keys in the table now (no kernel that adds any is in flight) */)
 {
 	BfcgRuntime &rt = bfcg_rt();
 	int r;
@@ -482,32 +476,42 @@ static int count_part_sorted(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_hi
 	const size_t smem = (size_t)g.blocks_per_part * CP_BLK_BYTES;
 	{
 		KTime kt(KT_COUNT_PART);
-		REC_DISPATCH(vb, (k_count_part<VT, PK><<<g.n_parts, CP_THREADS, smem, rt.stream>>>(p)));
+		if (getenv("BFC_B200_NO_BULK")) REC_DISPATCH(vb, (k_count_part<VT, PK, false><<<g.n_parts, CP_THREADS, smem, rt.stream>>>(p)));
+		else REC_DISPATCH(vb, (k_count_part<VT, PK, true><<<g.n_parts, CP_THREADS, smem, rt.stream>>>(p)));
 	}
 	BFCG_LAUNCH_CHECK();
-	const unsigned apply_grid = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)rt.sm_count * 8);
-	if (ch) {
-		BFCG_CUDA(cudaMemsetAsync(retry, 0, n / 8 + 8, rt.stream));
-		KTime kt(KT_TAB_APPLY);
-		REC_DISPATCH(vb, (k_tab_apply_marked<VT, PK, false><<<apply_grid, 256, 0, rt.stream>>>(tab_view(ch), key, (const VT*)val, n, retry, p.ctr + 4)));
-	}
-	BFCG_LAUNCH_CHECK();
-	if (launched && (r = (*launched)()) != BFCG_OK) return r; // host work that should overlap the kernels just enqueued
-	unsigned long long c[5];
-	BFCG_CUDA(cudaMemcpyAsync(c, p.ctr, sizeof(c), cudaMemcpyDeviceToHost, rt.stream));
-	BFCG_CUDA(cudaStreamSynchronize(rt.stream));
-	for (int round = 0; ch && c[4] > 0; ++round) { // regions that filled up: grow, apply what is left, as often as it takes
-		if (round == 40) return bfcg_fail(__func__, "table inserts did not settle", cudaSuccess);
-		if ((r = bfcg_tab_grow(ch)) != BFCG_OK) return r;
-		BFCG_CUDA(cudaMemsetAsync(p.ctr + 4, 0, 8, rt.stream));
+	// bfc_ch_insert for the records that passed.  The growth estimate (tab_before_window) sizes the table for the keys a
+	// window usually adds; should a window add far more (a saturated first filter passes everything), no region may
+	// fill up beyond what the parking list takes.  So the records are applied in stretches that cannot lift the load
+	// above 3/4 even if every one of them is a new key -- normally the whole window is one stretch -- and the table
+	// grows between stretches when it has to.
+	unsigned long long c[4];
+	for (uint64_t pos = 0; ch && pos < n;) {
+		const uint64_t cap = bfcg_tab_capacity(ch), skew = ch->skew > 1 ? (uint64_t)ch->skew : 1;
+		const unsigned long long c0 = pos == 0 ? n_before : bfc_ch_count(ch); // (the first stretch goes out without a host sync)
+		const uint64_t lim = cap / 4 * 3 / skew;
+		const uint64_t room = lim > c0 ? lim - c0 : 0;
+		if (room < std::min<uint64_t>(n - pos, std::max<uint64_t>(cap / 16 / skew, 1))) {
+			if ((r = bfcg_tab_grow(ch)) != BFCG_OK) return r;
+			continue;
+		}
+		const uint64_t m = std::min<uint64_t>(n - pos, room);
 		{
 			KTime kt(KT_TAB_APPLY);
-			REC_DISPATCH(vb, (k_tab_apply_marked<VT, PK, true><<<apply_grid, 256, 0, rt.stream>>>(tab_view(ch), key, (const VT*)val, n, retry, p.ctr + 4)));
+			const unsigned grid = (unsigned)std::min<uint64_t>((m + 255) / 256, (uint64_t)rt.sm_count * 8);
+			REC_DISPATCH(vb, (k_tab_apply_marked<VT, PK><<<grid, 256, 0, rt.stream>>>(tab_view(ch), key + pos, (const VT*)val + pos, m)));
 		}
 		BFCG_LAUNCH_CHECK();
-		BFCG_CUDA(cudaMemcpyAsync(c + 4, p.ctr + 4, 8, cudaMemcpyDeviceToHost, rt.stream));
-		BFCG_CUDA(cudaStreamSynchronize(rt.stream));
+		pos += m;
+		if (pos == m && launched) { // host work that should overlap the kernels just enqueued (the next window's copy)
+			if ((r = (*launched)()) != BFCG_OK) return r;
+			launched = 0;
+		}
+		if (pos < n && (r = bfcg_tab_drain_deferred(ch)) != BFCG_OK) return r; // (the last stretch is drained by the caller)
 	}
+	if (launched && (r = (*launched)()) != BFCG_OK) return r;
+	BFCG_CUDA(cudaMemcpyAsync(c, p.ctr, sizeof(c), cudaMemcpyDeviceToHost, rt.stream));
+	BFCG_CUDA(cudaStreamSynchronize(rt.stream));
 	if (stats) {
 		stats->n_kmers += c[1], stats->n_pass += c[2];
 		stats->n_pending += c[1] - c[2], stats->n_conflict += c[3];
@@ -537,7 +541,7 @@ static int count_part_window(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_hi
 		key = sc.s_key;
 	} else BFCG_CUDA(cudaMemcpyAsync(sc.s_val, in_val, n * value_bytes(vb), cudaMemcpyDeviceToDevice, rt.stream)); // the values get marked in place
 	const uint64_t run_off[2] = { 0, n };
-	if ((r = count_part_sorted(opt, bf, bf_high, ch, g, blk_mask, vb, key, sc.s_val, 1, run_off, sc.bounds, sc.retry, sc.ctr, stats, launched)) != BFCG_OK) return r;
+	if ((r = count_part_sorted(opt, bf, bf_high, ch, g, blk_mask, vb, key, sc.s_val, 1, run_off, sc.bounds, sc.ctr, stats, launched, before)) != BFCG_OK) return r;
 	return ch ? tab_after_window(ch, before) : BFCG_OK;
 }
 
@@ -546,11 +550,15 @@ static int part_kernel_setup()
 	static bool done = false;
 	if (!done) {
 		const int bytes = (1 << CP_SLOG2) * CP_BLK_BYTES;
-		BFCG_CUDA(cudaFuncSetAttribute(k_count_part<unsigned long long, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-		BFCG_CUDA(cudaFuncSetAttribute(k_count_part<uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-		BFCG_CUDA(cudaFuncSetAttribute(k_count_part<uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-		BFCG_CUDA(cudaFuncSetAttribute(k_count_part<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-		BFCG_CUDA(cudaFuncSetAttribute(k_count_part<unsigned long long, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+#define CP_ATTR(VT, PK) \
+		BFCG_CUDA(cudaFuncSetAttribute(k_count_part<VT, PK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); \
+		BFCG_CUDA(cudaFuncSetAttribute(k_count_part<VT, PK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))
+		CP_ATTR(unsigned long long, false);
+		CP_ATTR(uint8_t, true);
+		CP_ATTR(uint16_t, true);
+		CP_ATTR(uint32_t, true);
+		CP_ATTR(unsigned long long, true);
+#undef CP_ATTR
 		done = true;
 	}
 	return BFCG_OK;
@@ -782,14 +790,14 @@ int bfcg_count_part_runs(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, 
 	const uint64_t n = run_off[n_runs];
 	if (n == 0) return BFCG_OK;
 	if (n >= (1ULL << 32)) return bfcg_fail(__func__, "more than 2^32 records in one exchange", cudaSuccess), BFCG_ERR_ARG;
-	const size_t o_retry = align_up((size_t)n_runs * g.n_parts * 8, 256), o_ctr = o_retry + align_up(n / 8 + 8, 256);
+	const size_t o_ctr = align_up((size_t)n_runs * g.n_parts * 8, 256);
 	uint8_t *a = (uint8_t*)bfcg_arena(o_ctr + 256);
 	if (!a) return BFCG_ERR_NOMEM;
 	BfcgTimer timer(stats);
 	unsigned long long before = 0;
 	if (ch && (r = tab_before_window(ch, n, &before)) != BFCG_OK) return r;
 	if ((r = count_part_sorted(opt, bf, bf_high, ch, g, (1ULL << g.x) - 1, 0, (const unsigned long long*)d_y0, d_y1, n_runs, run_off,
-	                           (uint32_t*)a, (uint32_t*)(a + o_retry), (unsigned long long*)(a + o_ctr), stats, 0)) != BFCG_OK) return r;
+	                           (uint32_t*)a, (unsigned long long*)(a + o_ctr), stats, 0, before)) != BFCG_OK) return r;
 	if (ch && (r = tab_after_window(ch, before)) != BFCG_OK) return r;
 	timer.stop();
 	BFCG_CUDA(cudaStreamSynchronize(rt.stream));

@@ -64,9 +64,27 @@ def gz_write(path, data: bytes):
             fp.write(data)
 
 
+def heavy_case(name, seed, n_copy, unit, div, N, L, low_frac, k, b):
+    """Reads from MANY slightly diverged copies of one repeat unit, most of them with low quality throughout: no base
+    is ever "fixed" (correct.c:299-301), alternatives are solid wherever another copy differs, so the search branches
+    at every few bases -- the heap passes max_heap = 100 (the single-push rule, correct.c:349-355) and whole reads give
+    up with n_fail > 2n (ec_code 5, correct.c:342-347), which uniform genomes never reach."""
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 4, size=unit, dtype=np.uint8)
+    parts = []
+    for _ in range(n_copy):
+        s = base.copy()
+        m = rng.random(unit) < div
+        s[m] = (s[m] + rng.integers(1, 4, size=int(m.sum()), dtype=np.uint8)) & 3
+        parts.append(rng.integers(0, 4, size=300, dtype=np.uint8))
+        parts.append(s)
+    seq, qual = synth.make_reads(np.concatenate(parts), N, L, seed, err=0.005, n_rate=0.0)
+    qual[rng.random(N) < low_frac, :] = 33 + 10
+    case_from_fastq(name, synth.fastq_bytes(seq, qual), k, b, (),
+                    dict(kind="diverged repeat copies", seed=seed, n_copy=n_copy, unit=unit, div=div, N=N, L=L, low_frac=low_frac))
+
+
 def synth_case(name, G, N, L, seed, k, b, err=0.01, repeat=0.0, extra_edge=False, extra_args=()):
-    d = os.path.join(GOLD, name)
-    os.makedirs(d, exist_ok=True)
     tmp = tempfile.mkdtemp()
     fq = os.path.join(tmp, "in.fq")
     synth.write_fastq(fq, G, N, L, seed, err=err, repeat_frac=repeat)
@@ -82,11 +100,18 @@ def synth_case(name, G, N, L, seed, k, b, err=0.01, repeat=0.0, extra_edge=False
         for r in recs[110:160]:
             extra.append(b"@" + r[0] + b"_lc\n" + r[2].lower() + b"\n+\n" + r[3] + b"\n")
         data += b"".join(extra)
-        open(fq, "wb").write(data)
+    case_from_fastq(name, data, k, b, extra_args, dict(G=G, N=N, L=L, seed=seed, err=err, repeat=repeat, edge=extra_edge))
+
+
+def case_from_fastq(name, data, k, b, extra_args, generator):
+    d = os.path.join(GOLD, name)
+    os.makedirs(d, exist_ok=True)
+    tmp = tempfile.mkdtemp()
+    fq = os.path.join(tmp, "in.fq")
+    open(fq, "wb").write(data)
     gz_write(os.path.join(d, "in.fq.gz"), data)
     args = ["-k", str(k), "-b", str(b)] + list(extra_args)
-    meta = dict(name=name, k=k, b=b, extra_args=list(extra_args), n_records=len(orc.parse_fastx(data)),
-                generator=dict(G=G, N=N, L=L, seed=seed, err=err, repeat=repeat, edge=extra_edge))
+    meta = dict(name=name, k=k, b=b, extra_args=list(extra_args), n_records=len(orc.parse_fastx(data)), generator=generator)
     # normal mode
     pre = os.path.join(tmp, "bloom")
     out = orc.ref_run(args + ["-t1", fq], binary="bfc_bloomdump", env={"BFC_REF_BLOOM_DUMP": pre})
@@ -112,8 +137,16 @@ def synth_case(name, G, N, L, seed, k, b, err=0.01, repeat=0.0, extra_edge=False
     meta["bf_high_sha256"] = sha(t1)
     meta["bf_high_popcount"] = int(np.unpackbits(t1).sum())
     meta["trimmed_sha256"] = hashlib.sha256(tout).hexdigest()
+    # what the searches went through, from the reference's own ec:Z: tags (correct.c:599-604)
+    import re
+    tags = re.findall(rb"ec:Z:(\d)_(\d+):(\d+)_", out)
+    codes = re.findall(rb"ec:Z:(\d)", out)
+    meta["ec_codes"] = {str(c): sum(1 for t in codes if int(t) == c) for c in range(6)}
+    meta["max_heap_max"] = max(int(t[2]) for t in tags)
+    meta["max_heap_over_100"] = sum(1 for t in tags if int(t[2]) > 100)
     json.dump(meta, open(os.path.join(d, "case.json"), "w"), indent=1, sort_keys=True)
-    print(name, "records", meta["n_records"], "table", meta["table_n"], "bloom bits", meta["bloom_popcount"])
+    print(name, "records", meta["n_records"], "table", meta["table_n"], "bloom bits", meta["bloom_popcount"],
+          "ec codes", meta["ec_codes"], "max_heap", meta["max_heap_max"], "reads over 100:", meta["max_heap_over_100"])
 
 
 def kat():
@@ -180,6 +213,9 @@ if __name__ == "__main__":
     if not orc.have_ref():
         orc.build_oracle(ref=True)
     os.makedirs(GOLD, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "heavy":   # (only the case added in round 2)
+        heavy_case("k15_heavy", 8, 32, 250, 0.03, 6000, 100, 0.8, 15, 20)
+        sys.exit(0)
     kat()
     synth_case("k21_small", 20000, 3000, 100, 11, 21, 20)
     synth_case("k31_edge", 20000, 2500, 100, 12, 31, 21, repeat=0.2, extra_edge=True)
@@ -187,3 +223,4 @@ if __name__ == "__main__":
     synth_case("k55_rep", 12000, 1200, 150, 14, 55, 19, repeat=0.3)
     synth_case("k63_h7", 12000, 1000, 150, 15, 63, 19, extra_args=("-H", "7"))
     synth_case("k32_even", 12000, 1000, 100, 16, 32, 19, extra_args=("-c", "2", "-q", "30"))
+    heavy_case("k15_heavy", 8, 32, 250, 0.03, 6000, 100, 0.8, 15, 20)
