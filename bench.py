@@ -391,7 +391,7 @@ def run(args, wl):
             eng.stats = api.Stats()
     else:
         # rank r holds the r-th piece of every global chunk (bfc_b200/dist.py): local reads = its pieces back to back
-        from bfc_b200.dist import CudaBackend, ShardedCount, piece_bounds
+        from bfc_b200.dist import CudaBackend, NativeShardedCount, ShardedCount, piece_bounds
         G = genome_size(n)
         pieces = [piece_bounds(lo, min(n, lo + args.chunk_reads), rank, world) for lo in range(0, n, args.chunk_reads)]
         n_mine = sum(p1 - p0 for p0, p1 in pieces)
@@ -420,7 +420,8 @@ def run(args, wl):
         L.bfcg_dev_free(d_off_tmp)
         be = CudaBackend(opt, world, local_rank, rank=rank)
         L.bfcg_set_timing(1)
-        sc = ShardedCount(be, rank, world)
+        # the exchange runs inside the library (csrc/dist.cu); BFC_DIST_PY=1 selects the round-1 path (torch all_to_all_single)
+        sc = ShardedCount(be, rank, world) if os.environ.get("BFC_DIST_PY") else NativeShardedCount(be, rank, world)
 
         def dev_batch(seq_ptr, qual_ptr, first, count):
             b = api.Batch()
@@ -442,6 +443,7 @@ def run(args, wl):
             t1 = time.perf_counter()
             for b in count_pieces:
                 sc.count_piece(b)
+            sc.finish()
             L.bfcg_sync()
             t2 = time.perf_counter()
             if do_correct:
@@ -568,6 +570,7 @@ def run(args, wl):
                 be.reset()
                 for hb in hb_pieces:
                     sc.count_piece(hb)
+                sc.finish()
                 if do_correct:
                     sc.gather()
                 if n_mine and trim:
@@ -608,6 +611,11 @@ def run(args, wl):
         for p_ in pinned:
             L.bfcg_host_free_pinned(p_)
 
+    exchange = None
+    if world > 1 and hasattr(sc, "stats"):
+        exchange = sc.stats()
+        exchange["bytes_per_record"] = 9 if wl["k"] <= 35 else 10 if wl["k"] <= 39 else 12 if wl["k"] <= 47 else 16
+        exchange["note"] = "rank 0, whole run (warm-up, timed steps and the end-to-end steps): grouped ncclSend/ncclRecv on the library's exchange stream"
     n_distinct = None
     if world == 1:
         if eng.ch:
@@ -619,6 +627,7 @@ def run(args, wl):
         data.free()
     else:
         be.close()
+        NativeShardedCount.finalize(L)
 
     cli = None
     if rank == 0 and world == 1 and not args.no_cli and do_correct:
@@ -639,7 +648,7 @@ def run(args, wl):
         line = {"metric": wl["metric"], "value": value, "unit": "Mreads/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
-                "clocks": clk, "e2e": e2e, "e2e_cli": cli, "gpu_launches": int(st["n_launches"]), "roofline": roofline,
+                "clocks": clk, "e2e": e2e, "e2e_cli": cli, "exchange": exchange, "gpu_launches": int(st["n_launches"]), "roofline": roofline,
                 "cpu_baseline": cpu,
                 "stats": {"kmers_per_step": st["n_kmers"] // args.steps, "f_pass": st["n_pass"] / max(1, st["n_kmers"]),
                           "pending_frac": st["n_pending"] / max(1, st["n_kmers"]),

@@ -123,6 +123,16 @@ def lib():
     L.bfcg_bf_init_shard.restype = C.POINTER(BF)
     L.bfcg_bf_init_shard.argtypes = [C.c_int, C.c_int, C.c_int]
     L.bfcg_ch_set_shard.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.bfcg_dist_unique_id.argtypes = [C.c_void_p]
+    L.bfcg_dist_init.argtypes = [C.c_int, C.c_int, C.c_void_p]
+    L.bfcg_dist_finalize.restype = None
+    L.bfcg_dist_count_piece.argtypes = [C.POINTER(Opt), C.POINTER(BF), C.POINTER(BF), C.c_void_p, C.POINTER(Batch), C.POINTER(Stats)]
+    L.bfcg_dist_count_finish.argtypes = [C.POINTER(Opt), C.POINTER(BF), C.POINTER(BF), C.c_void_p, C.POINTER(Stats)]
+    L.bfcg_dist_gather_table.argtypes = [C.c_void_p, C.c_void_p]
+    L.bfcg_dist_gather_filter.argtypes = [C.POINTER(BF), C.POINTER(BF)]
+    L.bfcg_dist_allreduce_sum_u64.argtypes = [u64p, C.c_int]
+    L.bfcg_dist_allreduce_max_f64.argtypes = [C.POINTER(C.c_double), C.c_int]
+    L.bfcg_dist_stats.argtypes = [u64p, u64p, C.POINTER(C.c_double)]
     L.bfcg_ch_export_device.restype = C.c_uint64
     L.bfcg_ch_export_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.bfcg_ch_import_device.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]

@@ -169,6 +169,11 @@ int bfcg_count_part_records(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_hig
 int bfcg_enum_part_records(const bfc_opt_t *opt, const bfcg_batch_t *batch, int owner_bits, uint64_t *d_y0, uint64_t *d_y1, uint64_t *counts);
 int bfcg_count_part_runs(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, bfc_ch_t *ch, int n_runs, const uint64_t *run_counts,
                          const uint64_t *d_y0, uint64_t *d_y1, int owner_bits, bfcg_stats_t *stats);
+// the same two with the record format given (0 = 16-byte wire records, else bytes of a packed record's value)
+int bfcg_part_record_value_bytes(int k);
+int bfcg_enum_part_records_fmt(const bfc_opt_t *opt, const bfcg_batch_t *batch, int owner_bits, int vb, uint64_t *d_y0, void *d_y1, uint64_t *counts);
+int bfcg_count_part_runs_fmt(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, bfc_ch_t *ch, int n_runs, const uint64_t *run_counts,
+                             int vb, const uint64_t *d_y0, void *d_y1, int owner_bits, bfcg_stats_t *stats);
 
 #ifdef __CUDACC__
 
@@ -367,6 +372,39 @@ __device__ __forceinline__ int tab_get(const TabView &t, uint64_t y0, uint64_t y
 			if (v[j] == 0) return -1;
 			if ((v[j] >> 14) == key) return (int)(v[j] & 0x3fff);
 		}
+	}
+	return -1;
+}
+
+// ---- the same lookup in two halves, for callers that keep several of them in flight: tab_locate (where the key's
+// first bucket is), the caller's own loads of that bucket, tab_match_bucket (-2 = bucket full of other keys: go on
+// with tab_get_rest from the next bucket)
+__device__ __forceinline__ const unsigned long long *tab_locate(const TabView &t, uint64_t y0, uint64_t y1, uint64_t &key, uint32_t &h)
+{
+	uint32_t sub;
+	tab_subkey(t.k, t.l_pre, y0, y1, sub, key);
+	h = (uint32_t)(tab_mix(key) & ((1ULL << t.rbits) - 1) & ~3ULL);
+	return tab_region_ptr(t, sub);
+}
+
+__device__ __forceinline__ int tab_match_bucket(const ulonglong2 &v01, const ulonglong2 &v23, uint64_t key)
+{
+	const unsigned long long v[4] = { v01.x, v01.y, v23.x, v23.y };
+#pragma unroll
+	for (int j = 0; j < 4; ++j) {
+		if (v[j] == 0) return -1;
+		if ((v[j] >> 14) == key) return (int)(v[j] & 0x3fff);
+	}
+	return -2;
+}
+
+static __device__ __noinline__ int tab_get_rest(const TabView &t, const unsigned long long *reg, uint32_t h0, uint64_t key)
+{
+	const uint64_t R = 1ULL << t.rbits;
+	uint64_t h = ((uint64_t)h0 + 4) & (R - 1);
+	for (uint64_t n = 4; n < R; n += 4, h = (h + 4) & (R - 1)) {
+		const int r = tab_match_bucket(__ldg((const ulonglong2*)(reg + h)), __ldg((const ulonglong2*)(reg + h) + 1), key);
+		if (r != -2) return r;
 	}
 	return -1;
 }

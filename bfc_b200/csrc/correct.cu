@@ -848,7 +848,8 @@ __device__ __forceinline__ int code_flags(uint32_t c) { return (c & 1 ? FL_SOL :
 
 enum { P2_NEWJOB = 0, P2_POP, P2_STEP, P2_RES, P2_FINISH, P2_EXIT };
 
-__global__ void __launch_bounds__(EC_THREADS, EC2_CTAS_PER_SM) k_ec_search2(EcParams P)
+template <int CTAS>
+__global__ void __launch_bounds__(EC_THREADS, CTAS) k_ec_search2(EcParams P)
 {
 	const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	EcState *const pool = P.pool + slot * P.heap_cap;
@@ -1112,9 +1113,9 @@ __global__ void __launch_bounds__(EC_THREADS, EC2_CTAS_PER_SM) k_ec_search2(EcPa
 				for (;;) { // repeats only after stepping over decision-free bases
 					// Step over every decision-free base at once (see k_ec_search): possible while the path's last k-1
 					// bases are the read's own, which is what the jump planes were computed for
+					int run = 0;
 					if (z.i < n && memo_dir && z.clean >= k - 1 && heap_n <= 3) {
 						const int fz = dir ? n - 1 - z.i : z.i;
-						int run;
 						if (!dir) { const uint64_t w = ~bits64(plane(P, PL_J0), o + fz); run = w ? __ffsll((long long)w) - 1 : 64; }
 						else { const uint64_t w = ~bits64(plane(P, PL_J1), o + fz - 63); run = w ? __clzll((long long)w) : 64; }
 						if (bp >= 0) { // the rescued base is not the original one: stop in front of it
@@ -1129,19 +1130,23 @@ __global__ void __launch_bounds__(EC_THREADS, EC2_CTAS_PER_SM) k_ec_search2(EcPa
 								if (hk_pen(k0) == hk_pen(k1)) heapk.set(0, k1), heapk.set(1, k0);
 							}
 							z.i += run, z.clean += run;
-							extract_kmer(P, o, n, dir, z.i - 1, k - 1, -1, 0, z.x);
 						}
 					}
 					has_c = z.i < n;
 					cb = cob = -1, ff = 0, osf = 0, allowed = true, memo = own_known = false;
+					int ff2 = 0;
+					if (has_c) { // the flags of the position travel while the k-mer is cut out of the planes
+						f = dir ? n - 1 - z.i : z.i;
+						ff = __ldg(P.fl + o + f);
+						ff2 = dir && memo_dir && z.clean >= k - 1 ? (int)__ldg(P.fl + o + f + k - 1) : ff; // the k-mer ending here (in search order)
+					}
+					if (run > 0) extract_kmer(P, o, n, dir, z.i - 1, k - 1, -1, 0, z.x);
 					if (!has_c) break;
-					f = dir ? n - 1 - z.i : z.i;
-					ff = __ldg(P.fl + o + f);
 					const int ob = FL_OB(ff), cur = f == bp ? bb : ob;
 					cb = dir ? comp_b(cur) : cur, cob = dir ? comp_b(ob) : ob;
 					if (cb > 3) break;
 					memo = memo_dir && z.clean >= k - 1 && cb == cob; // the read's own k-mer: K5 fetched it
-					if (memo) { osf = __ldg(P.fl + o + (dir ? f + k - 1 : f)) & (FL_SOL | FL_A | FL_H); own_known = true; break; }
+					if (memo) { osf = ff2 & (FL_SOL | FL_A | FL_H); own_known = true; break; }
 					// looked up ahead?  Entry 0 of the cache becomes this position.
 					const int d = z.i - la_pos;
 					if (la_valid && d > 0 && d < 4) la_valid >>= d, la_code >>= 3 * d;
@@ -1194,14 +1199,16 @@ __global__ void __launch_bounds__(EC_THREADS, EC2_CTAS_PER_SM) k_ec_search2(EcPa
 							const int room = EC_RQ - __popc(rq_cur);
 							if ((int)ch_skip + room < len) len = (int)ch_skip + room;
 							ch_bases = (uint32_t)cb;
-							int m = 1;
-							for (; m < len; ++m) {
+							int obs[3];
+#pragma unroll
+							for (int m = 1; m < 4; ++m) { // (three independent loads)
 								const int fj = dir ? f - m : f + m;
-								if (fj == bp) break;
-								const int obj = FL_OB(__ldg(P.fl + o + fj));
-								if (obj > 3) break;
-								ch_bases |= (uint32_t)(dir ? 3 - obj : obj) << (2 * m);
+								obs[m - 1] = m < len && fj != bp ? FL_OB(__ldg(P.fl + o + fj)) : 7;
 							}
+							int m = 1;
+#pragma unroll
+							for (int t = 0; t < 3; ++t)
+								if (m == t + 1 && obs[t] <= 3) ch_bases |= (uint32_t)(dir ? 3 - obs[t] : obs[t]) << (2 * m), ++m;
 							ch_len = (uint32_t)m;
 							if (ch_len <= ch_skip) ch_len = ch_skip = 0; // nothing new to look up
 						}
@@ -1525,7 +1532,8 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 		{
 			KTime kt(KT_CORRECT);
 			if (search_v1) k_ec_search<<<(unsigned)(slots / threads), threads, 0, rt.stream>>>(P);
-			else k_ec_search2<<<(unsigned)(slots / threads), threads, 0, rt.stream>>>(P);
+			else if (ctas >= 5) k_ec_search2<5><<<(unsigned)(slots / threads), threads, 0, rt.stream>>>(P);
+			else k_ec_search2<4><<<(unsigned)(slots / threads), threads, 0, rt.stream>>>(P);
 		}
 		BFCG_LAUNCH_CHECK();
 		if (host && w + 1 < n_win) { // the next window travels while this one is searched (issued after the launches:
@@ -1556,7 +1564,7 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 			{
 				KTime kt(KT_CORRECT_REDO);
 				if (search_v1) k_ec_search<<<(unsigned)(rs / 32), 32, 0, rt.stream>>>(Q);
-				else k_ec_search2<<<(unsigned)(rs / 32), 32, 0, rt.stream>>>(Q);
+				else k_ec_search2<4><<<(unsigned)(rs / 32), 32, 0, rt.stream>>>(Q);
 			}
 			BFCG_LAUNCH_CHECK();
 			BFCG_CUDA(cudaMemcpyAsync(c, P.ctr, sizeof(c), cudaMemcpyDeviceToHost, rt.stream));

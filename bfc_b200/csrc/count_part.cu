@@ -720,17 +720,26 @@ int bfcg_count_part_records(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_hig
 // the other (count_part_sorted with n_runs = ranks) and never sorts.
 int bfcg_enum_part_records(const bfc_opt_t *opt, const bfcg_batch_t *batch, int owner_bits, uint64_t *d_y0, uint64_t *d_y1, uint64_t *counts)
 {
+	return bfcg_enum_part_records_fmt(opt, batch, owner_bits, 0, d_y0, d_y1, counts);
+}
+
+int bfcg_part_record_value_bytes(int k) { return packed_value_bytes(k); }
+
+// vb = 0: 16-byte wire records (key = y0 | is_high << 63, value = y1); vb = 1, 2, 4, 8: packed records with a vb-byte
+// value (Rec<VT, true>), what stays inside one job and what the library's own exchange (dist.cu) sends
+int bfcg_enum_part_records_fmt(const bfc_opt_t *opt, const bfcg_batch_t *batch, int owner_bits, int vb, uint64_t *d_y0, void *d_y1, uint64_t *counts)
+{
 	BfcgRuntime &rt = bfcg_rt();
 	const int n_owners = 1 << owner_bits;
 	const PartGeom g = part_geom(opt->bf_shift, owner_bits);
 	const bool host = batch->where == BFCG_HOST;
 	const uint64_t nb = batch->n_bytes, n_rec = el_padded(nb);
 	const int sort_bits = g.pbits + owner_bits;
-	size_t temp = sort_temp_bytes(0, n_rec, g.pshift, g.pshift + sort_bits);
+	size_t temp = sort_temp_bytes(vb, n_rec, g.pshift, g.pshift + sort_bits);
 	size_t o_seq = 0, o_qual = 0, o_y0, o_y1, o_tmp, o_bnd, tot = 0;
 	if (host) { o_seq = tot; tot = align_up(tot + nb, 256); o_qual = tot; tot = align_up(tot + nb, 256); }
 	o_y0 = tot; tot = align_up(tot + n_rec * 8, 256);
-	o_y1 = tot; tot = align_up(tot + n_rec * 8, 256);
+	o_y1 = tot; tot = align_up(tot + n_rec * value_bytes(vb), 256);
 	o_tmp = tot; tot = align_up(tot + temp, 256);
 	size_t o_enum = tot; tot += enum_scratch_bytes(n_rec);
 	o_bnd = tot; tot += 256;
@@ -739,26 +748,26 @@ int bfcg_enum_part_records(const bfc_opt_t *opt, const bfcg_batch_t *batch, int 
 	EnumLinParams ep;
 	memset(&ep, 0, sizeof(ep));
 	ep.k = opt->k, ep.q = opt->q, ep.len = nb, ep.emit_from = 0;
-	ep.key = (unsigned long long*)(a + o_y0), ep.val = a + o_y1; // n_rec (padded) records, wire format
+	ep.key = (unsigned long long*)(a + o_y0), ep.val = a + o_y1; // n_rec (padded) records
 	if (host) {
 		BFCG_CUDA(cudaMemcpyAsync(a + o_seq, batch->seq, nb, cudaMemcpyHostToDevice, rt.stream));
 		if (batch->qual) BFCG_CUDA(cudaMemcpyAsync(a + o_qual, batch->qual, nb, cudaMemcpyHostToDevice, rt.stream));
 		ep.seq = a + o_seq, ep.qual = batch->qual ? a + o_qual : 0;
 	} else ep.seq = batch->seq, ep.qual = batch->qual;
 	uint64_t nv = 0; // records = positions where a k-mer ends (<= batch->n_bytes, what the caller's arrays hold)
-	{ int er = enumerate_window(0, ep, n_rec, a + o_enum, &nv); if (er != BFCG_OK) return er; }
+	{ int er = enumerate_window(vb, ep, n_rec, a + o_enum, &nv); if (er != BFCG_OK) return er; }
 	if (nv == 0) return BFCG_OK;
 	if (sort_bits > 0) {
 		cudaError_t se;
 		{
 			KTime kt(KT_COUNT_SORT);
-			se = sort_records(a + o_tmp, temp, 0, ep.key, (unsigned long long*)d_y0, ep.val, d_y1, nv, g.pshift, g.pshift + sort_bits);
+			se = sort_records(a + o_tmp, temp, vb, ep.key, (unsigned long long*)d_y0, ep.val, d_y1, nv, g.pshift, g.pshift + sort_bits);
 		}
 		BFCG_CUDA(se);
 		rt.n_launches += 1 + (sort_bits + 7) / 8;
 	} else {
 		BFCG_CUDA(cudaMemcpyAsync(d_y0, ep.key, nv * 8, cudaMemcpyDeviceToDevice, rt.stream));
-		BFCG_CUDA(cudaMemcpyAsync(d_y1, ep.val, nv * 8, cudaMemcpyDeviceToDevice, rt.stream));
+		BFCG_CUDA(cudaMemcpyAsync(d_y1, ep.val, nv * value_bytes(vb), cudaMemcpyDeviceToDevice, rt.stream));
 	}
 	uint32_t h_bnd[2 * 8];
 	memset(h_bnd, 0, sizeof(h_bnd));
@@ -779,6 +788,12 @@ int bfcg_enum_part_records(const bfc_opt_t *opt, const bfcg_batch_t *batch, int 
 int bfcg_count_part_runs(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, bfc_ch_t *ch, int n_runs, const uint64_t *run_counts,
                          const uint64_t *d_y0, uint64_t *d_y1, int owner_bits, bfcg_stats_t *stats)
 {
+	return bfcg_count_part_runs_fmt(opt, bf, bf_high, ch, n_runs, run_counts, 0, d_y0, d_y1, owner_bits, stats);
+}
+
+int bfcg_count_part_runs_fmt(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, bfc_ch_t *ch, int n_runs, const uint64_t *run_counts,
+                             int vb, const uint64_t *d_y0, void *d_y1, int owner_bits, bfcg_stats_t *stats)
+{
 	BfcgRuntime &rt = bfcg_rt();
 	int r;
 	if ((r = part_kernel_setup()) != BFCG_OK) return r;
@@ -796,7 +811,7 @@ int bfcg_count_part_runs(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, 
 	BfcgTimer timer(stats);
 	unsigned long long before = 0;
 	if (ch && (r = tab_before_window(ch, n, &before)) != BFCG_OK) return r;
-	if ((r = count_part_sorted(opt, bf, bf_high, ch, g, (1ULL << g.x) - 1, 0, (const unsigned long long*)d_y0, d_y1, n_runs, run_off,
+	if ((r = count_part_sorted(opt, bf, bf_high, ch, g, (1ULL << g.x) - 1, vb, (const unsigned long long*)d_y0, d_y1, n_runs, run_off,
 	                           (uint32_t*)a, (unsigned long long*)(a + o_ctr), stats, 0, before)) != BFCG_OK) return r;
 	if (ch && (r = tab_after_window(ch, before)) != BFCG_OK) return r;
 	timer.stop();

@@ -104,6 +104,9 @@ class ShardedCount:
             self.be.count_records(r0, r1, int(sum(out_splits)), self.world)
         self._tick("count_records", t)
 
+    def finish(self):
+        """(Nothing is left in flight: every count_piece completes its own chunk.)"""
+
     def gather(self):
         """Replicate the result on every rank: the complete table (normal mode) or bf_high (trim mode)."""
         t = self._tick("other", 0.0)
@@ -154,6 +157,7 @@ class CudaBackend:
             raise api.BfcError("allocation failed: " + L.bfcg_last_error().decode())
         if self.ch and world > 1 and rank is not None:  # only 1/world of the sub-table regions can receive keys
             self._check(L.bfcg_ch_set_shard(self.ch, world, rank), "bfcg_ch_set_shard")
+        self._native_full_bf = None  # complete bf_high owned by the library (NativeShardedCount.gather)
         self.full_ch = None          # complete table after gather()
         self.full_bf_high = None     # complete bf_high (torch tensor keeps the memory) after gather()
         self._bf_high_view = None
@@ -262,6 +266,8 @@ class CudaBackend:
             if ch:
                 self._check(L.bfcg_ch_clear(ch), "bfcg_ch_clear")
         self.full_bf_high = self._bf_high_view = None
+        if self._native_full_bf:
+            self._check(L.bfcg_bf_clear(self._native_full_bf), "bfcg_bf_clear")
         if self.world > 1 and self.full_ch == self.ch:
             self.full_ch = None
 
@@ -294,9 +300,79 @@ class CudaBackend:
         if self.bf_high:
             L.bfc_bf_destroy(self.bf_high)
             self.bf_high = None
+        if self._native_full_bf:
+            L.bfc_bf_destroy(self._native_full_bf)
+            self._native_full_bf = None
         if self.full_ch and self.full_ch != self.ch:
             L.bfc_ch_destroy(self.full_ch)
         if self.ch:
             L.bfc_ch_destroy(self.ch)
         self.ch = self.full_ch = None
         self._buf.clear()
+
+
+class NativeShardedCount:
+    """The count phase of one rank with the exchange INSIDE the library (csrc/dist.cu: grouped ncclSend / ncclRecv on
+    the library's own stream, overlapped with the cascade of the previous chunk and the enumeration of the next piece).
+    Same interface as ShardedCount; torch.distributed only carries the 128-byte NCCL id to the ranks."""
+
+    _inited = None
+
+    def __init__(self, backend: "CudaBackend", rank: int, world: int, group=None):
+        owner_bits(world)
+        self.be, self.rank, self.world = backend, rank, world
+        self.prof = None
+        L = backend.L
+        if NativeShardedCount._inited is None:
+            idb = (C.c_uint8 * 128)()
+            if rank == 0:
+                backend._check(L.bfcg_dist_unique_id(idb), "bfcg_dist_unique_id")
+            if world > 1:
+                t = torch.tensor(list(idb), dtype=torch.uint8, device=backend.device)
+                dist.broadcast(t, 0, group=group)
+                idb = (C.c_uint8 * 128)(*[int(v) for v in t.cpu()])
+            backend._check(L.bfcg_dist_init(rank, world, idb), "bfcg_dist_init")
+            NativeShardedCount._inited = (rank, world)
+        elif NativeShardedCount._inited != (rank, world):
+            raise ValueError("the library's communicator was created for another (rank, world)")
+
+    def count_piece(self, piece):
+        be = self.be
+        be._check(be.L.bfcg_dist_count_piece(C.byref(be.opt), be.bf, be.bf_high, be.ch, C.byref(piece), C.byref(be.stats)),
+                  "bfcg_dist_count_piece")
+
+    def finish(self):
+        be = self.be
+        be._check(be.L.bfcg_dist_count_finish(C.byref(be.opt), be.bf, be.bf_high, be.ch, C.byref(be.stats)), "bfcg_dist_count_finish")
+
+    def gather(self):
+        """Drain the pipeline, then replicate the complete table (normal mode) or bf_high (trim mode) on every rank."""
+        be, L = self.be, self.be.L
+        self.finish()
+        if be.filter_mode:
+            if be._native_full_bf is None:
+                be._native_full_bf = L.bfc_bf_init(be.opt.bf_shift, be.opt.n_hashes)
+                if not be._native_full_bf:
+                    raise be.api.BfcError("bfc_bf_init failed: " + L.bfcg_last_error().decode())
+            be._check(L.bfcg_dist_gather_filter(be.bf_high, be._native_full_bf), "bfcg_dist_gather_filter")
+            be._bf_high_view = be._native_full_bf.contents
+            return
+        if self.world == 1:
+            be.full_ch = be.ch
+            return
+        full = be.full_ch if be.full_ch and be.full_ch != be.ch else L.bfc_ch_init(be.opt.k, be.opt.l_pre)
+        if not full:
+            raise be.api.BfcError("bfc_ch_init failed: " + L.bfcg_last_error().decode())
+        be.full_ch = full
+        be._check(L.bfcg_dist_gather_table(be.ch, full), "bfcg_dist_gather_table")
+
+    def stats(self):
+        sent, recv, ms = C.c_uint64(), C.c_uint64(), C.c_double()
+        self.be.L.bfcg_dist_stats(C.byref(sent), C.byref(recv), C.byref(ms))
+        return {"sent_records": sent.value, "received_records": recv.value, "exchange_ms": ms.value}
+
+    @staticmethod
+    def finalize(L):
+        if NativeShardedCount._inited is not None:
+            L.bfcg_dist_finalize()
+            NativeShardedCount._inited = None

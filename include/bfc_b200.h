@@ -127,6 +127,32 @@ int bfcg_ch_set_shard(bfc_ch_t *ch, int n_owners, int owner);
 uint64_t bfcg_ch_export_device(const bfc_ch_t *ch, uint32_t *d_sub, uint64_t *d_key);
 int      bfcg_ch_import_device(bfc_ch_t *ch, uint64_t n, const uint32_t *d_sub, const uint64_t *d_key);
 
+/* sharded counting with the exchange INSIDE the library (csrc/dist.cu): one rank per GPU, NCCL over NVLink ---------
+ * The caller only brings the ranks together: one rank makes an id (bfcg_dist_unique_id), hands its 128 bytes to the
+ * others by whatever means it has (MPI, a file, torch.distributed's store), and every rank calls bfcg_dist_init after
+ * selecting its device.  Then, per global chunk of reads, EVERY rank calls bfcg_dist_count_piece with its piece (a
+ * collective; an empty piece when it has run out of reads): the piece is enumerated and sorted by (owner, count
+ * partition) into packed records, the buckets travel by grouped ncclSend / ncclRecv on a stream of their own while the
+ * engine's stream runs the cascade over the previous chunk's records and enumerates the next piece.
+ * bfcg_dist_count_finish drains the pipeline; bf / bf_high are shards (bfcg_bf_init_shard), ch a shard table
+ * (bfcg_ch_set_shard).  Results: the reference's `-t1` run over all reads in global order, bit for bit.
+ * bfcg_dist_gather_table / _filter replicate the result on every rank (what the correction / trim phase needs). */
+#define BFCG_DIST_ID_BYTES 128
+int  bfcg_dist_unique_id(void *id);
+int  bfcg_dist_init(int rank, int world, const void *id);
+void bfcg_dist_finalize(void);
+int  bfcg_dist_rank(void);
+int  bfcg_dist_world(void);
+int  bfcg_dist_count_piece(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, bfc_ch_t *ch,
+                           const bfcg_batch_t *piece, bfcg_stats_t *stats);
+int  bfcg_dist_count_finish(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high, bfc_ch_t *ch, bfcg_stats_t *stats);
+int  bfcg_dist_gather_table(const bfc_ch_t *shard, bfc_ch_t *full);
+int  bfcg_dist_gather_filter(const bfc_bf_t *shard, bfc_bf_t *full);
+int  bfcg_dist_allreduce_sum_u64(uint64_t *v, int n);      /* host arrays, n <= 64 */
+int  bfcg_dist_allreduce_max_f64(double *v, int n);
+int  bfcg_dist_barrier(void);
+int  bfcg_dist_stats(uint64_t *sent_records, uint64_t *received_records, double *exchange_ms);
+
 /* device memory helpers for callers that keep batches resident in HBM -------------- */
 void *bfcg_dev_alloc(uint64_t bytes);
 void  bfcg_dev_free(void *p);

@@ -12,14 +12,14 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, k, b, trim, chunk, out):
+def _worker(rank, world, port, k, b, trim, chunk, out, native=False):
     import ctypes as C
     import torch
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
     import bfc_b200
     from bfc_b200 import api, synth
-    from bfc_b200.dist import CudaBackend, ShardedCount, piece_bounds
+    from bfc_b200.dist import CudaBackend, NativeShardedCount, ShardedCount, piece_bounds
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     assert api.lib().bfcg_set_device(rank) == 0
@@ -30,13 +30,14 @@ def _worker(rank, world, port, k, b, trim, chunk, out):
         n = len(seq)
         opt = bfc_b200.make_opt(k=k, bf_shift=b, filter_mode=1 if trim else 0)
         be = CudaBackend(opt, world, rank, rank=rank)
-        sc = ShardedCount(be, rank, world)
+        sc = NativeShardedCount(be, rank, world) if native else ShardedCount(be, rank, world)
         mine = []
         for lo in range(0, n, chunk):
             p0, p1 = piece_bounds(lo, min(n, lo + chunk), rank, world)
             s, q, off = synth.concat_batch(seq[p0:p1], qual[p0:p1])
             sc.count_piece(api.host_batch(s, q, off))
             mine.append((p0, p1))
+        sc.finish()
         res = {"bloom": be.bf_shard().cpu().numpy(), "n_kmers": int(be.stats.n_kmers), "n_pass": int(be.stats.n_pass)}
         sc.gather()
         for i, (p0, p1) in enumerate(mine):
@@ -53,12 +54,14 @@ def _worker(rank, world, port, k, b, trim, chunk, out):
             res[f"range{i}"] = np.array([p0, p1])
         np.savez(os.path.join(out, f"rank{rank}.npz"), **res)
         be.close()
+        NativeShardedCount.finalize(api.lib())
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("k,b,trim,chunk", [(31, 24, False, 7000), (33, 22, True, 24000)])
-def test_sharded_count_and_partitioned_correct_on_real_ranks(tmp_path, k, b, trim, chunk):
+@pytest.mark.parametrize("native", [False, True], ids=["torch-exchange", "library-exchange"])
+@pytest.mark.parametrize("k,b,trim,chunk", [(31, 24, False, 7000), (33, 22, True, 24000), (55, 26, False, 5000)])
+def test_sharded_count_and_partitioned_correct_on_real_ranks(tmp_path, k, b, trim, chunk, native):
     import torch
     import torch.multiprocessing as mp
     world = 1
@@ -68,8 +71,8 @@ def test_sharded_count_and_partitioned_correct_on_real_ranks(tmp_path, k, b, tri
         pytest.skip("needs at least 2 GPUs")
     sys.path.insert(0, ROOT)
     from bfc_b200 import synth
-    port = 29500 + (os.getpid() * 7 + k) % 2000
-    mp.spawn(_worker, args=(world, port, k, b, trim, chunk, str(tmp_path)), nprocs=world, join=True)
+    port = 29500 + (os.getpid() * 7 + k + (1000 if native else 0)) % 2000
+    mp.spawn(_worker, args=(world, port, k, b, trim, chunk, str(tmp_path), native), nprocs=world, join=True)
     genome = synth.make_genome(80000, k + b, 0.2)
     seq, qual = synth.make_reads(genome, 24000, 120, k + b)
     s, q, off = synth.concat_batch(seq, qual)

@@ -341,6 +341,54 @@ def test_sharded_count_kernels_emulated_on_one_gpu(bfc, monkeypatch, world, k, b
         o.close()
 
 
+@pytest.mark.parametrize("k,b,trim", [(33, 26, False), (31, 22, True), (55, 24, False)])
+def test_library_exchange_pipeline_single_rank(bfc, k, b, trim):
+    """csrc/dist.cu with a world of one (what a 1-GPU box can run of it): the enumerate -> exchange -> cascade pipeline
+    with its two buffer sets, NCCL send / receive to itself, several chunks in flight -- against the oracle."""
+    from bfc_b200.dist import CudaBackend, NativeShardedCount
+    seq, qual, off = synth_batch(60000, 15000, 120, seed=k + b, repeat=0.2)
+    N = len(off) - 1
+    opt = bfc.make_opt(k=k, bf_shift=b, filter_mode=1 if trim else 0)
+    o = orc.OracleRun(orc.make_opt(k=k, bf_shift=b, filter_mode=1 if trim else 0))
+    be = CudaBackend(opt, 1, 0, rank=0)
+    try:
+        sc = NativeShardedCount(be, 0, 1)
+        o.count(seq, qual, off)
+        empty = bfc.api.host_batch(seq[:0], qual[:0], off[:1])
+        for i, lo in enumerate(range(0, N, 2500)):
+            hi = min(N, lo + 2500)
+            sc.count_piece(bfc.api.host_batch(seq[int(off[lo]):int(off[hi])], qual[int(off[lo]):int(off[hi])], off[lo:hi + 1] - off[lo]))
+            if i == 2:
+                sc.count_piece(empty)  # a rank that has run out of reads still takes part
+        sc.gather()
+        assert np.array_equal(be.bf_shard().cpu().numpy(), o.bloom_bytes())
+        assert int(be.stats.n_kmers) == int(o.stats[0]) and int(be.stats.n_pass) == int(o.stats[1])
+        if trim:
+            assert np.array_equal(be.bf_high_shard().cpu().numpy(), o.bloom_bytes(high=True))
+            keep, ts, te = np.zeros(N, dtype=np.uint8), np.zeros(N, dtype=np.int32), np.zeros(N, dtype=np.int32)
+            be.trim_batch(bfc.api.host_batch(seq, None, off), keep.ctypes.data, ts.ctypes.data, te.ctypes.data)
+            ko, tso, teo = o.trim(seq, off)
+            assert np.array_equal(keep, ko) and np.array_equal(ts, tso) and np.array_equal(te, teo)
+        else:
+            L = bfc.lib()
+            n = int(L.bfcg_ch_export(be.full_ch, None, None))
+            sub, key = np.zeros(n, dtype=np.uint32), np.zeros(n, dtype=np.uint64)
+            L.bfcg_ch_export(be.full_ch, sub.ctypes.data_as(bfc.api.u32p), key.ctypes.data_as(bfc.api.u64p))
+            so, ko = o.table()
+            assert np.array_equal(sub, so) and np.array_equal(key, ko)
+            s2, q2 = seq.copy(), qual.copy()
+            aux = np.zeros(2 * N, dtype=np.uint32)
+            be.correct_batch(bfc.api.host_batch(s2, q2, off), aux.ctypes.data)
+            s1, q1, a1, _ = o.correct(seq, qual, off)
+            assert np.array_equal(aux, a1) and np.array_equal(s2, s1) and np.array_equal(q2, q1)
+        st = sc.stats()
+        assert st["received_records"] == int(o.stats[0]) and st["sent_records"] == 0
+    finally:
+        be.close()
+        NativeShardedCount.finalize(bfc.lib())
+        o.close()
+
+
 @pytest.mark.parametrize("path", ["part", "probe", "part-wire-noext"])
 def test_device_batches_and_many_windows(bfc, monkeypatch, path):
     """What bench.py runs: batches resident in HBM (BFCG_DEVICE), and host batches cut into many count /
