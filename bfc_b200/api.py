@@ -147,6 +147,8 @@ def lib():
     L.bfcg_bf_download.argtypes = [C.POINTER(BF), u8p]
     L.bfcg_bf_upload.argtypes = [C.POINTER(BF), u8p]
     L.bfcg_bf_clear.argtypes = [C.POINTER(BF)]
+    L.bfcg_bf_load.argtypes = [C.POINTER(BF), C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.bfcg_bf_suggest_shift.argtypes = [C.c_uint64, C.c_int, C.c_double]
     L.bfcg_ch_export.restype = C.c_uint64
     L.bfcg_ch_export.argtypes = [C.c_void_p, u32p, u64p]
     L.bfcg_ch_l_pre.argtypes = [C.c_void_p]

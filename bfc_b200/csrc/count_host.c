@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 #include "bfc.h"
 #include "bfc_b200.h"
 #include "fqblock.h"
@@ -83,6 +84,18 @@ void *bfc_count(const char *fn, const bfc_opt_t *opt)
 	if (bfc_verbose >= 3)
 		fprintf(stderr, "[M::%s] k-mer occurrences: %llu; passed the first filter: %llu; replayed in order: %llu\n", __func__,
 				(unsigned long long)cs.stats.n_kmers, (unsigned long long)cs.stats.n_pass, (unsigned long long)cs.stats.n_conflict);
+	if (bfc_verbose >= 3) { /* filter occupancy: how full -b left the first filter, and what that means for the table */
+		double load = 0, blocks = 0, fp = 0;
+		if (bfcg_bf_load(cs.bf, 1, &load, &blocks, &fp) == BFCG_OK) {
+			fprintf(stderr, "[M::%s] first Bloom filter (-b %d): %.2f%% of its bits set, %.1f%% of its blocks touched; a new k-mer passes it with p = %.2e\n",
+					__func__, opt->bf_shift, 100. * load, 100. * blocks, fp);
+			if (fp > 0.05) {
+				const uint64_t n_est = (uint64_t)(-(double)((uint64_t)1 << opt->bf_shift) * (504. / 512.) / opt->n_hashes * log(1. - (load < 0.999999 ? load : 0.999999)));
+				fprintf(stderr, "[W::%s] the first filter is saturated (about %llu distinct k-mers went in): singletons leak into the %s; -b %d would keep p below 1%%\n",
+						__func__, (unsigned long long)n_est, cs.ch ? "k-mer table" : "second filter", bfcg_bf_suggest_shift(n_est, opt->n_hashes, 0.01));
+			}
+		}
+	}
 	bfc_bf_destroy(cs.bf); /* the first filter never leaves this function (reference count.c:155) */
 	return ret;
 }

@@ -165,6 +165,11 @@ void  bfcg_host_free_pinned(void *p);
 int      bfcg_bf_download(const bfc_bf_t *bf, uint8_t *dst);          /* 2^(n_shift-3) bytes */
 int      bfcg_bf_upload(bfc_bf_t *bf, const uint8_t *src);
 int      bfcg_bf_clear(bfc_bf_t *bf);
+/* occupancy telemetry (a working version of what the reference's unused bfc_bf_load, bbf.c:65-79, was for): fraction of
+ * data bits set, fraction of blocks touched, false-positive rate of the filter at that load; n_owners > 1: `bf` is a shard */
+int      bfcg_bf_load(const bfc_bf_t *bf, int n_owners, double *bit_load, double *block_load, double *fp_rate);
+/* the -b (log2 bits) that keeps the false-positive rate <= target_fp after n_distinct different k-mers (at most 37) */
+int      bfcg_bf_suggest_shift(uint64_t n_distinct, int n_hashes, double target_fp);
 /* all entries as (sub-table index, key50<<14 | val14), sorted by (sub, key); pass NULLs to get n */
 uint64_t bfcg_ch_export(const bfc_ch_t *ch, uint32_t *sub, uint64_t *key);
 int      bfcg_ch_l_pre(const bfc_ch_t *ch);

@@ -235,6 +235,64 @@ def test_table_grows_when_regions_fill(bfc, monkeypatch, b, path):
         o.close()
 
 
+def test_reference_main_relinked(bfc, tmp_path):
+    """INTEGRATION.md level 1 as a binary: the reference's own bfc.c (its main, getopt loop and phase orchestration,
+    compiled against the reference's own bfc.h) linked with libbfc_b200.so in place of the reference's count / correct /
+    bbf / htab / kthread / bseq objects (oracle/Makefile: _ref/bfc_relinked).  Its output is the reference's."""
+    import subprocess
+    exe = os.path.join(orc.ROOT, "oracle", "_ref", "bfc_relinked")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/bfc_relinked is not built on this box")
+    for name in ("k31_edge", "k55_rep"):
+        c = Case(name)
+        fq = tmp_path / (name + ".fq")
+        fq.write_bytes(c.fastq)
+        args = ["-k", str(c.meta["k"]), "-b", str(c.meta["b"])] + c.meta["extra_args"]
+        out = subprocess.run([exe] + args + ["-t", "4", str(fq)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True).stdout
+        assert out == c.corrected
+        out = subprocess.run([exe] + args + ["-1", str(fq)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True).stdout
+        assert out == c.trimmed
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_cli_discard_and_noqual_flags(bfc, tmp_path, name):
+    """`-D` (drop reads with ec_code != 0, correct.c:598) and `-Q` (FASTA out, correct.c:596, 605-609) against digests of
+    the unmodified reference's output (tools/make_golden_flags.py)."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(bfc.lib_path()), "bfc")
+    c = Case(name)
+    fq = tmp_path / (name + ".fq")
+    fq.write_bytes(c.fastq)
+    args = ["-k", str(c.meta["k"]), "-b", str(c.meta["b"])] + c.meta["extra_args"]
+    for key, flags in (("discard", ["-D"]), ("noqual", ["-Q"]), ("discard_noqual", ["-D", "-Q"])):
+        out = subprocess.run([exe] + flags + args + ["-t", "3", str(fq)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True).stdout
+        assert len(out) == c.meta[key + "_bytes"] and hashlib.sha256(out).hexdigest() == c.meta[key + "_sha256"], key
+
+
+def test_filter_occupancy_telemetry(bfc):
+    """bfcg_bf_load (a working version of the reference's unused bfc_bf_load, bbf.c:65-79) against numpy on the downloaded
+    filter bytes, and bfcg_bf_suggest_shift against the load formula."""
+    import ctypes as C
+    seq, qual, off = synth_batch(50000, 12000, 100, seed=9, repeat=0.0)
+    e = bfc.Engine(bfc.make_opt(k=31, bf_shift=22))
+    L = bfc.lib()
+    try:
+        e.count(seq, qual, off)
+        load, blocks, fp = C.c_double(), C.c_double(), C.c_double()
+        assert L.bfcg_bf_load(e.bf, 1, C.byref(load), C.byref(blocks), C.byref(fp)) == 0
+        b = e.bloom_bytes()
+        bits = int(np.unpackbits(b).sum())
+        n_blocks = len(b) // 64
+        assert abs(load.value - bits / (n_blocks * 504)) < 1e-12
+        assert abs(blocks.value - float((b.reshape(n_blocks, 64).any(axis=1)).mean())) < 1e-12
+        assert abs(fp.value - load.value ** 4) < 1e-12 and 0 < fp.value < 1
+        # 1e6 distinct k-mers, H = 4, p <= 1 %: load = 0.01^(1/4) = 0.316, m = -4e6 / ln(1 - 0.316) = 1.05e7 bits -> 2^24
+        assert L.bfcg_bf_suggest_shift(1_000_000, 4, 0.01) == 24
+        assert L.bfcg_bf_suggest_shift(10**12, 4, 0.01) == 37  # capped at BFC_MAX_BF_SHIFT
+    finally:
+        e.close()
+
+
 def test_truncated_dump_is_rejected(bfc, tmp_path):
     """bfc_ch_restore on a dump cut short returns NULL (the reference asserts, htab.c:161-170) instead of a partial table."""
     seq, qual, off = synth_batch(20000, 4000, 100, seed=3, repeat=0.0)
