@@ -158,6 +158,10 @@ int bfcg_tab_align_to_filter(bfc_ch_s *ch, int x);
 int bfcg_tab_drain_deferred(bfc_ch_s *ch);
 // double the slots of every region
 int bfcg_tab_grow(bfc_ch_s *ch);
+// table replication by concatenating shard slot arrays (dist.cu)
+int bfcg_tab_set_rbits(bfc_ch_s *ch, int rbits);
+int bfcg_tab_shape_like_shards(bfc_ch_s *full, const bfc_ch_s *shard);
+int bfcg_tab_set_count(bfc_ch_s *ch, uint64_t n);
 // slots of the table (a shard holds 2^(l_pre - own_bits) regions)
 static inline uint64_t bfcg_tab_capacity(const bfc_ch_s *ch) { return 1ULL << (ch->l_pre - ch->own_bits + ch->rbits); }
 

@@ -166,7 +166,11 @@ int bfcg_dist_init(int rank, int world, const void *id)
 	ncclUniqueId u;
 	memcpy(&u, id, sizeof(u) < BFCG_DIST_ID_BYTES ? sizeof(u) : BFCG_DIST_ID_BYTES);
 	BFCG_NCCL(g_nccl.CommInitRank(&d->comm, world, u, rank));
-	BFCG_CUDA(cudaStreamCreateWithFlags(&d->xs, cudaStreamNonBlocking));
+	{ // the exchange's kernels are small and must not wait behind the million-CTA grids of the cascade: highest priority
+		int least = 0, greatest = 0;
+		BFCG_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+		BFCG_CUDA(cudaStreamCreateWithPriority(&d->xs, cudaStreamNonBlocking, greatest));
+	}
 	for (int i = 0; i < 2; ++i) {
 		BFCG_CUDA(cudaEventCreateWithFlags(&d->buf[i].sorted, cudaEventDisableTiming));
 		BFCG_CUDA(cudaEventCreateWithFlags(&d->buf[i].received, cudaEventDisableTiming));
@@ -308,6 +312,25 @@ int bfcg_dist_gather_table(const bfc_ch_t *shard, bfc_ch_t *full)
 	BfcgRuntime &rt = bfcg_rt();
 	if (!d || !shard || !full) return bfcg_fail(__func__, "invalid arguments", cudaSuccess), BFCG_ERR_ARG;
 	const int W = d->world;
+	if (shard->own_bits == d->owner_bits && full->own_bits == 0 && full != shard && !getenv("BFC_B200_GATHER_ENTRIES")) {
+		// The shards' slot arrays, concatenated in owner order, ARE the whole table (bfcg_tab_shape_like_shards) once every
+		// shard has the same region size: one all-gather over NVLink, no export, no re-insertion.
+		bfc_ch_s *mine = (bfc_ch_s*)shard;
+		uint64_t rb = (uint64_t)mine->rbits;
+		{ // the largest region size of any shard
+			double v = (double)rb;
+			if ((r = bfcg_dist_allreduce_max_f64(&v, 1)) != BFCG_OK) return r;
+			rb = (uint64_t)v;
+		}
+		if ((r = bfcg_tab_set_rbits(mine, (int)rb)) != BFCG_OK) return r;
+		if ((r = bfcg_tab_shape_like_shards(full, mine)) != BFCG_OK) return r;
+		uint64_t cnt = bfc_ch_count(mine);
+		if ((r = bfcg_dist_allreduce_sum_u64(&cnt, 1)) != BFCG_OK) return r;
+		BFCG_CUDA(cudaStreamSynchronize(rt.stream));
+		BFCG_NCCL(g_nccl.AllGather(mine->slots, full->slots, bfcg_tab_capacity(mine) * 8, ncclUint8, d->comm, d->xs));
+		BFCG_CUDA(cudaStreamSynchronize(d->xs));
+		return bfcg_tab_set_count(full, cnt);
+	}
 	const uint64_t n_mine = bfcg_ch_export_device(shard, 0, 0);
 	// sizes of every shard
 	d->h_cnt[0] = n_mine;

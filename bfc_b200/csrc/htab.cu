@@ -76,10 +76,15 @@ __global__ void k_tab_hist(const unsigned long long *slots, uint64_t n, unsigned
 __global__ void k_tab_export(const unsigned long long *slots, int rbits, int l_pre, int rot, uint32_t reg_hi, uint64_t n, uint32_t *sub, unsigned long long *key,
                              unsigned long long *cursor)
 {
-	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-		const unsigned long long s = __ldg(slots + i);
+	for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x; i0 < n; i0 += (uint64_t)gridDim.x * blockDim.x) { // (n is a multiple of 64: whole warps)
+		const uint64_t i = i0 + threadIdx.x;
+		const unsigned long long s = i < n ? __ldg(slots + i) : 0ULL;
+		const unsigned m = __ballot_sync(0xffffffffu, s != 0), lane = threadIdx.x & 31;
+		if (m == 0) continue;
+		unsigned long long at = 0;
+		if (lane == (unsigned)(__ffs(m) - 1)) at = atomicAdd(cursor, (unsigned long long)__popc(m)); // one atomic per warp
+		at = __shfl_sync(0xffffffffu, at, __ffs(m) - 1) + __popc(m & ((1u << lane) - 1));
 		if (s) {
-			const unsigned long long at = atomicAdd(cursor, 1ULL);
 			sub[at] = tab_region_inv(l_pre, rot, reg_hi | (uint32_t)(i >> rbits));
 			key[at] = s;
 		}
@@ -172,6 +177,39 @@ int bfcg_tab_reserve(bfc_ch_s *ch, uint64_t extra)
 }
 
 int bfcg_tab_grow(bfc_ch_s *ch) { return tab_resize(ch, ch->rbits + 1); }
+
+int bfcg_tab_set_rbits(bfc_ch_s *ch, int rbits) { return rbits > ch->rbits ? tab_resize(ch, rbits) : BFCG_OK; }
+
+// Make `full` (an ordinary table, its contents are dropped) the table whose slot array is the concatenation, in owner
+// order, of the slot arrays of the 2^own_bits shards shaped like `shard`: same region size, same region placement.
+// The shards' owner bits are the top bits of the region index (bfcg_tab_align_to_filter), so region r of shard o IS
+// region o << (l_pre - own_bits) | r of the whole table, probe sequences included.
+int bfcg_tab_shape_like_shards(bfc_ch_s *full, const bfc_ch_s *shard)
+{
+	BfcgRuntime &rt = bfcg_rt();
+	if (full->k != shard->k || full->l_pre != shard->l_pre) return bfcg_fail(__func__, "tables of different k", cudaSuccess);
+	if (full->own_bits != 0 || full->rbits != shard->rbits || full->rot != shard->rot) {
+		unsigned long long *ns = 0;
+		const uint64_t cap = 1ULL << (full->l_pre + shard->rbits);
+		cudaFree(full->slots);
+		full->slots = 0;
+		if (cudaMalloc(&ns, cap * 8) != cudaSuccess) return bfcg_fail(__func__, "cudaMalloc(k-mer table)", cudaErrorMemoryAllocation);
+		full->slots = ns, full->rbits = shard->rbits, full->rot = shard->rot, full->own_bits = 0, full->own_val = 0, full->skew = 1;
+		full->req_owners = 0;
+	}
+	BFCG_CUDA(cudaMemsetAsync(full->counters, 0, 16, rt.stream));
+	full->prev_new = 0, full->have_prev = 0;
+	return BFCG_OK;
+}
+
+int bfcg_tab_set_count(bfc_ch_s *ch, uint64_t n)
+{
+	BfcgRuntime &rt = bfcg_rt();
+	unsigned long long v = n;
+	BFCG_CUDA(cudaMemcpyAsync(ch->counters, &v, 8, cudaMemcpyHostToDevice, rt.stream));
+	BFCG_CUDA(cudaStreamSynchronize(rt.stream));
+	return BFCG_OK;
+}
 
 int bfcg_tab_drain_deferred(bfc_ch_s *ch)
 {
