@@ -13,7 +13,7 @@
 //   K1' radix sort     stable partition of the records by the top bits of their Bloom
 //                      block index (cub onesweep over bits [10, x) of y0): partition =
 //                      1024 consecutive blocks = 64 KB of the filter
-//   K2' k_part_bounds  first / last record of every partition
+//   K2' k_part_bounds  first / last record of every partition (binary searches in the sorted keys)
 //   K3' k_count_part   one CTA per partition: the 64 KB slice of the filter is loaded into
 //                      shared memory, the partition's records are replayed in stream order
 //                      256 at a time -- records whose bits are all set pass (order-free);
@@ -150,18 +150,24 @@ __global__ void __launch_bounds__(EL_THREADS) k_enum_lin(EnumLinParams p)
 
 // ------------------------------------------------------------------ K2': partition bounds
 
+// The records are sorted by partition: the range of partition p is found by two binary searches (a few million probes
+// per window, against streaming every key past a comparison).  y0 points at record `base` of the array the bounds refer to.
 __global__ void __launch_bounds__(256) k_part_bounds(const unsigned long long *y0, uint64_t n, uint64_t base, int shift, uint32_t pmask, uint32_t *start, uint32_t *end)
 {
-	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; // y0 points at record `base` of the array the bounds refer to
-	const unsigned lane = threadIdx.x & 31;
-	const bool in = i < n;
-	const uint32_t p = in ? (uint32_t)(__ldg(y0 + i) >> shift) & pmask : 0;
-	uint32_t prev = __shfl_up_sync(0xffffffffu, p, 1), next = __shfl_down_sync(0xffffffffu, p, 1);
-	if (!in) return;
-	if (lane == 0 && i > 0) prev = (uint32_t)(__ldg(y0 + i - 1) >> shift) & pmask;
-	if (lane == 31 && i + 1 < n) next = (uint32_t)(__ldg(y0 + i + 1) >> shift) & pmask;
-	if (i == 0 || prev != p) start[p] = (uint32_t)(base + i);
-	if (i + 1 == n || next != p) end[p] = (uint32_t)(base + i + 1);
+	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p > pmask) return;
+	uint64_t lo = 0, hi = n; // first record whose partition is >= p
+	while (lo < hi) {
+		const uint64_t mid = (lo + hi) >> 1;
+		if (((uint32_t)(__ldg(y0 + mid) >> shift) & pmask) < p) lo = mid + 1; else hi = mid;
+	}
+	const uint64_t first = lo;
+	hi = n;              // first record whose partition is > p
+	while (lo < hi) {
+		const uint64_t mid = (lo + hi) >> 1;
+		if (((uint32_t)(__ldg(y0 + mid) >> shift) & pmask) <= p) lo = mid + 1; else hi = mid;
+	}
+	start[p] = (uint32_t)(base + first), end[p] = (uint32_t)(base + lo);
 }
 
 // ------------------------------------------------------------------ K3': one CTA per partition
@@ -466,8 +472,8 @@ static int count_part_sorted(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_hi
 		KTime kt(KT_COUNT_BOUNDS);
 		for (int i = 0; i < n_runs; ++i) {
 			const uint64_t m = run_off[i + 1] - run_off[i];
-			if (m) k_part_bounds<<<(unsigned)((m + 255) / 256), 256, 0, rt.stream>>>(key + run_off[i], m, run_off[i], g.pshift, g.n_parts - 1,
-			                                                                        start + (size_t)i * g.n_parts, end + (size_t)i * g.n_parts);
+			if (m) k_part_bounds<<<(g.n_parts + 255) / 256, 256, 0, rt.stream>>>(key + run_off[i], m, run_off[i], g.pshift, g.n_parts - 1,
+			                                                                    start + (size_t)i * g.n_parts, end + (size_t)i * g.n_parts);
 		}
 	}
 	BFCG_LAUNCH_CHECK();
@@ -774,7 +780,7 @@ int bfcg_enum_part_records_fmt(const bfc_opt_t *opt, const bfcg_batch_t *batch, 
 	if (owner_bits > 0) { // bucket sizes = runs of the owner bits in the sorted keys
 		uint32_t *bnd = (uint32_t*)(a + o_bnd);
 		BFCG_CUDA(cudaMemsetAsync(bnd, 0, 64, rt.stream));
-		{ KTime kt(KT_BUCKET); k_part_bounds<<<(unsigned)((nv + 255) / 256), 256, 0, rt.stream>>>((const unsigned long long*)d_y0, nv, 0, g.pshift + g.pbits, n_owners - 1, bnd, bnd + 8); }
+		{ KTime kt(KT_BUCKET); k_part_bounds<<<1, 256, 0, rt.stream>>>((const unsigned long long*)d_y0, nv, 0, g.pshift + g.pbits, n_owners - 1, bnd, bnd + 8); }
 		BFCG_LAUNCH_CHECK();
 		BFCG_CUDA(cudaMemcpyAsync(h_bnd, bnd, 64, cudaMemcpyDeviceToHost, rt.stream));
 	} else h_bnd[8] = (uint32_t)nv;
