@@ -32,7 +32,7 @@ typedef struct {
 	int32_t *ts, *te;
 } ec_step_t;
 
-static size_t batch_text_bytes(const bfc_opt_t *opt) { return (size_t)opt->chunk_size * 10; }
+static size_t batch_text_bytes(const bfc_opt_t *opt) { return (size_t)opt->chunk_size * 5 / 2; }
 
 /* parse_stats (reference correct.c:517-531) over the text after "ec:Z:", packed as worker_ec packs the result
  * (correct.c:552-553): numbers separated by one character each; what is missing counts as 0 */

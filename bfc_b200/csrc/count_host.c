@@ -21,9 +21,11 @@ typedef struct {
 	bfcg_stats_t stats;
 } cnt_shared_t;
 
-/* text per batch: the reference batches by bases (-L, count.c:103); here a batch is a block of input text, large
- * enough that the per-window costs of the GPU count (one sweep of the filter and of the table) stay small */
-static size_t batch_text_bytes(const bfc_opt_t *opt) { return (size_t)opt->chunk_size * 10; }
+/* text per batch: the reference batches by bases (-L, count.c:103); here a batch is a block of input text -- 250 MB
+ * at the default -L: the GPU's per-batch costs (one sweep of the filter and of the table, ~10 ms) stay far below what
+ * the host needs to read and pack it, and the pinned staging buffers and the recycled text buffers stay small enough
+ * that filling the pool with first-touch pages is over after a fraction of a second */
+static size_t batch_text_bytes(const bfc_opt_t *opt) { return (size_t)opt->chunk_size * 5 / 2; }
 
 static void *count_cb(void *shared, int step, void *_data)
 {

@@ -13,6 +13,57 @@
 bseq_file_t *bseq_open_from(void *gz, unsigned char *pre, size_t pre_len, const char *comment); /* bseq.c */
 int bseq_at_eof(const bseq_file_t *f);
 
+/* ---------------------------------------------------------------- recycled large buffers
+ * A batch is about a gigabyte of text plus a few hundred megabytes of offsets and as much formatted output again.
+ * Fresh from malloc, every one of those pages is mapped, zeroed and faulted in on first touch and unmapped on free --
+ * per batch -- which cost more than reading and splitting the text.  Large buffers therefore go back to a small pool
+ * and are handed out again (first fit within 2x), up to a fixed total. */
+#include <pthread.h>
+#define BIG_MIN   ((size_t)1 << 20)
+#define BIG_SLOTS 96
+#define BIG_POOL_MAX ((size_t)12 << 30)
+typedef struct { size_t cap, pooled; char pad[48]; } big_hdr_t; /* 64 bytes in front of every buffer */
+static big_hdr_t *big_pool[BIG_SLOTS];
+static size_t big_pool_bytes;
+static pthread_mutex_t big_mu = PTHREAD_MUTEX_INITIALIZER;
+
+static void *big_alloc(size_t n)
+{
+	big_hdr_t *h = 0;
+	if (n >= BIG_MIN) {
+		int i, best = -1;
+		pthread_mutex_lock(&big_mu);
+		for (i = 0; i < BIG_SLOTS; ++i)
+			if (big_pool[i] && big_pool[i]->cap >= n && big_pool[i]->cap <= 2 * n + BIG_MIN && (best < 0 || big_pool[i]->cap < big_pool[best]->cap)) best = i;
+		if (best >= 0) h = big_pool[best], big_pool[best] = 0, big_pool_bytes -= h->cap;
+		pthread_mutex_unlock(&big_mu);
+	}
+	if (h == 0) {
+		const size_t cap = n >= BIG_MIN ? n + n / 8 : n;
+		h = (big_hdr_t*)malloc(sizeof(big_hdr_t) + cap + 1);
+		if (h == 0) return 0;
+		h->cap = cap, h->pooled = n >= BIG_MIN;
+	}
+	return h + 1;
+}
+
+static void big_free(void *p)
+{
+	big_hdr_t *h;
+	if (p == 0) return;
+	h = (big_hdr_t*)p - 1;
+	if (h->pooled) {
+		int i, done = 0;
+		pthread_mutex_lock(&big_mu);
+		if (big_pool_bytes + h->cap <= BIG_POOL_MAX)
+			for (i = 0; i < BIG_SLOTS && !done; ++i)
+				if (big_pool[i] == 0) big_pool[i] = h, big_pool_bytes += h->cap, done = 1;
+		pthread_mutex_unlock(&big_mu);
+		if (done) return;
+	}
+	free(h);
+}
+
 struct fq_reader_s {
 	gzFile fp;
 	int fd;                     /* >= 0: an uncompressed regular file, read with parallel pread()s; the gzFile then only
@@ -91,8 +142,8 @@ int fq_reader_is_fast(const fq_reader_t *r) { return r->fast; }
 
 void fq_block_free(fq_block_t *b)
 {
-	free(b->buf); free(b->name_off); free(b->com_off); free(b->seq_off); free(b->qual_off);
-	free(b->name_len); free(b->com_len); free(b->seq_len);
+	big_free(b->buf); big_free(b->name_off); big_free(b->com_off); big_free(b->seq_off); big_free(b->qual_off);
+	big_free(b->name_len); big_free(b->com_len); big_free(b->seq_len);
 	memset(b, 0, sizeof(*b));
 }
 
@@ -100,9 +151,9 @@ static int blk_alloc(fq_block_t *b, int64_t n)
 {
 	const size_t m = n > 0 ? (size_t)n : 1;
 	b->n = n;
-	b->name_off = (uint64_t*)malloc(m * 8), b->com_off = (uint64_t*)malloc(m * 8);
-	b->seq_off = (uint64_t*)malloc(m * 8), b->qual_off = (uint64_t*)malloc(m * 8);
-	b->name_len = (uint32_t*)malloc(m * 4), b->com_len = (uint32_t*)malloc(m * 4), b->seq_len = (uint32_t*)malloc(m * 4);
+	b->name_off = (uint64_t*)big_alloc(m * 8), b->com_off = (uint64_t*)big_alloc(m * 8);
+	b->seq_off = (uint64_t*)big_alloc(m * 8), b->qual_off = (uint64_t*)big_alloc(m * 8);
+	b->name_len = (uint32_t*)big_alloc(m * 4), b->com_len = (uint32_t*)big_alloc(m * 4), b->seq_len = (uint32_t*)big_alloc(m * 4);
 	return b->name_off && b->com_off && b->seq_off && b->qual_off && b->name_len && b->com_len && b->seq_len ? 0 : -1;
 }
 
@@ -188,7 +239,10 @@ static void sticky_comments(fq_reader_t *rd, fq_block_t *b, int keep_comment)
 		int any = 0;
 		for (r = 0; r < b->n && b->com_off[r] == FQ_NONE - 1; ++r) any = 1;
 		if (any) {
-			b->buf = (char*)realloc(b->buf, b->buf_len + l + 1);
+			char *nb = (char*)big_alloc(b->buf_len + l + 1); /* (rare: one block in a file whose first records lack comments) */
+			memcpy(nb, b->buf, b->buf_len);
+			big_free(b->buf);
+			b->buf = nb;
 			memcpy(b->buf + b->buf_len, rd->last_comment, l + 1);
 			for (r = 0; r < b->n && b->com_off[r] == FQ_NONE - 1; ++r) b->com_off[r] = b->buf_len, b->com_len[r] = (uint32_t)l;
 			b->buf_len += l + 1;
@@ -217,17 +271,17 @@ static int fast_block(fq_reader_t *rd, char *data, size_t len, int keep_comment,
 	kt_for(rd->n_threads, count_nl_worker, &sp, sp.n_parts);
 	for (i = 0; i < sp.n_parts; ++i) { const size_t c = sp.cnt[i]; sp.cnt[i] = run; run += c; }
 	n_lines = run;
-	sp.nl = (uint64_t*)malloc((n_lines + 2) * sizeof(uint64_t));
+	sp.nl = (uint64_t*)big_alloc((n_lines + 2) * sizeof(uint64_t));
 	if (sp.nl == 0) { free(sp.cnt); return -1; }
 	kt_for(rd->n_threads, fill_nl_worker, &sp, sp.n_parts);
 	if (rd->eof && (n_lines == 0 || sp.nl[n_lines - 1] + 1 != len)) sp.nl[n_lines++] = len; /* last line without a newline */
-	if (n_lines < 4 || (rd->eof && n_lines % 4 != 0)) { free(sp.cnt); free(sp.nl); return 0; }
+	if (n_lines < 4 || (rd->eof && n_lines % 4 != 0)) { free(sp.cnt); big_free(sp.nl); return 0; }
 	memset(b, 0, sizeof(*b));
-	if (blk_alloc(b, (int64_t)(n_lines / 4)) < 0) { free(sp.cnt); free(sp.nl); fq_block_free(b); return -1; }
+	if (blk_alloc(b, (int64_t)(n_lines / 4)) < 0) { free(sp.cnt); big_free(sp.nl); fq_block_free(b); return -1; }
 	sp.b = b, sp.keep_comment = keep_comment;
 	kt_for(rd->n_threads, parse_worker, &sp, (long)((b->n + REC_PER_ITEM - 1) / REC_PER_ITEM));
 	*used = sp.nl[4 * b->n - 1] + 1 > len ? len : sp.nl[4 * b->n - 1] + 1;
-	free(sp.cnt); free(sp.nl);
+	free(sp.cnt); big_free(sp.nl);
 	if (sp.bad) { fq_block_free(b); return 0; }
 	b->buf = data, b->buf_len = len, b->any_qual = 1;
 	for (r = 0; r < b->n; ++r) b->n_bases += b->seq_len[r];
@@ -255,7 +309,7 @@ static int slow_block(fq_reader_t *rd, size_t target, int keep_comment, fq_block
 	}
 	for (i = 0; i < n; ++i)
 		tot += strlen(seqs[i].name) + 1 + (seqs[i].comment ? strlen(seqs[i].comment) + 1 : 0) + (size_t)seqs[i].l_seq * (seqs[i].qual ? 2 : 1) + 2;
-	if (blk_alloc(b, n) < 0 || (b->buf = (char*)malloc(tot + 1)) == 0) { fq_block_free(b); return -1; }
+	if (blk_alloc(b, n) < 0 || (b->buf = (char*)big_alloc(tot + 1)) == 0) { fq_block_free(b); return -1; }
 	for (i = 0; i < n; ++i) {
 		bseq1_t *s = &seqs[i];
 		size_t l = strlen(s->name);
@@ -279,7 +333,7 @@ int fq_next(fq_reader_t *rd, size_t target, int keep_comment, fq_block_t *b)
 	if (target < 4096) target = 4096;
 	while (rd->fast) {
 		const size_t carry0 = rd->carry_len;
-		char *data = (char*)malloc(carry0 + target + 1);
+		char *data = (char*)big_alloc(carry0 + target + 1);
 		size_t len = carry0, used = 0;
 		int rc;
 		if (data == 0) return -1;
@@ -290,7 +344,7 @@ int fq_next(fq_reader_t *rd, size_t target, int keep_comment, fq_block_t *b)
 			if (got == 0) { rd->eof = 1; break; }
 			len += got;
 		}
-		if (len == 0) { free(data); return 0; }
+		if (len == 0) { big_free(data); return 0; }
 		rc = fast_block(rd, data, len, keep_comment, b, &used);
 		if (rc == 1) {
 			if (used < len) { /* the incomplete tail waits for the next block */
@@ -300,11 +354,17 @@ int fq_next(fq_reader_t *rd, size_t target, int keep_comment, fq_block_t *b)
 			}
 			return 1;
 		}
-		if (rc < 0) { free(data); return -1; }
+		if (rc < 0) { big_free(data); return -1; }
 		/* not plain four-line FASTQ: the tolerant parser takes the stream over, starting with this block's text */
 		rd->fast = 0;
 		if (rd->fd >= 0) gzseek(rd->fp, (z_off_t)rd->pos, SEEK_SET); /* the stream goes on where the pread()s stopped */
-		rd->slow = bseq_open_from(rd->fp, (unsigned char*)data, len, rd->last_comment);
+		{
+			unsigned char *pre = (unsigned char*)malloc(len + 1); /* (bseq.c frees it with free()) */
+			if (pre == 0) { big_free(data); return -1; }
+			memcpy(pre, data, len);
+			big_free(data);
+			rd->slow = bseq_open_from(rd->fp, pre, len, rd->last_comment);
+		}
 	}
 	return slow_block(rd, target, keep_comment, b); /* 1, 0 at end of input, -1 out of memory */
 }
@@ -445,7 +505,7 @@ static void write_worker(void *data, long i, int tid)
 	char *out, *p;
 	(void)tid;
 	for (r = r0; r < r1; ++r) cap += (size_t)b->name_len[r] + b->com_len[r] + 2 * (size_t)b->seq_len[r] + 96;
-	out = p = (char*)malloc(cap);
+	out = p = (char*)big_alloc(cap);
 	if (out == 0) { w->oom = 1; w->piece[i] = 0, w->piece_len[i] = 0; return; }
 	for (r = r0; r < r1; ++r) {
 		const int64_t j = w->flat->flat_idx[r]; /* index in the batch; < 0: the record was left out of it */
@@ -504,7 +564,7 @@ int fq_write(FILE *fp, const fq_block_t *b, const fq_flat_t *flat, const fq_out_
 	kt_for(n_threads, write_worker, &w, w.n_items);
 	for (i = 0; i < w.n_items; ++i) {
 		if (!w.oom && w.piece_len[i] && fwrite(w.piece[i], 1, w.piece_len[i], fp) != w.piece_len[i]) rc = -1;
-		free(w.piece[i]);
+		big_free(w.piece[i]);
 	}
 	free(w.piece); free(w.piece_len);
 	return w.oom ? -1 : rc;
