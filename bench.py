@@ -265,7 +265,6 @@ def kernel_accounting(wl, st, kt, n, RB, steps, ms, peak):
     alg = {
         "enum_lin": 2 * pos + rec * nk,                     # seq + qual in, one packed record per k-mer out
         "conflict_sort": 2 * rec * nk,                      # a partition reads and writes every record once
-        "count_bounds": 8 * nk,
         "count_part": 64 * nk + 64 * npend + rec * nk,      # Bloom block in, written back when a bit is new (bbf.c:35-44), record in
         "tab_apply": 16 * npass + rec * nk,                 # slot read + write for every passing occurrence (htab.c:60-82)
         "ec_lookup": 32 * n_kcov + 3 * pos,                 # one 32-byte sector per lookup; seq + qual in, plane bits out

@@ -155,6 +155,7 @@ def lib():
     L.bfcg_ch_capacity_log2.argtypes = [C.c_void_p]
     L.bfcg_ch_clear.argtypes = [C.c_void_p]
     L.bfcg_ch_reserve.argtypes = [C.c_void_p, C.c_uint64]
+    L.bfcg_partition_records.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int]
     L.bfcg_ch_get_batch.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
     L.bfcg_kernel_times.argtypes = [C.POINTER(C.c_double), u64p, C.c_int]
     L.bfcg_event_record.argtypes = [C.c_int]

@@ -28,6 +28,7 @@
 // replay path (random access, same results) is used.
 #include "common.cuh"
 #include "enum.cuh"
+#include "partition.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <algorithm>
@@ -388,12 +389,28 @@ bool bfcg_count_part_usable(const bfc_opt_t *opt, int n_shift, int owner_bits)
 	return x <= opt->k && x - owner_bits >= 0 && x - owner_bits <= 36;
 }
 
-// stable partition of n records by bits [begin, end) of the key (cub onesweep); vb = record format (REC_DISPATCH)
+static inline int value_bytes(int vb);
+
+// Stable partition of n records by bits [begin, end) of the key; vb = record format (REC_DISPATCH).  The work is done
+// by partition.cuh (two passes of 10 bits for the usual 20 partition bits); BFC_B200_CUB_SORT=1 switches back to the
+// library radix sort of round 1 (three passes of 8 bits) for comparison.  Called with tmp == 0 it only reports the
+// scratch it needs.
+static bool use_cub_sort() { static int v = -1; if (v < 0) v = getenv("BFC_B200_CUB_SORT") != 0; return v != 0; }
+
 static cudaError_t sort_records(void *tmp, size_t &tmp_bytes, int vb, const unsigned long long *k_in, unsigned long long *k_out,
                                 const void *v_in, void *v_out, uint64_t n, int begin, int end)
 {
 	cudaError_t e = cudaSuccess;
-	REC_DISPATCH(vb, e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, (const VT*)v_in, (VT*)v_out, (int64_t)n, begin, end, bfcg_rt().stream));
+	if (use_cub_sort()) {
+		REC_DISPATCH(vb, e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, (const VT*)v_in, (VT*)v_out, (int64_t)n, begin, end, bfcg_rt().stream));
+		if (tmp) bfcg_rt().n_launches += 1 + (end - begin + 7) / 8; // histogram + one onesweep pass per 8 bits
+		return e;
+	}
+	const size_t o_val = align_up(n * 8, 256), o_scr = o_val + align_up(n * (size_t)value_bytes(vb), 256);
+	if (tmp == 0) { tmp_bytes = o_scr + rp_scratch_bytes(n, begin, end); return cudaSuccess; }
+	uint8_t *t = (uint8_t*)tmp;
+	REC_DISPATCH(vb, e = rp_partition<VT>(bfcg_rt().stream, bfcg_rt().sm_count, k_in, (const VT*)v_in, k_out, (VT*)v_out, (unsigned long long*)t, (VT*)(t + o_val),
+	                                      t + o_scr, n, begin, end, &bfcg_rt().n_launches));
 	return e;
 }
 
@@ -405,6 +422,22 @@ static size_t sort_temp_bytes(int vb, uint64_t n, int begin, int end)
 }
 
 static inline int value_bytes(int vb) { return vb ? vb : 8; }
+
+// the partition on its own (tests): n records with vb-byte values (1, 2, 4 or 8) in device arrays
+extern "C" int bfcg_partition_records(const uint64_t *d_key_in, const void *d_val_in, uint64_t *d_key_out, void *d_val_out, uint64_t n, int vb, int begin, int end)
+{
+	int r;
+	if ((r = bfcg_rt_init()) != BFCG_OK) return r;
+	BfcgRuntime &rt = bfcg_rt();
+	if ((vb != 1 && vb != 2 && vb != 4 && vb != 8) || begin < 0 || end > 64 || end <= begin || n >= (1ULL << 30)) return BFCG_ERR_ARG;
+	size_t tb = sort_temp_bytes(vb, n, begin, end);
+	uint8_t *a = (uint8_t*)bfcg_arena(tb + 256);
+	if (!a) return BFCG_ERR_NOMEM;
+	BFCG_CUDA(sort_records(a, tb, vb, (const unsigned long long*)d_key_in, (unsigned long long*)d_key_out, d_val_in, d_val_out, n, begin, end));
+	BFCG_CUDA(cudaStreamSynchronize(rt.stream));
+	return BFCG_OK;
+}
+
 
 struct PartScratch {
 	unsigned long long *s_key; // sorted records
@@ -543,7 +576,6 @@ static int count_part_window(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_hi
 			se = sort_records(sc.tmp, tb, vb, in_key, sc.s_key, in_val, sc.s_val, n, g.pshift, g.pshift + g.pbits);
 		}
 		BFCG_CUDA(se);
-		rt.n_launches += 1 + (g.pbits + 7) / 8; // histogram + one onesweep pass per 8 bits
 		key = sc.s_key;
 	} else BFCG_CUDA(cudaMemcpyAsync(sc.s_val, in_val, n * value_bytes(vb), cudaMemcpyDeviceToDevice, rt.stream)); // the values get marked in place
 	const uint64_t run_off[2] = { 0, n };
@@ -770,7 +802,6 @@ int bfcg_enum_part_records_fmt(const bfc_opt_t *opt, const bfcg_batch_t *batch, 
 			se = sort_records(a + o_tmp, temp, vb, ep.key, (unsigned long long*)d_y0, ep.val, d_y1, nv, g.pshift, g.pshift + sort_bits);
 		}
 		BFCG_CUDA(se);
-		rt.n_launches += 1 + (sort_bits + 7) / 8;
 	} else {
 		BFCG_CUDA(cudaMemcpyAsync(d_y0, ep.key, nv * 8, cudaMemcpyDeviceToDevice, rt.stream));
 		BFCG_CUDA(cudaMemcpyAsync(d_y1, ep.val, nv * value_bytes(vb), cudaMemcpyDeviceToDevice, rt.stream));

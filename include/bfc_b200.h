@@ -176,6 +176,10 @@ int      bfcg_ch_l_pre(const bfc_ch_t *ch);
 int      bfcg_ch_capacity_log2(const bfc_ch_t *ch);
 int      bfcg_ch_clear(bfc_ch_t *ch);
 int      bfcg_ch_reserve(bfc_ch_t *ch, uint64_t n_keys);              /* pre-size for n_keys distinct keys */
+/* the count phase's stable radix partition on its own (csrc/partition.cuh): n < 2^30 records = 64-bit keys + vb-byte
+ * values (vb = 1, 2, 4, 8) in device arrays, ordered by bits [begin, end) of the key, ties in input order */
+int      bfcg_partition_records(const uint64_t *d_key_in, const void *d_val_in, uint64_t *d_key_out, void *d_val_out,
+                                uint64_t n, int vb, int begin, int end);
 /* batched lookups: y = n pairs of k-bit words (bfc_kmer_hash output); out[i] = bfc_ch_get */
 int      bfcg_ch_get_batch(const bfc_ch_t *ch, int where, uint64_t n, const uint64_t *y, int32_t *out);
 

@@ -269,6 +269,32 @@ def test_cli_discard_and_noqual_flags(bfc, tmp_path, name):
         assert len(out) == c.meta[key + "_bytes"] and hashlib.sha256(out).hexdigest() == c.meta[key + "_sha256"], key
 
 
+@pytest.mark.parametrize("n,vb,begin,end", [(1, 1, 8, 28), (4095, 1, 8, 28), (4097, 1, 8, 28), (1_000_003, 1, 8, 28), (300_000, 8, 3, 36),
+                                             (70_000, 2, 8, 19), (50_000, 4, 0, 7), (2_500_000, 1, 10, 31)])
+def test_stable_radix_partition(bfc, monkeypatch, n, vb, begin, end):
+    """csrc/partition.cuh on its own against torch's stable sort: ordered by the chosen key bits, ties in input order
+    (stream order inside a Bloom block is what the exact count rests on), values travelling with their keys."""
+    import torch
+    import ctypes as C
+    L = bfc.lib()
+    g = torch.Generator(device="cuda").manual_seed(n + vb)
+    key = torch.randint(0, 1 << 62, (n,), dtype=torch.int64, device="cuda", generator=g)
+    if n > 1000:
+        key[: n // 3] &= ~(((1 << (end - begin)) - 1) << begin) | (5 << begin)   # a long run of one digit
+    vdt = {1: torch.uint8, 2: torch.int16, 4: torch.int32, 8: torch.int64}[vb]
+    val = (torch.arange(n, device="cuda", dtype=torch.int64) * 2654435761 % 251).to(vdt)
+    ko, vo = torch.empty_like(key), torch.empty_like(val)
+    torch.cuda.synchronize()
+    for cub in (False, True):
+        if cub:
+            monkeypatch.setenv("BFC_B200_CUB_SORT", "1")  # (read once per process: only checks the call path stays valid)
+        assert L.bfcg_partition_records(C.c_void_p(key.data_ptr()), C.c_void_p(val.data_ptr()), C.c_void_p(ko.data_ptr()),
+                                        C.c_void_p(vo.data_ptr()), n, vb, begin, end) == 0
+        digit = (key >> begin) & ((1 << (end - begin)) - 1)
+        order = torch.sort(digit, stable=True).indices
+        assert torch.equal(ko, key[order]) and torch.equal(vo, val[order])
+
+
 def test_filter_occupancy_telemetry(bfc):
     """bfcg_bf_load (a working version of the reference's unused bfc_bf_load, bbf.c:65-79) against numpy on the downloaded
     filter bytes, and bfcg_bf_suggest_shift against the load formula."""
