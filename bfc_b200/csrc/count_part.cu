@@ -30,7 +30,6 @@
 #include "enum.cuh"
 #include "partition.cuh"
 #include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
 #include <algorithm>
 #include <functional>
 
@@ -617,7 +616,33 @@ static uint64_t window_positions(uint64_t n_positions, bool host, const PartGeom
 	return std::min(P, el_padded(n_positions));
 }
 
-#define ENUM_SCAN_TMP (1 << 20)
+#define ENUM_SCAN_TMP 256
+
+// exclusive prefix sum of the per-segment record counts (at most 2^17 + 1 of them): one CTA, every thread sums a
+// contiguous stretch, the stretch totals are scanned across the CTA, the stretches are written back
+__global__ void __launch_bounds__(1024) k_seg_scan(const uint32_t *cnt, uint32_t *off, uint32_t n)
+{
+	__shared__ uint32_t s_w[33];
+	const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t per = (n + 1023) / 1024, lo = tid * per < n ? tid * per : n, hi = lo + per < n ? lo + per : n;
+	uint32_t sum = 0;
+	for (uint32_t i = lo; i < hi; ++i) sum += cnt[i];
+	uint32_t inc = sum;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (unsigned)d) inc += u; }
+	if (lane == 31) s_w[warp] = inc;
+	__syncthreads();
+	if (warp == 0) {
+		const uint32_t t = s_w[lane];
+		uint32_t ti = t;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, ti, d); if (lane >= (unsigned)d) ti += u; }
+		s_w[lane] = ti - t;
+	}
+	__syncthreads();
+	uint32_t run = s_w[warp] + inc - sum;
+	for (uint32_t i = lo; i < hi; ++i) { const uint32_t c = cnt[i]; off[i] = run; run += c; }
+}
 
 // bytes of scratch enumerate_window needs for n_pos (padded) positions: per-segment counts + offsets + scan scratch
 static size_t enum_scratch_bytes(uint64_t n_pos) { return 2 * align_up((n_pos / EL_SEG + 1) * 4, 256) + ENUM_SCAN_TMP; }
@@ -628,17 +653,13 @@ static int enumerate_window(int vb, EnumLinParams ep, uint64_t n_pos, uint8_t *s
 	BfcgRuntime &rt = bfcg_rt();
 	const uint64_t n_seg = n_pos / EL_SEG;
 	uint32_t *seg_cnt = (uint32_t*)scratch, *seg_off = (uint32_t*)(scratch + align_up((n_seg + 1) * 4, 256));
-	void *scan_tmp = scratch + 2 * align_up((n_seg + 1) * 4, 256);
-	size_t scan_bytes = 0;
 	uint32_t last[2];
 	ep.seg_cnt = seg_cnt, ep.seg_off = seg_off;
 	KTime kt(KT_ENUM_LIN);
 	k_enum_count<<<(unsigned)n_seg, EL_THREADS, 0, rt.stream>>>(ep);
 	BFCG_LAUNCH_CHECK();
-	BFCG_CUDA(cub::DeviceScan::ExclusiveSum((void*)0, scan_bytes, seg_cnt, seg_off, (int)n_seg, rt.stream));
-	if (scan_bytes > ENUM_SCAN_TMP) return bfcg_fail(__func__, "scan scratch too small", cudaSuccess);
-	BFCG_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, seg_cnt, seg_off, (int)n_seg, rt.stream));
-	++rt.n_launches;
+	k_seg_scan<<<1, 1024, 0, rt.stream>>>(seg_cnt, seg_off, (uint32_t)n_seg);
+	BFCG_LAUNCH_CHECK();
 	REC_DISPATCH(vb, (k_enum_lin<VT, PK><<<(unsigned)n_seg, EL_THREADS, 0, rt.stream>>>(ep)));
 	BFCG_LAUNCH_CHECK();
 	BFCG_CUDA(cudaMemcpyAsync(&last[0], seg_cnt + n_seg - 1, 4, cudaMemcpyDeviceToHost, rt.stream));

@@ -7,8 +7,8 @@
 //   * k_rp_hist has counted every digit of every pass beforehand (one read of the keys), k_rp_scan turned the counts
 //     into the first output position of every digit;
 //   * tiles of RP_TILE records are taken in order (a ticket), each by one CTA: keys and values are read coalesced,
-//     warp w owning records [w * 256, (w + 1) * 256) of the tile, 32 at a time, in order;
-//   * the rank of a record among the records of its digit in the tile comes from __match_any_sync (peers of the same
+//     warp w owning records [w * 256, (w + 1) * 256) of the tile, 32 at a time, in order (one CTA of 1024 threads per SM);
+//   * the rank of a record among the records of its digit in the tile comes from ballots over the digit's bits (peers of the same
 //     digit inside a warp step, lower lanes first) + a per-warp running count per digit in shared memory + a scan over
 //     the warps: stream order is preserved inside every digit = the partition is STABLE, which is what keeps the
 //     records of one Bloom block in read order (the reference's -t1 semantics, count.c:54-70);
@@ -19,8 +19,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
-#define RP_THREADS 512
+#define RP_THREADS 1024                         // one thread per digit in the look-back; one CTA per SM
 #define RP_ITEMS   8
 #define RP_TILE    (RP_THREADS * RP_ITEMS)      // records per tile
 #define RP_WARPS   (RP_THREADS / 32)
@@ -118,11 +119,11 @@ struct RpPassParams {
 };
 
 template <typename VT>
-__global__ void __launch_bounds__(RP_THREADS, 2) k_rp_pass(RpPassParams<VT> p)
+__global__ void __launch_bounds__(RP_THREADS, 1) k_rp_pass(RpPassParams<VT> p)
 {
-	extern __shared__ __align__(16) unsigned char s_raw[];
+	extern __shared__ __align__(128) unsigned char s_raw[];
 	// layout: per-warp digit counts (u16) | digit starts inside the sorted tile, then output offsets (u32) | keys | values
-	uint16_t (*const s_wh)[RP_MAX_NB] = (uint16_t (*)[RP_MAX_NB])s_raw;
+	uint16_t *const s_wh = (uint16_t*)s_raw; // [warp][digit] (lanes of a warp spread over the banks by their digits)
 	uint32_t *const s_start = (uint32_t*)(s_raw + sizeof(uint16_t) * RP_WARPS * RP_MAX_NB);
 	unsigned long long *const s_key = (unsigned long long*)(s_start + RP_MAX_NB);
 	VT *const s_val = (VT*)(s_key + RP_TILE);
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(RP_THREADS, 2) k_rp_pass(RpPassParams<VT> p)
 	const uint32_t nb = 1u << p.bits, dmask = nb - 1;
 
 	if (tid == 0) s_tile = atomicAdd(p.ticket, 1u); // tiles start in order: whatever a tile waits for is already running
-	for (uint32_t i = tid; i < RP_WARPS * RP_MAX_NB / 2; i += RP_THREADS) ((uint32_t*)s_raw)[i] = 0;
+	for (uint32_t i = tid; i < RP_WARPS * RP_MAX_NB / 8; i += RP_THREADS) ((uint4*)s_raw)[i] = make_uint4(0, 0, 0, 0);
 	__syncthreads();
 	const uint64_t tile = s_tile, t0 = tile * RP_TILE;
 	const uint32_t n_tile = (uint32_t)(p.n - t0 < RP_TILE ? p.n - t0 : RP_TILE);
@@ -147,85 +148,94 @@ __global__ void __launch_bounds__(RP_THREADS, 2) k_rp_pass(RpPassParams<VT> p)
 		const bool valid = it < n_tile;
 		key[j] = valid ? __ldg(p.key_in + t0 + it) : 0ULL;
 		val[j] = valid ? __ldg(p.val_in + t0 + it) : (VT)0;
-		const uint32_t d = valid ? (uint32_t)(key[j] >> p.shift) & dmask : 0x80000000u | lane; // (a record past the end matches nobody)
-		const unsigned peers = __match_any_sync(0xffffffffu, d);
-		const int leader = __ffs(peers) - 1;
-		uint32_t before = 0;
-		if (valid && (int)lane == leader) { before = s_wh[warp][d]; s_wh[warp][d] = (uint16_t)(before + __popc(peers)); }
-		before = __shfl_sync(0xffffffffu, before, leader);
+	}
+#pragma unroll
+	for (int j = 0; j < RP_ITEMS; ++j) {
+		const uint32_t it = warp * (32 * RP_ITEMS) + j * 32 + lane;
+		const bool valid = it < n_tile;
+		const uint32_t d = valid ? (uint32_t)(key[j] >> p.shift) & dmask : 0, idx = warp * RP_MAX_NB + d;
+		// The lanes of this step that hold the same digit.  32 records over 2^bits digits: usually none do, and that is
+		// found out through the count itself -- every lane reads it, tags it with its lane number, and sees after a
+		// warp barrier whether its tag survived.  Only when some lane lost does the warp work the groups out, with one
+		// ballot per digit bit (match.any is far slower than that here).
+		const uint32_t before = valid ? s_wh[idx] : 0; // < 512: a warp holds 256 records of a tile
+		__syncwarp();
+		if (valid) s_wh[idx] = (uint16_t)(lane << 9 | before);
+		__syncwarp();
+		const bool lost = valid && (uint32_t)(s_wh[idx] >> 9) != lane;
+		unsigned peers = 1u << lane;
+		if (__any_sync(0xffffffffu, lost)) {
+			peers = __ballot_sync(0xffffffffu, valid);
+			for (int b = 0; b < p.bits; ++b) {
+				const unsigned m = __ballot_sync(0xffffffffu, d >> b & 1);
+				peers &= (d >> b & 1) ? m : ~m;
+			}
+			if (!valid) peers = 1u << lane; // (a record past the end matches nobody)
+		}
+		__syncwarp();
+		if (valid && (int)lane == __ffs(peers) - 1) s_wh[idx] = (uint16_t)(before + __popc(peers));
 		dr[j] = valid ? d | (before + __popc(peers & ((1u << lane) - 1))) << 16 : 0xffffffffu;
 		__syncwarp();
 	}
 	__syncthreads();
 
-	// ---- per digit: counts of the warps -> offsets of the warps; count of the tile
-	uint32_t cnt[RP_MAX_NB / RP_THREADS];
-#pragma unroll
-	for (int q = 0; q < RP_MAX_NB / RP_THREADS; ++q) {
-		const uint32_t d = tid + q * RP_THREADS;
-		uint32_t acc = 0;
-		if (d < nb) {
-#pragma unroll
-			for (int w = 0; w < RP_WARPS; ++w) { const uint32_t c = s_wh[w][d]; s_wh[w][d] = (uint16_t)acc; acc += c; }
-		}
-		cnt[q] = acc;
+	// ---- digit `tid`: counts of the warps -> offsets of the warps; count of the tile
+	uint32_t cnt = 0;
+	if (tid < nb) {
+#pragma unroll 8
+		for (int w = 0; w < RP_WARPS; ++w) { const uint32_t c = s_wh[w * RP_MAX_NB + tid]; s_wh[w * RP_MAX_NB + tid] = (uint16_t)cnt; cnt += c; }
 	}
-	// ---- publish the tile's counts, look back for its offset inside every digit, publish the running totals
-	uint32_t excl[RP_MAX_NB / RP_THREADS];
+	// ---- publish the tile's count, look back for its offset inside the digit, publish the running total.  The earlier
+	// tiles are read four at a time (the reads of a walk are independent; only the decisions are in order).
+	uint32_t excl = 0;
+	if (tid < nb) {
+		volatile uint32_t *st = p.status + tid;
+		st[tile * nb] = cnt | (tile == 0 ? RP_PREFIX : RP_AGG);
+		int64_t t = (int64_t)tile - 1;
+		bool done = t < 0;
+		while (!done) {
+			uint32_t v[4];
 #pragma unroll
-	for (int q = 0; q < RP_MAX_NB / RP_THREADS; ++q) {
-		const uint32_t d = tid + q * RP_THREADS;
-		excl[q] = 0;
-		if (d < nb) {
-			volatile uint32_t *st = p.status + d;
-			st[tile * nb] = cnt[q] | (tile == 0 ? RP_PREFIX : RP_AGG);
-			for (int64_t t = (int64_t)tile - 1; t >= 0; --t) {
-				uint32_t v;
-				do { v = st[(uint64_t)t * nb]; } while ((v & (RP_AGG | RP_PREFIX)) == 0);
-				excl[q] += v & RP_VALUE;
-				if (v & RP_PREFIX) break;
+			for (int q = 0; q < 4; ++q) v[q] = t - q >= 0 ? st[(uint64_t)(t - q) * nb] : RP_PREFIX;
+#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				if (done) break;
+				if ((v[q] & (RP_AGG | RP_PREFIX)) == 0) break; // not published yet: read again from here
+				excl += v[q] & RP_VALUE;
+				--t;
+				if ((v[q] & RP_PREFIX) || t < 0) done = true;
 			}
-			if (tile) st[tile * nb] = ((excl[q] + cnt[q]) & RP_VALUE) | RP_PREFIX;
 		}
+		if (tile) st[tile * nb] = ((excl + cnt) & RP_VALUE) | RP_PREFIX;
 	}
 	// ---- where every digit starts inside the tile once it is in digit order (exclusive scan of the counts)
 	{
-		uint32_t local = 0, mine[RP_MAX_NB / RP_THREADS];
-		// thread tid holds digits tid and tid + RP_THREADS: scan the low half first, then the high half on top of it
+		uint32_t inc = cnt;
 #pragma unroll
-		for (int q = 0; q < RP_MAX_NB / RP_THREADS; ++q) {
-			uint32_t inc = cnt[q];
+		for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (unsigned)d) inc += u; }
+		if (lane == 31) s_scan[warp] = inc;
+		__syncthreads();
+		if (warp == 0) {
+			const uint32_t tsum = s_scan[lane];
+			uint32_t ti = tsum;
 #pragma unroll
-			for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (unsigned)d) inc += u; }
-			if (lane == 31) s_scan[warp] = inc;
-			__syncthreads();
-			if (tid == 0) { uint32_t run = local; for (int w = 0; w < RP_WARPS; ++w) { const uint32_t t = s_scan[w]; s_scan[w] = run; run += t; } s_scan[RP_WARPS] = run; }
-			__syncthreads();
-			mine[q] = s_scan[warp] + inc - cnt[q];
-			local = s_scan[RP_WARPS];
-			__syncthreads();
+			for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, ti, d); if (lane >= (unsigned)d) ti += u; }
+			s_scan[lane] = ti - tsum;
 		}
-#pragma unroll
-		for (int q = 0; q < RP_MAX_NB / RP_THREADS; ++q) {
-			const uint32_t d = tid + q * RP_THREADS;
-			if (d < nb) s_start[d] = mine[q];
-		}
+		__syncthreads();
+		if (tid < nb) s_start[tid] = s_scan[warp] + inc - cnt;
 	}
 	__syncthreads();
 	// ---- into digit order in shared memory (stable: digit start + offset of the warp + rank inside the warp)
 #pragma unroll
 	for (int j = 0; j < RP_ITEMS; ++j)
 		if (dr[j] != 0xffffffffu) {
-			const uint32_t d = dr[j] & 0xffff, at = s_start[d] + s_wh[warp][d] + (dr[j] >> 16);
+			const uint32_t d = dr[j] & 0xffff, at = s_start[d] + s_wh[warp * RP_MAX_NB + d] + (dr[j] >> 16);
 			s_key[at] = key[j], s_val[at] = val[j];
 		}
 	__syncthreads();
 	// s_start[d] becomes: output position of the digit's first record of this tile - its position in the tile
-#pragma unroll
-	for (int q = 0; q < RP_MAX_NB / RP_THREADS; ++q) {
-		const uint32_t d = tid + q * RP_THREADS;
-		if (d < nb) s_start[d] = __ldg(p.base + d) + excl[q] - s_start[d];
-	}
+	if (tid < nb) s_start[tid] = __ldg(p.base + tid) + excl - s_start[tid];
 	__syncthreads();
 	for (uint32_t i = tid; i < n_tile; i += RP_THREADS) {
 		const unsigned long long k = s_key[i];
