@@ -273,27 +273,6 @@ __device__ __forceinline__ void extract_kmer(const EcParams &P, int64_t o, int n
 
 // ------------------------------------------------------------------ K6a: per-read setup
 
-// reference correct.c:63-80
-__device__ int ec_greedy_k(const EcParams &P, const uint64_t x[4], unsigned long long &n_lookups)
-{
-	const int k = P.k;
-	int max = 0, max_ec = -1, max2 = 0;
-	for (int i = 0; i < k; ++i) {
-		const int c = (int)((x[1] >> i & 1) << 1 | (x[0] >> i & 1));
-		for (int j = 0; j < 4; ++j) {
-			if (j == c) continue;
-			uint64_t y[4] = { x[0], x[1], x[2], x[3] };
-			bfc_kmer_change(k, y, i, j);
-			const int ret = tab_kmer_occ(P.tab, y);
-			++n_lookups;
-			if (ret < 0) continue;
-			if ((max & 0xff) < (ret & 0xff)) max2 = max, max = ret, max_ec = i << 2 | j;
-			else if ((max2 & 0xff) < (ret & 0xff)) max2 = ret;
-		}
-	}
-	return (max & 0xff) * 3 > P.mode && (max2 & 0xff) < 3 ? max_ec : -1;
-}
-
 // reference correct.c:82-94: position of the k-th base of the first run of k ACGT bases at or after `start` (n if none)
 __device__ int ec_first_kmer_end(const EcParams &P, int64_t o, int n, int start)
 {
@@ -349,26 +328,77 @@ __global__ void __launch_bounds__(128) k_ec_setup(EcParams P)
 			}
 			if (l > max) max = l, max_i = n;
 			if (max > 0) d.start0 = max_i - max - k + 1, d.start1 = n - max_i;
-			else { // no solid k-mer: single-edit rescue (correct.c:405-421)
-				int start = 0, end, ec = -1;
-				while ((end = ec_first_kmer_end(P, o, n, start)) < n) {
-					uint64_t x[4];
-					extract_kmer(P, o, n, 0, end, k, -1, 0, x);
-					ec = ec_greedy_k(P, x, n_lookups);
-					if (ec >= 0) break;
-					if (end + (k >> 1) >= n) break;
-					start = end - (k >> 1);
-				}
-				if (ec >= 0) {
-					d.brute = (end - (ec >> 2)) << 2 | (ec & 3);
-					++end;
-					d.start0 = end - k, d.start1 = n - end;
-				} else d.code = 3;
+			else { // no solid k-mer: the single-edit rescue (correct.c:405-421) tries 3k edits per k-mer -- a warp's job (k_ec_rescue)
+				P.overflow[atomicAdd(P.ctr + 4, 1ULL)] = (uint32_t)r; // (the search's overflow list is not in use yet)
+				d.code = 3;                                           // until the rescue finds an edit
 			}
 		}
 		P.desc[r] = d;
 		P.jobs[2 * r] = make_int4((int)o, n, d.start0, d.brute);
 		P.jobs[2 * r + 1] = make_int4((int)o, n, d.start0 < 0 ? -1 : d.start1, d.brute);
+	}
+	block_add(P.ctr + 1, n_lookups);
+}
+
+// ------------------------------------------------------------------ K6a+: the single-edit rescue, one read per warp
+
+// bfc_ec_greedy_k (correct.c:63-80) tries every single-base edit of a k-mer -- 3k lookups -- and bfc_ec1 walks the read
+// in steps of k/2 until an edit is accepted (correct.c:405-421).  The lanes of a warp share the 3k lookups of one k-mer;
+// what the sequential loop keeps -- the FIRST edit (in its i, j order) with the largest count, and the second-largest
+// count, equal counts included -- is order-free apart from that "first", so it reduces across lanes exactly.
+__global__ void __launch_bounds__(256) k_ec_rescue(EcParams P)
+{
+	const unsigned lane = threadIdx.x & 31;
+	const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+	const uint64_t n_list = P.ctr[4];
+	const int k = P.k;
+	unsigned long long n_lookups = 0;
+	for (uint64_t li = warp; li < n_list; li += n_warps) {
+		const int64_t r = (int64_t)P.overflow[li];
+		const uint64_t ob = P.off[r];
+		const int64_t o = (int64_t)(ob - P.base0);
+		const int n = (int)(P.off[r + 1] - ob - 1);
+		int start = 0, end, ec = -1;
+		while ((end = ec_first_kmer_end(P, o, n, start)) < n) {
+			uint64_t x[4];
+			extract_kmer(P, o, n, 0, end, k, -1, 0, x);
+			// candidate t = i * 4 + j: base i of the k-mer (kmer.h bit order) changed to j, the sequential loop's order
+			int best = 0, best_id = -1, second = 0;
+			for (int t = (int)lane; t < 4 * k; t += 32) {
+				const int i = t >> 2, j = t & 3, c = (int)((x[1] >> i & 1) << 1 | (x[0] >> i & 1));
+				if (j == c) continue;
+				uint64_t y[4] = { x[0], x[1], x[2], x[3] };
+				bfc_kmer_change(k, y, i, j);
+				const int ret = tab_kmer_occ(P.tab, y);
+				++n_lookups;
+				if (ret < 0) continue;
+				const int cnt = ret & 0xff;
+				if (cnt > best) second = best, best = cnt, best_id = t;
+				else if (cnt > second) second = cnt;
+			}
+			for (int s = 16; s > 0; s >>= 1) { // merge the lanes' (largest, where first, second largest)
+				const int ob_ = __shfl_xor_sync(0xffffffffu, best, s), oi = __shfl_xor_sync(0xffffffffu, best_id, s), os = __shfl_xor_sync(0xffffffffu, second, s);
+				if (ob_ > best) second = best > os ? best : os, best = ob_, best_id = oi;
+				else if (ob_ < best) second = second > ob_ ? second : ob_;
+				else { // the same largest count on both sides: it is also the second largest; the earlier edit stays
+					second = best;
+					if (oi >= 0 && (best_id < 0 || oi < best_id)) best_id = oi;
+				}
+			}
+			ec = best * 3 > P.mode && second < 3 ? best_id : -1; // correct.c:79 (best_id = i << 2 | j)
+			if (ec >= 0) break;
+			if (end + (k >> 1) >= n) break;
+			start = end - (k >> 1);
+		}
+		if (lane == 0 && ec >= 0) {
+			ReadDesc d;
+			d.brute = (end - (ec >> 2)) << 2 | (ec & 3);
+			++end;
+			d.start0 = end - k, d.start1 = n - end, d.code = 0;
+			P.desc[r] = d;
+			P.jobs[2 * r] = make_int4((int)o, n, d.start0, d.brute);
+			P.jobs[2 * r + 1] = make_int4((int)o, n, d.start1, d.brute);
+		}
 	}
 	block_add(P.ctr + 1, n_lookups);
 }
@@ -1522,7 +1552,9 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 			KTime kt(KT_EC_SETUP);
 			k_ec_cov<<<(unsigned)((n_rec / 32 + 255) / 256), 256, 0, rt.stream>>>(P, n_rec, (uint16_t*)(a + o_fl), (uint64_t*)(a + o_pl));
 			k_ec_setup<<<(unsigned)((nr + 127) / 128), 128, 0, rt.stream>>>(P);
+			k_ec_rescue<<<rt.sm_count * 8, 256, 0, rt.stream>>>(P);
 		}
+		++rt.n_launches;
 		BFCG_LAUNCH_CHECK();
 		++rt.n_launches;
 		if (P.ext) {
