@@ -1,7 +1,7 @@
 /* correct_host.c -- bfc_correct(): the correction / trimming driver (interface:
- * reference bfc.h:40; shape: reference correct.c:573-655).  Three-step kt_pipeline as
- * in the reference: read | correct on the GPU (bfcg_correct_batch / bfcg_trim_batch
- * replace kt_for(worker_ec)) | print.  The printer reproduces correct.c:591-611 byte
+ * reference bfc.h:40; shape: reference correct.c:573-655).  The reference's three-step
+ * kt_pipeline with the packing as a step of its own: read | pack into a pinned flat batch | correct on the GPU
+ * (bfcg_correct_batch / bfcg_trim_batch replace kt_for(worker_ec)) | print.  The printer reproduces correct.c:591-611 byte
  * for byte, including the ec:Z: tag. */
 #include <stdio.h>
 #include <stdlib.h>
@@ -10,7 +10,7 @@
 #include "bfc_b200.h"
 #include "fqblock.h"
 
-#define N_FLAT 3 /* a batch's flat buffers live from step 1 (GPU) to the end of step 2 (write) */
+#define N_FLAT 4 /* = the batches in flight: a batch's flat buffers live from step 1 (pack) to the end of step 3 (write) */
 
 typedef struct {
 	const bfc_opt_t *opt;
@@ -56,12 +56,13 @@ static void parse_ec_tag(const char *s, size_t l, uint32_t ori[2])
 	}
 }
 
-static void ec_step1(ec_shared_t *es, ec_step_t *data)
+#define STAMP(what) do { if (bfc_verbose >= 4) fprintf(stderr, "[D::%s @%.3f] %s\n", __func__, realtime() - bfc_real_time, what); } while (0)
+
+static void ec_pack(ec_shared_t *es, ec_step_t *data)
 {
 	const bfc_opt_t *opt = es->opt;
 	const size_t n = (size_t)data->blk.n;
 	uint8_t *skip = 0;
-	int rc = BFCG_OK;
 	data->flat = &es->flat[es->n_batches++ % N_FLAT];
 	if (!opt->filter_mode) data->aux = (uint32_t*)malloc((n ? n : 1) * 2 * sizeof(uint32_t));
 	if (opt->refine_ec && !opt->filter_mode) { /* worker_ec's refine branch (correct.c:542-550), in read order */
@@ -81,6 +82,14 @@ static void ec_step1(ec_shared_t *es, ec_step_t *data)
 		exit(1);
 	}
 	free(skip);
+	STAMP("batch packed");
+}
+
+static void ec_gpu(ec_shared_t *es, ec_step_t *data)
+{
+	const bfc_opt_t *opt = es->opt;
+	const size_t n = (size_t)data->blk.n;
+	int rc = BFCG_OK;
 	if (!opt->filter_mode) {
 		if (data->flat->b.n_reads) rc = bfcg_correct_batch(opt, es->ch, es->mode, &data->flat->b, data->aux, &es->stats);
 	} else {
@@ -101,20 +110,27 @@ static void *ec_cb(void *shared, int step, void *_data)
 		ec_step_t *ret = (ec_step_t*)calloc(1, sizeof(ec_step_t));
 		const int keep_comment = (es->opt->filter_mode || es->opt->refine_ec);
 		const int ok = fq_next(es->ks, batch_text_bytes(es->opt), keep_comment, &ret->blk);
+		STAMP("block read and split");
 		if (ok < 0) { fprintf(stderr, "[E::%s] out of host memory while reading\n", "bfc_correct"); exit(1); }
 		fprintf(stderr, "[M::%s] read %ld sequences\n", "bfc_ec_cb", (long)ret->blk.n);
 		if (ok) return ret;
 		free(ret);
 	} else if (step == 1) {
+		ec_pack(es, (ec_step_t*)_data);
+		return _data;
+	} else if (step == 2) {
 		ec_step_t *data = (ec_step_t*)_data;
-		ec_step1(es, data);
+		STAMP("batch taken");
+		ec_gpu(es, data);
+		STAMP("batch corrected");
 		fprintf(stderr, "[M::%s @%.1f*%.1f%%] processed %ld sequences\n", "bfc_ec_cb", realtime() - bfc_real_time,
 				100. * cputime() / (realtime() - bfc_real_time + 1e-6), (long)data->blk.n);
 		return data;
-	} else if (step == 2) { /* correct.c:591-616 */
+	} else if (step == 3) { /* correct.c:591-616 */
 		ec_step_t *data = (ec_step_t*)_data;
 		fq_out_t o;
 		memset(&o, 0, sizeof(o));
+		STAMP("write begins");
 		o.filter_mode = es->opt->filter_mode, o.discard = es->opt->discard, o.no_qual = es->opt->no_qual;
 		o.refine = es->opt->refine_ec && !es->opt->filter_mode;
 		o.aux = data->aux, o.keep = data->keep, o.tstart = data->ts, o.tend = data->te;
@@ -122,6 +138,7 @@ static void *ec_cb(void *shared, int step, void *_data)
 			fprintf(stderr, "[E::%s] writing the output failed\n", "bfc_correct");
 			exit(1);
 		}
+		STAMP("batch written");
 		fq_block_free(&data->blk);
 		free(data->aux); free(data->keep); free(data->ts); free(data->te);
 		free(data);
@@ -153,7 +170,7 @@ void bfc_correct(const char *fn, const bfc_opt_t *opt, const void *ptr)
 		fprintf(stderr, "[E::%s] cannot open '%s'\n", __func__, fn);
 		exit(1);
 	}
-	kt_pipeline(opt->no_mt_io ? 1 : 3, ec_cb, &es, 3);
+	kt_pipeline(opt->no_mt_io ? 1 : N_FLAT, ec_cb, &es, 4);
 	fq_close(es.ks);
 	{ int i; for (i = 0; i < N_FLAT; ++i) fq_flat_free(&es.flat[i]); }
 	if (bfc_verbose >= 3 && !opt->filter_mode)

@@ -1,25 +1,35 @@
 /* count_host.c -- bfc_count(): the count-phase driver (interface: reference bfc.h:39;
- * shape: reference count.c:91-157).  The host keeps the reference's two-step
- * kt_pipeline (read a batch | count it); batches are blocks of input text split by all -t
- * threads (fqblock.c), and what the reference does inside kt_for(worker_count) is one
+ * shape: reference count.c:91-157).  The reference's two-step kt_pipeline (read a batch | count it) becomes
+ * three steps -- read and split a block of text | pack it into a pinned flat batch | count it on the GPU -- so that
+ * the host's packing of batch i+1 runs beside the GPU's work on batch i; batches are blocks of input text split by
+ * all -t threads (fqblock.c), and what the reference does inside kt_for(worker_count) is one
  * bfcg_count_batch() call on the GPU.  Progress lines on
  * stderr keep the reference's wording (count.c:98, 110-115). */
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <sys/stat.h>
 #include "bfc.h"
 #include "bfc_b200.h"
 #include "fqblock.h"
+
+#define N_FLAT 3 /* = the batches the pipeline keeps in flight */
 
 typedef struct {
 	const bfc_opt_t *opt;
 	fq_reader_t *ks;
 	bfc_bf_t *bf, *bf_high;
 	bfc_ch_t *ch;
-	fq_flat_t flat;        /* pinned, reused by every batch (step 1 never overlaps itself) */
+	fq_flat_t flat[N_FLAT]; /* pinned, reused round robin: a batch holds one from step 1 (pack) to the end of step 2 (GPU) */
+	long n_batches;
 	bfcg_stats_t stats;
 } cnt_shared_t;
+
+typedef struct {
+	fq_block_t blk;
+	fq_flat_t *flat;
+} cnt_step_t;
 
 /* text per batch: the reference batches by bases (-L, count.c:103); here a batch is a block of input text -- 250 MB
  * at the default -L: the GPU's per-batch costs (one sweep of the filter and of the table, ~10 ms) stay far below what
@@ -27,33 +37,53 @@ typedef struct {
  * that filling the pool with first-touch pages is over after a fraction of a second */
 static size_t batch_text_bytes(const bfc_opt_t *opt) { return (size_t)opt->chunk_size * 5 / 2; }
 
+/* a regular file smaller than that is not worth a thread that pins buffers ahead; pipes and "-" count as big */
+static int input_is_big(const char *fn, size_t bytes)
+{
+	struct stat st;
+	if (fn == 0 || strcmp(fn, "-") == 0 || stat(fn, &st) != 0 || !S_ISREG(st.st_mode)) return 1;
+	return (size_t)st.st_size >= bytes;
+}
+
+#define STAMP(what) do { if (bfc_verbose >= 4) fprintf(stderr, "[D::%s @%.3f] %s\n", __func__, realtime() - bfc_real_time, what); } while (0)
+
 static void *count_cb(void *shared, int step, void *_data)
 {
 	cnt_shared_t *cs = (cnt_shared_t*)shared;
 	if (step == 0) {
-		fq_block_t *blk = (fq_block_t*)calloc(1, sizeof(fq_block_t));
-		const int ok = fq_next(cs->ks, batch_text_bytes(cs->opt), 0, blk);
+		cnt_step_t *d = (cnt_step_t*)calloc(1, sizeof(cnt_step_t));
+		const int ok = fq_next(cs->ks, batch_text_bytes(cs->opt), 0, &d->blk);
+		STAMP("block read and split");
 		if (ok < 0) { fprintf(stderr, "[E::%s] out of host memory while reading\n", "bfc_count"); exit(1); }
-		fprintf(stderr, "[M::%s] read %ld sequences\n", "bfc_count_cb", (long)blk->n);
-		if (ok) return blk;
-		free(blk);
+		fprintf(stderr, "[M::%s] read %ld sequences\n", "bfc_count_cb", (long)d->blk.n);
+		if (ok) return d;
+		free(d);
 	} else if (step == 1) {
-		fq_block_t *blk = (fq_block_t*)_data;
+		cnt_step_t *d = (cnt_step_t*)_data;
+		d->flat = &cs->flat[cs->n_batches++ % N_FLAT];
+		if (fq_flat_fill(d->flat, &d->blk, 0, cs->opt->n_threads) < 0) {
+			fprintf(stderr, "[E::%s] out of host memory while packing\n", "bfc_count");
+			exit(1);
+		}
+		STAMP("batch packed");
+		return d;
+	} else if (step == 2) {
+		cnt_step_t *d = (cnt_step_t*)_data;
 		double rt, eff;
-		if (fq_flat_fill(&cs->flat, blk, 0, cs->opt->n_threads) < 0 ||
-			bfcg_count_batch(cs->opt, cs->bf, cs->bf_high, cs->ch, &cs->flat.b, &cs->stats) != BFCG_OK) {
+		if (bfcg_count_batch(cs->opt, cs->bf, cs->bf_high, cs->ch, &d->flat->b, &cs->stats) != BFCG_OK) {
 			fprintf(stderr, "[E::%s] GPU count failed: %s\n", "bfc_count", bfcg_last_error());
 			exit(1);
 		}
+		STAMP("batch counted");
 		rt = realtime() - bfc_real_time;
 		eff = 100. * cputime() / (rt + 1e-6);
 		if (cs->ch)
 			fprintf(stderr, "[M::%s @%.1f*%.1f%%] processed %ld sequences; # distinct k-mers: %ld\n",
-					"bfc_count_cb", rt, eff, (long)blk->n, (long)bfc_ch_count(cs->ch));
+					"bfc_count_cb", rt, eff, (long)d->blk.n, (long)bfc_ch_count(cs->ch));
 		else
-			fprintf(stderr, "[M::%s @%.1f*%.1f%%] processed %ld sequences\n", "bfc_count_cb", rt, eff, (long)blk->n);
-		fq_block_free(blk);
-		free(blk);
+			fprintf(stderr, "[M::%s @%.1f*%.1f%%] processed %ld sequences\n", "bfc_count_cb", rt, eff, (long)d->blk.n);
+		fq_block_free(&d->blk);
+		free(d);
 	}
 	return 0;
 }
@@ -64,7 +94,11 @@ void *bfc_count(const char *fn, const bfc_opt_t *opt)
 	void *ret;
 	memset(&cs, 0, sizeof(cs));
 	cs.opt = opt;
+	STAMP("start");
+	if (!opt->no_mt_io && input_is_big(fn, 2 * batch_text_bytes(opt)))
+		fq_flat_prewarm(batch_text_bytes(opt), 4); /* beside the allocation of the filter; bfc_correct inherits them */
 	cs.bf = bfc_bf_init(opt->bf_shift, opt->n_hashes);
+	STAMP("filter allocated");
 	if (cs.bf == 0) {
 		fprintf(stderr, "[E::%s] cannot create the Bloom filter (-b %d): %s\n", __func__, opt->bf_shift, bfcg_last_error());
 		exit(1);
@@ -75,14 +109,16 @@ void *bfc_count(const char *fn, const bfc_opt_t *opt)
 		fprintf(stderr, "[E::%s] cannot create the k-mer table / second filter: %s\n", __func__, bfcg_last_error());
 		exit(1);
 	}
+	STAMP("table allocated");
 	cs.ks = fq_open(fn, opt->n_threads);
 	if (cs.ks == 0) {
 		fprintf(stderr, "[E::%s] cannot open '%s'\n", __func__, fn);
 		exit(1);
 	}
-	kt_pipeline(opt->no_mt_io ? 1 : 2, count_cb, &cs, 2);
+	kt_pipeline(opt->no_mt_io ? 1 : N_FLAT, count_cb, &cs, 3);
+	fq_flat_prewarm_finish();
 	fq_close(cs.ks);
-	fq_flat_free(&cs.flat);
+	{ int i; for (i = 0; i < N_FLAT; ++i) fq_flat_free(&cs.flat[i]); }
 	if (bfc_verbose >= 3)
 		fprintf(stderr, "[M::%s] k-mer occurrences: %llu; passed the first filter: %llu; replayed in order: %llu\n", __func__,
 				(unsigned long long)cs.stats.n_kmers, (unsigned long long)cs.stats.n_pass, (unsigned long long)cs.stats.n_conflict);

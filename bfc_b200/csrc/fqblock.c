@@ -395,28 +395,95 @@ static void fill_worker(void *data, long i, int tid)
 	}
 }
 
-/* pinning host memory costs ~0.3 s per GB: buffers released by one phase are parked here for the next one */
+/* pinning host memory costs 0.3-0.7 s per GB: buffers released by one phase are parked here for the next one, and
+ * fq_flat_prewarm() fills the park from a thread of its own while the caller is still busy creating the filter */
 #define FLAT_CACHE 4
 static struct { uint8_t *seq, *qual; size_t cap; } flat_cache[FLAT_CACHE];
+static pthread_mutex_t flat_mu = PTHREAD_MUTEX_INITIALIZER;
+static pthread_cond_t flat_cv = PTHREAD_COND_INITIALIZER;
+static int flat_coming;         /* buffer pairs the prewarm thread has yet to deliver */
+static int flat_running;        /* the prewarm thread is alive */
+static size_t flat_coming_cap;
 
 static int flat_cache_take(fq_flat_t *f, size_t need)
 {
-	int i;
-	for (i = 0; i < FLAT_CACHE; ++i)
-		if (flat_cache[i].seq && flat_cache[i].cap >= need) {
-			f->seq_buf = flat_cache[i].seq, f->qual_buf = flat_cache[i].qual, f->cap_bytes = flat_cache[i].cap, f->pinned = 1;
-			flat_cache[i].seq = 0;
-			return 1;
-		}
-	return 0;
+	int i, got = 0;
+	pthread_mutex_lock(&flat_mu);
+	for (;;) {
+		for (i = 0; i < FLAT_CACHE && !got; ++i)
+			if (flat_cache[i].seq && flat_cache[i].cap >= need) {
+				f->seq_buf = flat_cache[i].seq, f->qual_buf = flat_cache[i].qual, f->cap_bytes = flat_cache[i].cap, f->pinned = 1;
+				flat_cache[i].seq = 0;
+				got = 1;
+			}
+		if (got || flat_coming == 0 || flat_coming_cap < need) break;
+		pthread_cond_wait(&flat_cv, &flat_mu); /* one that fits is on its way */
+	}
+	pthread_mutex_unlock(&flat_mu);
+	return got;
 }
 
 static int flat_cache_put(uint8_t *seq, uint8_t *qual, size_t cap)
 {
-	int i;
-	for (i = 0; i < FLAT_CACHE; ++i)
-		if (flat_cache[i].seq == 0) { flat_cache[i].seq = seq, flat_cache[i].qual = qual, flat_cache[i].cap = cap; return 1; }
+	int i, put = 0;
+	pthread_mutex_lock(&flat_mu);
+	for (i = 0; i < FLAT_CACHE && !put; ++i)
+		if (flat_cache[i].seq == 0) flat_cache[i].seq = seq, flat_cache[i].qual = qual, flat_cache[i].cap = cap, put = 1;
+	pthread_mutex_unlock(&flat_mu);
+	return put;
+}
+
+static void *prewarm_main(void *arg)
+{
+	const size_t cap = flat_coming_cap;
+	(void)arg;
+	for (;;) {
+		uint8_t *seq, *qual;
+		int left;
+		pthread_mutex_lock(&flat_mu);
+		left = flat_coming;
+		if (left == 0) { flat_running = 0; pthread_cond_broadcast(&flat_cv); }
+		pthread_mutex_unlock(&flat_mu);
+		if (left == 0) break;
+		seq = (uint8_t*)bfcg_host_alloc_pinned(cap);
+		qual = seq ? (uint8_t*)bfcg_host_alloc_pinned(cap) : 0;
+		if (seq && qual && flat_cache_put(seq, qual, cap)) {
+			pthread_mutex_lock(&flat_mu);
+			if (flat_coming > 0) --flat_coming;
+		} else { /* no memory, or nowhere to park it: the packer allocates for itself */
+			if (seq) bfcg_host_free_pinned(seq);
+			if (qual) bfcg_host_free_pinned(qual);
+			pthread_mutex_lock(&flat_mu);
+			flat_coming = 0;
+		}
+		pthread_cond_broadcast(&flat_cv);
+		pthread_mutex_unlock(&flat_mu);
+	}
 	return 0;
+}
+
+void fq_flat_prewarm(size_t text_bytes, int n)
+{
+	pthread_t t;
+	pthread_attr_t at;
+	pthread_mutex_lock(&flat_mu);
+	if (!flat_running && n > 0) {
+		flat_coming = n < FLAT_CACHE ? n : FLAT_CACHE, flat_running = 1;
+		flat_coming_cap = text_bytes / 16 * 9; /* bases + one byte per read of a block of four-line FASTQ, with head-room */
+		pthread_attr_init(&at);
+		pthread_attr_setdetachstate(&at, PTHREAD_CREATE_DETACHED);
+		if (pthread_create(&t, &at, prewarm_main, 0) != 0) flat_coming = 0, flat_running = 0;
+		pthread_attr_destroy(&at);
+	}
+	pthread_mutex_unlock(&flat_mu);
+}
+
+void fq_flat_prewarm_finish(void)
+{
+	pthread_mutex_lock(&flat_mu);
+	flat_coming = 0; /* whatever it is allocating right now is its last */
+	while (flat_running) pthread_cond_wait(&flat_cv, &flat_mu);
+	pthread_mutex_unlock(&flat_mu);
 }
 
 int fq_flat_fill(fq_flat_t *f, const fq_block_t *b, const uint8_t *skip, int n_threads)

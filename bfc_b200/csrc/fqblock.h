@@ -59,6 +59,9 @@ typedef struct {
 /* skip: NULL, or one byte per record, non-zero = the record does not go into the batch.  0 ok, -1 out of memory */
 int  fq_flat_fill(fq_flat_t *f, const fq_block_t *blk, const uint8_t *skip, int n_threads);
 void fq_flat_free(fq_flat_t *f);
+/* starts pinning n buffer pairs for batches of text_bytes of input on a thread of its own; fq_flat_fill picks them up */
+void fq_flat_prewarm(size_t text_bytes, int n);
+void fq_flat_prewarm_finish(void);  /* stops it after the pair it is working on and waits for it: call before the phase returns */
 
 /* the writer of correct.c:591-611 over a block + the (corrected / trimmed) flat batch: formats on n_threads
  * threads, then writes the pieces in order.  aux/aux2 as packed by worker_ec (correct.c:552-553); in filter mode
