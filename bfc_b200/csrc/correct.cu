@@ -1407,7 +1407,10 @@ extern "C" int bfcg_correct_batch(const bfc_opt_t *opt, const bfc_ch_t *ch, int 
 	const bool host = batch->where == BFCG_HOST;
 	const int64_t n = batch->n_reads;
 
-	const uint64_t limit = batch_bytes_limit();
+	// a host batch is cut into at least three windows (of at least 16 MB) so that its copies in and out overlap the
+	// search even when it is small (the command line's batches are ~120 MB)
+	uint64_t limit = batch_bytes_limit();
+	if (host && getenv("BFC_B200_EC_BATCH") == 0) limit = std::min<uint64_t>(limit, std::max<uint64_t>((uint64_t)16 << 20, batch->n_bytes / 3 + 1));
 	// windows of at most `limit` bytes / 2^30 reads, cut at read boundaries; for a device batch the cuts are
 	// found on the device (one thread, a binary search per window) so the offsets never travel to the host
 	std::vector<uint64_t> cut_r, cut_b; // read index / byte offset of every window start, plus the end

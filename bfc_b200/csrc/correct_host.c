@@ -19,6 +19,7 @@ typedef struct {
 	const bfc_ch_t *ch;
 	int mode;
 	long n_batches;
+	long kept, next_kept;   /* blocks the count pass kept for this file (-1: none, read it again) */
 	uint32_t ori[2];        /* -R: the stats of the latest tagged read (e->ori_st of the reference, correct.c:176, 543) */
 	fq_flat_t flat[N_FLAT];
 	bfcg_stats_t stats;
@@ -64,6 +65,7 @@ static void ec_pack(ec_shared_t *es, ec_step_t *data)
 	const size_t n = (size_t)data->blk.n;
 	uint8_t *skip = 0;
 	data->flat = &es->flat[es->n_batches++ % N_FLAT];
+	STAMP("pack begins");
 	if (!opt->filter_mode) data->aux = (uint32_t*)malloc((n ? n : 1) * 2 * sizeof(uint32_t));
 	if (opt->refine_ec && !opt->filter_mode) { /* worker_ec's refine branch (correct.c:542-550), in read order */
 		const fq_block_t *b = &data->blk;
@@ -109,7 +111,10 @@ static void *ec_cb(void *shared, int step, void *_data)
 	if (step == 0) {
 		ec_step_t *ret = (ec_step_t*)calloc(1, sizeof(ec_step_t));
 		const int keep_comment = (es->opt->filter_mode || es->opt->refine_ec);
-		const int ok = fq_next(es->ks, batch_text_bytes(es->opt), keep_comment, &ret->blk);
+		int ok;
+		STAMP("read begins");
+		if (es->kept >= 0) ok = fq_keep_take(es->next_kept++, &ret->blk);
+		else ok = fq_next(es->ks, batch_text_bytes(es->opt), keep_comment, &ret->blk);
 		STAMP("block read and split");
 		if (ok < 0) { fprintf(stderr, "[E::%s] out of host memory while reading\n", "bfc_correct"); exit(1); }
 		fprintf(stderr, "[M::%s] read %ld sequences\n", "bfc_ec_cb", (long)ret->blk.n);
@@ -165,13 +170,18 @@ void bfc_correct(const char *fn, const bfc_opt_t *opt, const void *ptr)
 				else fprintf(stderr, "[M::%s] %3d : %llu\n", __func__, i, (unsigned long long)hist[i]);
 			}
 	} else es.bf = (const bfc_bf_t*)ptr;
-	es.ks = fq_open(fn, opt->n_threads);
-	if (es.ks == 0) {
-		fprintf(stderr, "[E::%s] cannot open '%s'\n", __func__, fn);
-		exit(1);
-	}
+	es.kept = fq_keep_match(fn, opt->filter_mode || opt->refine_ec);
+	if (es.kept < 0) {
+		fq_keep_drop();
+		es.ks = fq_open(fn, opt->n_threads);
+		if (es.ks == 0) {
+			fprintf(stderr, "[E::%s] cannot open '%s'\n", __func__, fn);
+			exit(1);
+		}
+	} else if (bfc_verbose >= 4) fprintf(stderr, "[M::%s] %ld blocks of '%s' are still in memory from the count pass\n", __func__, es.kept, fn);
 	kt_pipeline(opt->no_mt_io ? 1 : N_FLAT, ec_cb, &es, 4);
-	fq_close(es.ks);
+	if (es.ks) fq_close(es.ks);
+	fq_keep_drop();
 	{ int i; for (i = 0; i < N_FLAT; ++i) fq_flat_free(&es.flat[i]); }
 	if (bfc_verbose >= 3 && !opt->filter_mode)
 		fprintf(stderr, "[M::%s] table lookups: %llu; reads re-run with a larger search stack: %llu\n", __func__,

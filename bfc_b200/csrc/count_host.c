@@ -9,7 +9,6 @@
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
-#include <sys/stat.h>
 #include "bfc.h"
 #include "bfc_b200.h"
 #include "fqblock.h"
@@ -23,6 +22,7 @@ typedef struct {
 	bfc_ch_t *ch;
 	fq_flat_t flat[N_FLAT]; /* pinned, reused round robin: a batch holds one from step 1 (pack) to the end of step 2 (GPU) */
 	long n_batches;
+	int keep_comment;       /* what bfc_correct will ask the reader for: the blocks are kept for it */
 	bfcg_stats_t stats;
 } cnt_shared_t;
 
@@ -37,14 +37,6 @@ typedef struct {
  * that filling the pool with first-touch pages is over after a fraction of a second */
 static size_t batch_text_bytes(const bfc_opt_t *opt) { return (size_t)opt->chunk_size * 5 / 2; }
 
-/* a regular file smaller than that is not worth a thread that pins buffers ahead; pipes and "-" count as big */
-static int input_is_big(const char *fn, size_t bytes)
-{
-	struct stat st;
-	if (fn == 0 || strcmp(fn, "-") == 0 || stat(fn, &st) != 0 || !S_ISREG(st.st_mode)) return 1;
-	return (size_t)st.st_size >= bytes;
-}
-
 #define STAMP(what) do { if (bfc_verbose >= 4) fprintf(stderr, "[D::%s @%.3f] %s\n", __func__, realtime() - bfc_real_time, what); } while (0)
 
 static void *count_cb(void *shared, int step, void *_data)
@@ -52,7 +44,9 @@ static void *count_cb(void *shared, int step, void *_data)
 	cnt_shared_t *cs = (cnt_shared_t*)shared;
 	if (step == 0) {
 		cnt_step_t *d = (cnt_step_t*)calloc(1, sizeof(cnt_step_t));
-		const int ok = fq_next(cs->ks, batch_text_bytes(cs->opt), 0, &d->blk);
+		int ok;
+		STAMP("read begins");
+		ok = fq_next(cs->ks, batch_text_bytes(cs->opt), cs->keep_comment, &d->blk);
 		STAMP("block read and split");
 		if (ok < 0) { fprintf(stderr, "[E::%s] out of host memory while reading\n", "bfc_count"); exit(1); }
 		fprintf(stderr, "[M::%s] read %ld sequences\n", "bfc_count_cb", (long)d->blk.n);
@@ -61,6 +55,7 @@ static void *count_cb(void *shared, int step, void *_data)
 	} else if (step == 1) {
 		cnt_step_t *d = (cnt_step_t*)_data;
 		d->flat = &cs->flat[cs->n_batches++ % N_FLAT];
+		STAMP("pack begins");
 		if (fq_flat_fill(d->flat, &d->blk, 0, cs->opt->n_threads) < 0) {
 			fprintf(stderr, "[E::%s] out of host memory while packing\n", "bfc_count");
 			exit(1);
@@ -70,6 +65,7 @@ static void *count_cb(void *shared, int step, void *_data)
 	} else if (step == 2) {
 		cnt_step_t *d = (cnt_step_t*)_data;
 		double rt, eff;
+		STAMP("count begins");
 		if (bfcg_count_batch(cs->opt, cs->bf, cs->bf_high, cs->ch, &d->flat->b, &cs->stats) != BFCG_OK) {
 			fprintf(stderr, "[E::%s] GPU count failed: %s\n", "bfc_count", bfcg_last_error());
 			exit(1);
@@ -82,7 +78,7 @@ static void *count_cb(void *shared, int step, void *_data)
 					"bfc_count_cb", rt, eff, (long)d->blk.n, (long)bfc_ch_count(cs->ch));
 		else
 			fprintf(stderr, "[M::%s @%.1f*%.1f%%] processed %ld sequences\n", "bfc_count_cb", rt, eff, (long)d->blk.n);
-		fq_block_free(&d->blk);
+		if (!fq_keep_add(&d->blk)) fq_block_free(&d->blk);
 		free(d);
 	}
 	return 0;
@@ -95,8 +91,6 @@ void *bfc_count(const char *fn, const bfc_opt_t *opt)
 	memset(&cs, 0, sizeof(cs));
 	cs.opt = opt;
 	STAMP("start");
-	if (!opt->no_mt_io && input_is_big(fn, 2 * batch_text_bytes(opt)))
-		fq_flat_prewarm(batch_text_bytes(opt), 4); /* beside the allocation of the filter; bfc_correct inherits them */
 	cs.bf = bfc_bf_init(opt->bf_shift, opt->n_hashes);
 	STAMP("filter allocated");
 	if (cs.bf == 0) {
@@ -115,8 +109,10 @@ void *bfc_count(const char *fn, const bfc_opt_t *opt)
 		fprintf(stderr, "[E::%s] cannot open '%s'\n", __func__, fn);
 		exit(1);
 	}
+	cs.keep_comment = opt->filter_mode || opt->refine_ec;
+	fq_keep_begin(fn, cs.keep_comment);
 	kt_pipeline(opt->no_mt_io ? 1 : N_FLAT, count_cb, &cs, 3);
-	fq_flat_prewarm_finish();
+	fq_keep_end(1);
 	fq_close(cs.ks);
 	{ int i; for (i = 0; i < N_FLAT; ++i) fq_flat_free(&cs.flat[i]); }
 	if (bfc_verbose >= 3)

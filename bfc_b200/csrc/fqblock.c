@@ -19,6 +19,7 @@ int bseq_at_eof(const bseq_file_t *f);
  * per batch -- which cost more than reading and splitting the text.  Large buffers therefore go back to a small pool
  * and are handed out again (first fit within 2x), up to a fixed total. */
 #include <pthread.h>
+#include <time.h>
 #define BIG_MIN   ((size_t)1 << 20)
 #define BIG_SLOTS 96
 #define BIG_POOL_MAX ((size_t)12 << 30)
@@ -64,12 +65,15 @@ static void big_free(void *p)
 	free(h);
 }
 
+#define PREAD_PIECE_DEFAULT ((size_t)2 << 20) /* BFC_B200_READ_PIECE=<bytes> (tests): the grain of the parallel read and split */
+
 struct fq_reader_s {
 	gzFile fp;
 	int fd;                     /* >= 0: an uncompressed regular file, read with parallel pread()s; the gzFile then only
 	                               serves the hand-over to the tolerant parser (repositioned with gzseek) */
 	int64_t pos, size;
 	int n_threads, eof, fast;
+	size_t piece;               /* bytes per work item of the parallel read and split */
 	char *carry;                /* text read but not yet delivered (the incomplete tail of the previous block) */
 	size_t carry_len;
 	char *last_comment;         /* kseq's sticky comment (bseq.c header) */
@@ -84,6 +88,7 @@ fq_reader_t *fq_open(const char *fn, int n_threads)
 	gzbuffer(g, 1 << 20);
 	r = (fq_reader_t*)calloc(1, sizeof(fq_reader_t));
 	r->fp = g, r->n_threads = n_threads < 1 ? 1 : n_threads, r->fast = 1, r->fd = -1;
+	r->piece = getenv("BFC_B200_READ_PIECE") && atoll(getenv("BFC_B200_READ_PIECE")) >= 16 ? (size_t)atoll(getenv("BFC_B200_READ_PIECE")) : PREAD_PIECE_DEFAULT;
 	if (fn && strcmp(fn, "-")) { /* plain regular file? (zlib would copy it through its own buffer on one thread) */
 		struct stat st;
 		unsigned char magic[2] = {0, 0};
@@ -95,32 +100,45 @@ fq_reader_t *fq_open(const char *fn, int n_threads)
 	return r;
 }
 
-typedef struct { int fd; char *dst; int64_t pos, len; int err; } pread_t;
-#define PREAD_PIECE (8 << 20)
+typedef struct { int fd; char *dst; int64_t pos, len, piece; int err; size_t *nl_cnt; } pread_t;
+
+static size_t count_newlines(const char *p, const char *e)
+{
+	size_t c = 0;
+	for (; p < e && (p = (const char*)memchr(p, '\n', (size_t)(e - p))) != 0; ++p) ++c;
+	return c;
+}
 
 static void pread_worker(void *data, long i, int tid)
 {
 	pread_t *p = (pread_t*)data;
-	int64_t o = i * (int64_t)PREAD_PIECE, e = o + PREAD_PIECE < p->len ? o + PREAD_PIECE : p->len;
+	const int64_t o0 = i * p->piece;
+	int64_t o = o0, e = o + p->piece < p->len ? o + p->piece : p->len;
 	(void)tid;
 	while (o < e) {
 		const ssize_t got = pread(p->fd, p->dst + o, (size_t)(e - o), (off_t)(p->pos + o));
 		if (got <= 0) { p->err = 1; return; }
 		o += got;
 	}
+	if (p->nl_cnt) p->nl_cnt[i] = count_newlines(p->dst + o0, p->dst + e); /* the piece is still in this core's cache */
 }
 
-/* up to `want` more bytes of input at dst; 0 at end of input */
-static size_t rd_more(fq_reader_t *rd, char *dst, size_t want)
+/* up to `want` more bytes of input at dst; 0 at end of input.  nl_cnt (optional, room for a count per rd->piece bytes of
+ * `want`): filled with the newlines of every piece when the bytes came from parallel pread()s, *n_pieces says how many */
+static size_t rd_more(fq_reader_t *rd, char *dst, size_t want, size_t *nl_cnt, long *n_pieces)
 {
+	if (n_pieces) *n_pieces = 0;
 	if (rd->fd >= 0) {
 		pread_t p;
-		p.fd = rd->fd, p.dst = dst, p.pos = rd->pos, p.err = 0;
+		const long np = (long)(((rd->size - rd->pos < (int64_t)want ? rd->size - rd->pos : (int64_t)want) + (int64_t)rd->piece - 1) / (int64_t)rd->piece);
+		p.piece = (int64_t)rd->piece;
+		p.fd = rd->fd, p.dst = dst, p.pos = rd->pos, p.err = 0, p.nl_cnt = nl_cnt;
 		p.len = rd->size - rd->pos < (int64_t)want ? rd->size - rd->pos : (int64_t)want;
 		if (p.len <= 0) return 0;
-		kt_for(rd->n_threads, pread_worker, &p, (long)((p.len + PREAD_PIECE - 1) / PREAD_PIECE));
+		kt_for(rd->n_threads, pread_worker, &p, np);
 		if (p.err) return 0;
 		rd->pos += p.len;
+		if (n_pieces && nl_cnt) *n_pieces = np;
 		return (size_t)p.len;
 	} else {
 		const int got = gzread(rd->fp, dst, (unsigned)(want > (1u << 30) ? (1u << 30) : want));
@@ -162,75 +180,90 @@ static int blk_alloc(fq_block_t *b, int64_t n)
 typedef struct {
 	const char *s;
 	size_t len;
-	int n_parts;
-	size_t *cnt;        /* newlines per part, then exclusive prefix */
-	uint64_t *nl;       /* positions of the newlines */
-	/* phase 2 */
+	int virt_nl;        /* the input ended without a newline: one is imagined at s[len] */
+	long n_parts;
+	size_t *lo;         /* part i = [lo[i], lo[i + 1]) */
+	size_t *cnt;        /* newlines per part, then their exclusive prefix = the index of the line that holds byte lo[i] */
 	fq_block_t *b;
 	int keep_comment, bad;
+	size_t used;        /* end of the last complete record */
+	uint64_t *part_bases;
+	int64_t *part_last_com; /* the last record of the part that has a comment (-1: none), and where that comment is */
+	uint64_t *part_com_off;
+	uint32_t *part_com_len;
 } split_t;
-
-static void part_range(const split_t *sp, long i, size_t *lo, size_t *hi)
-{
-	*lo = sp->len / sp->n_parts * i;
-	*hi = i + 1 == sp->n_parts ? sp->len : sp->len / sp->n_parts * (i + 1);
-}
 
 static void count_nl_worker(void *data, long i, int tid)
 {
 	split_t *sp = (split_t*)data;
-	size_t lo, hi, c = 0;
-	const char *p, *e;
 	(void)tid;
-	part_range(sp, i, &lo, &hi);
-	for (p = sp->s + lo, e = sp->s + hi; p < e && (p = (const char*)memchr(p, '\n', e - p)) != 0; ++p) ++c;
-	sp->cnt[i] = c;
+	sp->cnt[i] = count_newlines(sp->s + sp->lo[i], sp->s + sp->lo[i + 1]);
 }
 
-static void fill_nl_worker(void *data, long i, int tid)
-{
-	split_t *sp = (split_t*)data;
-	size_t lo, hi;
-	uint64_t *out = sp->nl + sp->cnt[i];
-	const char *p, *e;
-	(void)tid;
-	part_range(sp, i, &lo, &hi);
-	for (p = sp->s + lo, e = sp->s + hi; p < e && (p = (const char*)memchr(p, '\n', e - p)) != 0; ++p) *out++ = (uint64_t)(p - sp->s);
-}
-
-#define REC_PER_ITEM 4096
-
-/* records [i * REC_PER_ITEM, ...): four lines each; anything kseq would read differently flags the block */
+/* Part i delivers the records whose '@' line starts inside it (reading on into the next part for the rest of its last
+ * record).  Which line a byte belongs to follows from the newline counts alone, so no index of line starts is built:
+ * one pass over the text.  Anything kseq would read differently flags the block. */
 static void parse_worker(void *data, long i, int tid)
 {
 	split_t *sp = (split_t*)data;
 	fq_block_t *b = sp->b;
-	const char *s = sp->s;
-	int64_t r, r1 = (i + 1) * (int64_t)REC_PER_ITEM < b->n ? (i + 1) * (int64_t)REC_PER_ITEM : b->n;
+	const char *s = sp->s, *q;
+	const size_t len = sp->len, hi = sp->lo[i + 1];
+	size_t p = sp->lo[i];
+	uint64_t line = sp->cnt[i], bases = 0, last_off = 0;
+	uint32_t last_len = 0;
+	int64_t last_com = -1;
 	(void)tid;
-	for (r = i * (int64_t)REC_PER_ITEM; r < r1; ++r) {
-		const uint64_t l0 = r ? sp->nl[4 * r - 1] + 1 : 0, e0 = sp->nl[4 * r], e1 = sp->nl[4 * r + 1], e2 = sp->nl[4 * r + 2], e3 = sp->nl[4 * r + 3];
-		const uint64_t l1 = e0 + 1, l2 = e1 + 1, l3 = e2 + 1;
-		uint64_t p;
-		if (e0 == l0 || s[l0] != '@' || e1 == l1 || s[l2] != '+' || e2 == l2 || e3 - l3 != e1 - l1 ||
-			s[l1] == '>' || s[l1] == '+' || s[l1] == '@' || s[e0 - 1] == '\r' || s[e1 - 1] == '\r' || s[e2 - 1] == '\r' || s[e3 - 1] == '\r' ||
-			e1 - l1 > 0x7fffffffULL) { sp->bad = 1; return; }
-		for (p = l0 + 1; p < e0 && !isspace((unsigned char)s[p]); ++p) {}
-		b->name_off[r] = l0 + 1, b->name_len[r] = (uint32_t)(p - (l0 + 1));
-		if (p < e0) b->com_off[r] = p + 1, b->com_len[r] = (uint32_t)(e0 - (p + 1)); /* the rest of the line after ONE delimiter */
-		else b->com_off[r] = FQ_NONE, b->com_len[r] = 0;
-		b->seq_off[r] = l1, b->seq_len[r] = (uint32_t)(e1 - l1), b->qual_off[r] = l3;
+	sp->part_bases[i] = 0, sp->part_last_com[i] = -1;
+	if (p > 0 && s[p - 1] != '\n') { /* the line that holds lo[i] began in an earlier part */
+		if ((q = (const char*)memchr(s + p, '\n', len - p)) == 0) return;
+		p = (size_t)(q - s) + 1, ++line;
 	}
+	for (; line & 3; ++line) { /* on to the next '@' line */
+		if (p >= hi || (q = (const char*)memchr(s + p, '\n', len - p)) == 0) return;
+		p = (size_t)(q - s) + 1;
+	}
+	for (; p < hi && (int64_t)(line >> 2) < b->n; line += 4) {
+		const int64_t r = (int64_t)(line >> 2);
+		const uint64_t l0 = p;
+		uint64_t e[4], c;
+		int j;
+		for (j = 0; j < 4; ++j) {
+			q = p < len ? (const char*)memchr(s + p, '\n', len - p) : 0;
+			if (q == 0 && !(sp->virt_nl && j == 3)) { sp->bad = 1; return; } /* (cannot happen: r < n counts whole records) */
+			e[j] = q ? (uint64_t)(q - s) : len;
+			p = (size_t)e[j] + 1;
+		}
+		{
+			const uint64_t l1 = e[0] + 1, l2 = e[1] + 1, l3 = e[2] + 1;
+			if (e[0] == l0 || s[l0] != '@' || e[1] == l1 || s[l2] != '+' || e[2] == l2 || e[3] - l3 != e[1] - l1 ||
+				s[l1] == '>' || s[l1] == '+' || s[l1] == '@' || s[e[0] - 1] == '\r' || s[e[1] - 1] == '\r' || s[e[2] - 1] == '\r' || s[e[3] - 1] == '\r' ||
+				e[1] - l1 > 0x7fffffffULL) { sp->bad = 1; return; }
+			for (c = l0 + 1; c < e[0] && !isspace((unsigned char)s[c]); ++c) {}
+			b->name_off[r] = l0 + 1, b->name_len[r] = (uint32_t)(c - (l0 + 1));
+			b->com_off[r] = FQ_NONE, b->com_len[r] = 0;
+			if (c < e[0]) { /* the rest of the line after ONE delimiter */
+				last_com = r, last_off = c + 1, last_len = (uint32_t)(e[0] - (c + 1));
+				if (sp->keep_comment) b->com_off[r] = last_off, b->com_len[r] = last_len;
+			}
+			b->seq_off[r] = l1, b->seq_len[r] = (uint32_t)(e[1] - l1), b->qual_off[r] = l3;
+			bases += e[1] - l1;
+			if (r == b->n - 1) sp->used = e[3] + 1 > len ? len : (size_t)e[3] + 1;
+		}
+	}
+	sp->part_bases[i] = bases, sp->part_last_com[i] = last_com, sp->part_com_off[i] = last_off, sp->part_com_len[i] = last_len;
 }
 
-/* kseq never clears its comment buffer: a record without one inherits the latest (bseq.c header) */
-static void sticky_comments(fq_reader_t *rd, fq_block_t *b, int keep_comment)
+/* kseq never clears its comment buffer: a record without one inherits the latest (bseq.c header).  `last` = the last
+ * record of the block that carries a comment of its own (-1: none) */
+static void sticky_comments(fq_reader_t *rd, fq_block_t *b, int keep_comment, int64_t last, uint64_t last_off, uint32_t last_len)
 {
-	int64_t r, last = -1;
-	for (r = 0; r < b->n; ++r) {
-		if (b->com_off[r] != FQ_NONE) last = r;
-		else if (keep_comment) {
-			if (last >= 0) b->com_off[r] = b->com_off[last], b->com_len[r] = b->com_len[last];
+	int64_t r;
+	if (keep_comment) {
+		int64_t seen = -1;
+		for (r = 0; r < b->n; ++r) {
+			if (b->com_off[r] != FQ_NONE) seen = r;
+			else if (seen >= 0) b->com_off[r] = b->com_off[seen], b->com_len[r] = b->com_len[seen];
 			else if (rd->last_comment) b->com_off[r] = FQ_NONE - 1; /* patched below: lives outside this block */
 		}
 	}
@@ -250,42 +283,75 @@ static void sticky_comments(fq_reader_t *rd, fq_block_t *b, int keep_comment)
 	}
 	if (last >= 0) {
 		free(rd->last_comment);
-		rd->last_comment = (char*)malloc((size_t)b->com_len[last] + 1);
-		memcpy(rd->last_comment, b->buf + b->com_off[last], b->com_len[last]);
-		rd->last_comment[b->com_len[last]] = 0;
+		rd->last_comment = (char*)malloc((size_t)last_len + 1);
+		memcpy(rd->last_comment, b->buf + last_off, last_len);
+		rd->last_comment[last_len] = 0;
 	}
-	if (!keep_comment) for (r = 0; r < b->n; ++r) b->com_off[r] = FQ_NONE, b->com_len[r] = 0;
 }
 
-/* 1 = block delivered, 0 = not plain four-line FASTQ (nothing consumed; *data is handed back), -1 = out of memory */
-static int fast_block(fq_reader_t *rd, char *data, size_t len, int keep_comment, fq_block_t *b, size_t *used)
+static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+extern int bfc_verbose;
+
+/* 1 = block delivered, 0 = not plain four-line FASTQ (nothing consumed; *data is handed back), -1 = out of memory.
+ * pre_cnt/pre_n: newline counts the reader already took of the pieces [pre_lo + j * rd->piece, ...) */
+static int fast_block(fq_reader_t *rd, char *data, size_t len, int keep_comment, fq_block_t *b, size_t *used,
+                      const size_t *pre_cnt, long pre_n, size_t pre_lo)
 {
 	split_t sp;
 	size_t run = 0, n_lines;
 	long i;
-	int64_t r;
+	int64_t last = -1;
+	uint64_t last_off = 0;
+	uint32_t last_len = 0;
+	double t[4];
 	memset(&sp, 0, sizeof(sp));
-	sp.s = data, sp.len = len, sp.n_parts = rd->n_threads * 4;
 	if (len == 0 || data[0] != '@') return 0;
-	sp.cnt = (size_t*)calloc((size_t)sp.n_parts + 1, sizeof(size_t));
-	kt_for(rd->n_threads, count_nl_worker, &sp, sp.n_parts);
+	t[0] = now_s();
+	sp.s = data, sp.len = len, sp.keep_comment = keep_comment;
+	sp.virt_nl = rd->eof && data[len - 1] != '\n'; /* last line without a newline */
+	const size_t piece = rd->piece;
+	if (pre_n > 0 && pre_lo + (size_t)pre_n * piece >= len && pre_lo + (size_t)(pre_n - 1) * piece < len) {
+		/* parts = the carried-over head, then the pieces as they were read (and counted) */
+		sp.n_parts = pre_n + (pre_lo > 0);
+		sp.lo = (size_t*)malloc(((size_t)sp.n_parts + 1) * sizeof(size_t)), sp.cnt = (size_t*)calloc((size_t)sp.n_parts + 1, sizeof(size_t));
+		if (pre_lo > 0) sp.lo[0] = 0, sp.cnt[0] = count_newlines(data, data + pre_lo);
+		for (i = 0; i < pre_n; ++i) sp.lo[i + (pre_lo > 0)] = pre_lo + (size_t)i * piece, sp.cnt[i + (pre_lo > 0)] = pre_cnt[i];
+		sp.lo[sp.n_parts] = len;
+	} else {
+		sp.n_parts = (long)((len + piece - 1) / piece);
+		sp.lo = (size_t*)malloc(((size_t)sp.n_parts + 1) * sizeof(size_t)), sp.cnt = (size_t*)calloc((size_t)sp.n_parts + 1, sizeof(size_t));
+		for (i = 0; i < sp.n_parts; ++i) sp.lo[i] = (size_t)i * piece;
+		sp.lo[sp.n_parts] = len;
+		kt_for(rd->n_threads, count_nl_worker, &sp, sp.n_parts);
+	}
 	for (i = 0; i < sp.n_parts; ++i) { const size_t c = sp.cnt[i]; sp.cnt[i] = run; run += c; }
-	n_lines = run;
-	sp.nl = (uint64_t*)big_alloc((n_lines + 2) * sizeof(uint64_t));
-	if (sp.nl == 0) { free(sp.cnt); return -1; }
-	kt_for(rd->n_threads, fill_nl_worker, &sp, sp.n_parts);
-	if (rd->eof && (n_lines == 0 || sp.nl[n_lines - 1] + 1 != len)) sp.nl[n_lines++] = len; /* last line without a newline */
-	if (n_lines < 4 || (rd->eof && n_lines % 4 != 0)) { free(sp.cnt); big_free(sp.nl); return 0; }
+	n_lines = run + (size_t)sp.virt_nl;
+	t[1] = now_s();
+	if (n_lines < 4 || (rd->eof && n_lines % 4 != 0)) { free(sp.cnt); free(sp.lo); return 0; }
 	memset(b, 0, sizeof(*b));
-	if (blk_alloc(b, (int64_t)(n_lines / 4)) < 0) { free(sp.cnt); big_free(sp.nl); fq_block_free(b); return -1; }
-	sp.b = b, sp.keep_comment = keep_comment;
-	kt_for(rd->n_threads, parse_worker, &sp, (long)((b->n + REC_PER_ITEM - 1) / REC_PER_ITEM));
-	*used = sp.nl[4 * b->n - 1] + 1 > len ? len : sp.nl[4 * b->n - 1] + 1;
-	free(sp.cnt); big_free(sp.nl);
-	if (sp.bad) { fq_block_free(b); return 0; }
+	sp.part_bases = (uint64_t*)calloc((size_t)sp.n_parts, 8), sp.part_last_com = (int64_t*)calloc((size_t)sp.n_parts, 8);
+	sp.part_com_off = (uint64_t*)calloc((size_t)sp.n_parts, 8), sp.part_com_len = (uint32_t*)calloc((size_t)sp.n_parts, 4);
+	if (blk_alloc(b, (int64_t)(n_lines / 4)) < 0) {
+		free(sp.cnt); free(sp.lo); free(sp.part_bases); free(sp.part_last_com); free(sp.part_com_off); free(sp.part_com_len);
+		fq_block_free(b);
+		return -1;
+	}
+	sp.b = b;
+	kt_for(rd->n_threads, parse_worker, &sp, sp.n_parts);
+	t[2] = now_s();
+	for (i = 0; i < sp.n_parts; ++i) {
+		b->n_bases += sp.part_bases[i];
+		if (sp.part_last_com[i] > last) last = sp.part_last_com[i], last_off = sp.part_com_off[i], last_len = sp.part_com_len[i];
+	}
+	*used = sp.used;
+	free(sp.cnt); free(sp.lo); free(sp.part_bases); free(sp.part_last_com); free(sp.part_com_off); free(sp.part_com_len);
+	if (sp.bad || sp.used == 0) { fq_block_free(b); return 0; }
 	b->buf = data, b->buf_len = len, b->any_qual = 1;
-	for (r = 0; r < b->n; ++r) b->n_bases += b->seq_len[r];
-	sticky_comments(rd, b, keep_comment);
+	sticky_comments(rd, b, keep_comment, last, last_off, last_len);
+	t[3] = now_s();
+	if (bfc_verbose >= 5)
+		fprintf(stderr, "[D::%s] newline counts %.1f ms, records %.1f, rest %.1f\n", __func__,
+				1e3 * (t[1] - t[0]), 1e3 * (t[2] - t[1]), 1e3 * (t[3] - t[2]));
 	return 1;
 }
 
@@ -333,19 +399,26 @@ int fq_next(fq_reader_t *rd, size_t target, int keep_comment, fq_block_t *b)
 	if (target < 4096) target = 4096;
 	while (rd->fast) {
 		const size_t carry0 = rd->carry_len;
+		const double t0 = now_s();
 		char *data = (char*)big_alloc(carry0 + target + 1);
 		size_t len = carry0, used = 0;
 		int rc;
 		if (data == 0) return -1;
 		if (carry0) memcpy(data, rd->carry, carry0);
 		free(rd->carry); rd->carry = 0, rd->carry_len = 0;
+		size_t *pre_cnt = (size_t*)malloc((target / rd->piece + 2) * sizeof(size_t));
+		long pre_n = 0, calls = 0;
 		while (!rd->eof && len < carry0 + target) {
-			const size_t got = rd_more(rd, data + len, carry0 + target - len);
+			long np = 0;
+			const size_t got = rd_more(rd, data + len, carry0 + target - len, calls == 0 ? pre_cnt : 0, &np);
 			if (got == 0) { rd->eof = 1; break; }
+			pre_n = calls++ == 0 ? np : 0; /* counts are only good when one call brought everything */
 			len += got;
 		}
-		if (len == 0) { big_free(data); return 0; }
-		rc = fast_block(rd, data, len, keep_comment, b, &used);
+		if (len == 0) { big_free(data); free(pre_cnt); return 0; }
+		if (bfc_verbose >= 5) fprintf(stderr, "[D::%s] %.1f MB of text in %.1f ms\n", __func__, len / 1e6, 1e3 * (now_s() - t0));
+		rc = fast_block(rd, data, len, keep_comment, b, &used, pre_cnt, pre_n, carry0);
+		free(pre_cnt);
 		if (rc == 1) {
 			if (used < len) { /* the incomplete tail waits for the next block */
 				rd->carry_len = len - used;
@@ -369,7 +442,93 @@ int fq_next(fq_reader_t *rd, size_t target, int keep_comment, fq_block_t *b)
 	return slow_block(rd, target, keep_comment, b); /* 1, 0 at end of input, -1 out of memory */
 }
 
+/* ---------------------------------------------------------------- blocks kept from one phase to the next */
+
+/* bfc reads its input twice (count, then correct: reference bfc.c:131-148).  For gzip'd input, where the second pass
+ * would inflate everything again on one thread, the parsed blocks of the first pass are kept when they fit into a
+ * quarter of the host's memory, and the second pass takes them from here.  For plain files this is off by default:
+ * on the B200 box (16 cores) keeping the blocks saves the correct pass 4 ms per 250 MB block and costs the count pass
+ * 8 ms, because kept buffers cannot be recycled and every new one is paid for in page faults.
+ * BFC_B200_KEEP_MAX=<bytes> switches it on for every regular file (0: off for all). */
+static struct {
+	char *fn;
+	off_t size;
+	struct timespec mtime;
+	int keep_comment, complete, over;
+	fq_block_t *blk;
+	long n, m;
+	size_t bytes, budget;
+} kept;
+
+static size_t block_bytes(const fq_block_t *b) { return b->buf_len + (size_t)(b->n > 0 ? b->n : 1) * 44; }
+
+void fq_keep_drop(void)
+{
+	long i;
+	for (i = 0; i < kept.n; ++i) fq_block_free(&kept.blk[i]);
+	free(kept.blk); free(kept.fn);
+	memset(&kept, 0, sizeof(kept));
+}
+
+void fq_keep_begin(const char *fn, int keep_comment)
+{
+	struct stat st;
+	const char *e = getenv("BFC_B200_KEEP_MAX"); /* bytes; 0 switches the cache off */
+	fq_keep_drop();
+	if (fn == 0 || strcmp(fn, "-") == 0 || stat(fn, &st) != 0 || !S_ISREG(st.st_mode)) return;
+	if (e) kept.budget = (size_t)strtoull(e, 0, 10);
+	else {
+		unsigned char magic[2] = {0, 0};
+		FILE *fp = fopen(fn, "rb");
+		const int gz = fp && fread(magic, 1, 2, fp) == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+		if (fp) fclose(fp);
+		kept.budget = gz ? (size_t)sysconf(_SC_PHYS_PAGES) / 4 * (size_t)sysconf(_SC_PAGESIZE) : 0;
+	}
+	if (kept.budget == 0) return;
+	kept.fn = strdup(fn), kept.size = st.st_size, kept.mtime = st.st_mtim, kept.keep_comment = keep_comment;
+}
+
+int fq_keep_add(fq_block_t *b)
+{
+	if (kept.fn == 0 || kept.over) return 0;
+	if (kept.bytes + block_bytes(b) > kept.budget) { /* too big for this host: the second pass reads the file again */
+		long i;
+		for (i = 0; i < kept.n; ++i) fq_block_free(&kept.blk[i]);
+		kept.n = 0, kept.bytes = 0, kept.over = 1;
+		return 0;
+	}
+	if (kept.n == kept.m) {
+		fq_block_t *nb = (fq_block_t*)realloc(kept.blk, (size_t)(kept.m ? kept.m * 2 : 64) * sizeof(fq_block_t));
+		if (nb == 0) { kept.over = 1; return 0; }
+		kept.blk = nb, kept.m = kept.m ? kept.m * 2 : 64;
+	}
+	kept.bytes += block_bytes(b);
+	kept.blk[kept.n++] = *b;
+	memset(b, 0, sizeof(*b));
+	return 1;
+}
+
+void fq_keep_end(int complete) { kept.complete = complete && kept.fn && !kept.over; }
+
+long fq_keep_match(const char *fn, int keep_comment)
+{
+	struct stat st;
+	if (!kept.complete || fn == 0 || strcmp(fn, kept.fn) != 0 || keep_comment != kept.keep_comment) return -1;
+	if (stat(fn, &st) != 0 || st.st_size != kept.size || st.st_mtim.tv_sec != kept.mtime.tv_sec || st.st_mtim.tv_nsec != kept.mtime.tv_nsec) return -1;
+	return kept.n;
+}
+
+int fq_keep_take(long i, fq_block_t *b)
+{
+	if (i < 0 || i >= kept.n) return 0;
+	*b = kept.blk[i];
+	memset(&kept.blk[i], 0, sizeof(fq_block_t));
+	return 1;
+}
+
 /* ---------------------------------------------------------------- flat batch */
+
+#define REC_PER_ITEM 4096
 
 typedef struct { fq_flat_t *f; const fq_block_t *b; } fill_t;
 
@@ -395,30 +554,23 @@ static void fill_worker(void *data, long i, int tid)
 	}
 }
 
-/* pinning host memory costs 0.3-0.7 s per GB: buffers released by one phase are parked here for the next one, and
- * fq_flat_prewarm() fills the park from a thread of its own while the caller is still busy creating the filter */
+/* pinning host memory costs ~0.4 s per GB (cudaMallocHost, B200 box): buffers released by one phase are parked here for
+ * the next one.  (Pinning them ahead on a helper thread while the filter is being created was measured and dropped:
+ * the driver serialises it with the context's own allocations, the first batch came out 0.3 s later, not earlier.) */
 #define FLAT_CACHE 4
 static struct { uint8_t *seq, *qual; size_t cap; } flat_cache[FLAT_CACHE];
 static pthread_mutex_t flat_mu = PTHREAD_MUTEX_INITIALIZER;
-static pthread_cond_t flat_cv = PTHREAD_COND_INITIALIZER;
-static int flat_coming;         /* buffer pairs the prewarm thread has yet to deliver */
-static int flat_running;        /* the prewarm thread is alive */
-static size_t flat_coming_cap;
 
 static int flat_cache_take(fq_flat_t *f, size_t need)
 {
 	int i, got = 0;
 	pthread_mutex_lock(&flat_mu);
-	for (;;) {
-		for (i = 0; i < FLAT_CACHE && !got; ++i)
-			if (flat_cache[i].seq && flat_cache[i].cap >= need) {
-				f->seq_buf = flat_cache[i].seq, f->qual_buf = flat_cache[i].qual, f->cap_bytes = flat_cache[i].cap, f->pinned = 1;
-				flat_cache[i].seq = 0;
-				got = 1;
-			}
-		if (got || flat_coming == 0 || flat_coming_cap < need) break;
-		pthread_cond_wait(&flat_cv, &flat_mu); /* one that fits is on its way */
-	}
+	for (i = 0; i < FLAT_CACHE && !got; ++i)
+		if (flat_cache[i].seq && flat_cache[i].cap >= need) {
+			f->seq_buf = flat_cache[i].seq, f->qual_buf = flat_cache[i].qual, f->cap_bytes = flat_cache[i].cap, f->pinned = 1;
+			flat_cache[i].seq = 0;
+			got = 1;
+		}
 	pthread_mutex_unlock(&flat_mu);
 	return got;
 }
@@ -431,59 +583,6 @@ static int flat_cache_put(uint8_t *seq, uint8_t *qual, size_t cap)
 		if (flat_cache[i].seq == 0) flat_cache[i].seq = seq, flat_cache[i].qual = qual, flat_cache[i].cap = cap, put = 1;
 	pthread_mutex_unlock(&flat_mu);
 	return put;
-}
-
-static void *prewarm_main(void *arg)
-{
-	const size_t cap = flat_coming_cap;
-	(void)arg;
-	for (;;) {
-		uint8_t *seq, *qual;
-		int left;
-		pthread_mutex_lock(&flat_mu);
-		left = flat_coming;
-		if (left == 0) { flat_running = 0; pthread_cond_broadcast(&flat_cv); }
-		pthread_mutex_unlock(&flat_mu);
-		if (left == 0) break;
-		seq = (uint8_t*)bfcg_host_alloc_pinned(cap);
-		qual = seq ? (uint8_t*)bfcg_host_alloc_pinned(cap) : 0;
-		if (seq && qual && flat_cache_put(seq, qual, cap)) {
-			pthread_mutex_lock(&flat_mu);
-			if (flat_coming > 0) --flat_coming;
-		} else { /* no memory, or nowhere to park it: the packer allocates for itself */
-			if (seq) bfcg_host_free_pinned(seq);
-			if (qual) bfcg_host_free_pinned(qual);
-			pthread_mutex_lock(&flat_mu);
-			flat_coming = 0;
-		}
-		pthread_cond_broadcast(&flat_cv);
-		pthread_mutex_unlock(&flat_mu);
-	}
-	return 0;
-}
-
-void fq_flat_prewarm(size_t text_bytes, int n)
-{
-	pthread_t t;
-	pthread_attr_t at;
-	pthread_mutex_lock(&flat_mu);
-	if (!flat_running && n > 0) {
-		flat_coming = n < FLAT_CACHE ? n : FLAT_CACHE, flat_running = 1;
-		flat_coming_cap = text_bytes / 16 * 9; /* bases + one byte per read of a block of four-line FASTQ, with head-room */
-		pthread_attr_init(&at);
-		pthread_attr_setdetachstate(&at, PTHREAD_CREATE_DETACHED);
-		if (pthread_create(&t, &at, prewarm_main, 0) != 0) flat_coming = 0, flat_running = 0;
-		pthread_attr_destroy(&at);
-	}
-	pthread_mutex_unlock(&flat_mu);
-}
-
-void fq_flat_prewarm_finish(void)
-{
-	pthread_mutex_lock(&flat_mu);
-	flat_coming = 0; /* whatever it is allocating right now is its last */
-	while (flat_running) pthread_cond_wait(&flat_cv, &flat_mu);
-	pthread_mutex_unlock(&flat_mu);
 }
 
 int fq_flat_fill(fq_flat_t *f, const fq_block_t *b, const uint8_t *skip, int n_threads)

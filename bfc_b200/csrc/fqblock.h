@@ -46,6 +46,16 @@ int  fq_next(fq_reader_t *r, size_t target_bytes, int keep_comment, fq_block_t *
 void fq_block_free(fq_block_t *blk);
 int  fq_reader_is_fast(const fq_reader_t *r);           /* still on the parallel path (tests) */
 
+/* blocks kept from the count pass for the correct pass over the same file (both passes must ask for the same
+ * keep_comment).  By default only for gzip'd input, and everything is dropped again when the blocks do not fit into
+ * a quarter of the host's memory; BFC_B200_KEEP_MAX=<bytes> sets the budget for every regular file (0 = never keep) */
+void fq_keep_begin(const char *fn, int keep_comment);   /* forgets what was kept; fn must be a regular file for anything to be kept */
+int  fq_keep_add(fq_block_t *blk);                      /* 1 = kept: the block now belongs to the cache and *blk is zeroed */
+void fq_keep_end(int complete);                         /* complete: every block of the input was offered */
+long fq_keep_match(const char *fn, int keep_comment);   /* number of blocks kept for exactly this file (size, mtime), or -1 */
+int  fq_keep_take(long i, fq_block_t *blk);             /* moves block i out */
+void fq_keep_drop(void);
+
 /* the flat batch of bfc_b200.h over a block: pinned buffers that are reused from batch to batch */
 typedef struct {
 	bfcg_batch_t b;            /* b.qual is NULL for a batch without any quality string */
@@ -59,9 +69,6 @@ typedef struct {
 /* skip: NULL, or one byte per record, non-zero = the record does not go into the batch.  0 ok, -1 out of memory */
 int  fq_flat_fill(fq_flat_t *f, const fq_block_t *blk, const uint8_t *skip, int n_threads);
 void fq_flat_free(fq_flat_t *f);
-/* starts pinning n buffer pairs for batches of text_bytes of input on a thread of its own; fq_flat_fill picks them up */
-void fq_flat_prewarm(size_t text_bytes, int n);
-void fq_flat_prewarm_finish(void);  /* stops it after the pair it is working on and waits for it: call before the phase returns */
 
 /* the writer of correct.c:591-611 over a block + the (corrected / trimmed) flat batch: formats on n_threads
  * threads, then writes the pieces in order.  aux/aux2 as packed by worker_ec (correct.c:552-553); in filter mode

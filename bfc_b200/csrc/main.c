@@ -108,15 +108,17 @@ int main(int argc, char *argv[])
 	if (ch) {
 		if (out_hash) bfc_ch_dump(ch, out_hash);
 		if (!no_ec) bfc_correct(next_fn, &opt, ch);
-		bfc_ch_destroy(ch);
-	} else if (bf) {
-		bfc_correct(next_fn, &opt, bf);
-		bfc_bf_destroy(bf);
-	}
+	} else if (bf) bfc_correct(next_fn, &opt, bf);
 
 	fprintf(stderr, "[M::%s] Version: %s\n", __func__, BFC_VERSION);
 	fprintf(stderr, "[M::%s] CMD:", __func__);
 	for (i = 0; i < argc; ++i) fprintf(stderr, " %s", argv[i]);
 	fprintf(stderr, "\n[M::%s] Real time: %.3f sec; CPU: %.3f sec\n", __func__, realtime() - bfc_real_time, cputime());
-	return 0;
+	/* The process ends here without tearing anything down: releasing the table, the pinned buffers and the CUDA context
+	 * one by one took 0.3-1.5 s on the B200 box, and the kernel and the driver reclaim all of it at exit anyway. */
+	if (fflush(stdout) != 0 || ferror(stdout)) {
+		fprintf(stderr, "[E::%s] writing the output failed\n", __func__);
+		_exit(1);
+	}
+	_exit(0);
 }

@@ -27,6 +27,17 @@ class Block(C.Structure):
 NONE = (1 << 64) - 1
 
 
+@pytest.fixture(autouse=True, params=[None, 64, 1000])
+def read_piece(request, monkeypatch):
+    """The grain of the parallel read / split (2 MB by default): tiny grains put part boundaries inside every line
+    and every record of the small test inputs."""
+    if request.param is None:
+        monkeypatch.delenv("BFC_B200_READ_PIECE", raising=False)
+    else:
+        monkeypatch.setenv("BFC_B200_READ_PIECE", str(request.param))
+    return request.param
+
+
 @pytest.fixture(scope="module")
 def L():
     lib = C.CDLL(bfc_b200.lib_path())
@@ -274,3 +285,87 @@ def test_fuzz_record_reader_equals_the_reference_reader(L, tmp_path, seed):
             f.write(data)
         for keep in (0, 1):
             assert one_batch(L, p, keep) == one_batch(R, p, keep), (seed, it, keep)
+
+
+def block_records(b):
+    raw = C.string_at(b.buf, b.buf_len)
+    out = []
+    for i in range(b.n):
+        com = None if b.com_off[i] == NONE else raw[b.com_off[i]:b.com_off[i] + b.com_len[i]]
+        qual = None if b.qual_off[i] == NONE else raw[b.qual_off[i]:b.qual_off[i] + b.seq_len[i]]
+        out.append((raw[b.name_off[i]:b.name_off[i] + b.name_len[i]], com, raw[b.seq_off[i]:b.seq_off[i] + b.seq_len[i]], qual))
+    return out
+
+
+def test_blocks_kept_for_the_second_pass(L, tmp_path, monkeypatch):
+    """fq_keep_*: what the count pass parsed is handed to the correct pass of the same file; a changed file, another
+    keep_comment or a budget that is too small means "read it again" (fq_keep_match = -1)."""
+    L.fq_keep_begin.argtypes = [C.c_char_p, C.c_int]
+    L.fq_keep_add.argtypes = [C.POINTER(Block)]
+    L.fq_keep_end.argtypes = [C.c_int]
+    L.fq_keep_match.restype = C.c_long
+    L.fq_keep_match.argtypes = [C.c_char_p, C.c_int]
+    L.fq_keep_take.argtypes = [C.c_long, C.POINTER(Block)]
+    path = str(tmp_path / "in.fq")
+    with open(path, "wb") as fp:
+        fp.write(rand_fastq(3000, 5, comments=0.5))
+    want, _ = read_fast(L, path, 1, 20000)
+
+    def first_pass(budget=1 << 30):
+        monkeypatch.setenv("BFC_B200_KEEP_MAX", str(budget))
+        L.fq_keep_begin(path.encode(), 1)
+        f = L.fq_open(path.encode(), 3)
+        n_blocks = 0
+        while True:
+            b = Block()
+            if L.fq_next(f, 20000, 1, C.byref(b)) != 1:
+                break
+            n_blocks += 1
+            if not L.fq_keep_add(C.byref(b)):
+                L.fq_block_free(C.byref(b))
+            else:
+                assert not b.buf and b.n == 0       # ownership moved
+        L.fq_close(f)
+        L.fq_keep_end(1)
+        return n_blocks
+
+    n_blocks = first_pass()
+    assert n_blocks > 3
+    assert L.fq_keep_match(path.encode(), 0) == -1                     # the other pass wants other blocks
+    assert L.fq_keep_match((path + "x").encode(), 1) == -1
+    assert L.fq_keep_match(path.encode(), 1) == n_blocks
+    got = []
+    for i in range(n_blocks):
+        b = Block()
+        assert L.fq_keep_take(i, C.byref(b)) == 1
+        got += block_records(b)
+        L.fq_block_free(C.byref(b))
+    assert got == want
+    L.fq_keep_drop()
+    assert L.fq_keep_match(path.encode(), 1) == -1
+
+    first_pass(budget=50000)                                           # two blocks fit, the third does not: nothing is kept
+    assert L.fq_keep_match(path.encode(), 1) == -1
+    first_pass(budget=0)
+    assert L.fq_keep_match(path.encode(), 1) == -1
+
+    monkeypatch.delenv("BFC_B200_KEEP_MAX")                              # default: plain files are read again, gzip'd ones are kept
+    L.fq_keep_begin(path.encode(), 1)
+    b = Block()
+    f = L.fq_open(path.encode(), 3)
+    assert L.fq_next(f, 20000, 1, C.byref(b)) == 1 and L.fq_keep_add(C.byref(b)) == 0
+    L.fq_block_free(C.byref(b))
+    L.fq_close(f)
+    gz = path + ".gz"
+    with open(path, "rb") as src, gzip.open(gz, "wb") as dst:
+        dst.write(src.read())
+    L.fq_keep_begin(gz.encode(), 1)
+    f = L.fq_open(gz.encode(), 3)
+    assert L.fq_next(f, 20000, 1, C.byref(b)) == 1 and L.fq_keep_add(C.byref(b)) == 1
+    L.fq_close(f)
+    L.fq_keep_drop()
+
+    first_pass()
+    os.utime(path, ns=(1, 1))                                          # the file changed between the passes
+    assert L.fq_keep_match(path.encode(), 1) == -1
+    L.fq_keep_drop()

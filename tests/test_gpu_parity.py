@@ -207,6 +207,32 @@ def test_cli_matches_reference_golden(bfc, tmp_path):
         assert out == c.corrected
 
 
+@pytest.mark.parametrize("keep_max,gz", [(None, False), (None, True), ("0", True), ("150000", False), ("100000000", False)])
+def test_cli_many_small_batches_with_and_without_kept_blocks(bfc, tmp_path, keep_max, gz):
+    """`-L` small enough for dozens of batches per pass: the four-step pipeline, the ring of pinned buffers and the
+    blocks kept from the count pass (by default for gzip'd input only; BFC_B200_KEEP_MAX sets a budget for any file),
+    read again (budget 0, or plain input) or given up half-way (a budget that overflows) all produce the reference's
+    bytes."""
+    import gzip, subprocess
+    exe = os.path.join(os.path.dirname(bfc.lib_path()), "bfc")
+    env = dict(os.environ)
+    env.pop("BFC_B200_KEEP_MAX", None)
+    if keep_max is not None:
+        env["BFC_B200_KEEP_MAX"] = keep_max
+    kept = (keep_max is None and gz) or keep_max == "100000000"
+    for name in ("k31_edge", "k33_rep"):
+        c = Case(name)
+        fq = tmp_path / (name + (".fq.gz" if gz else ".fq"))
+        fq.write_bytes(gzip.compress(c.fastq, 1) if gz else c.fastq)
+        args = ["-k", str(c.meta["k"]), "-b", str(c.meta["b"])] + c.meta["extra_args"] + ["-L", "8000", "-V", "4"]
+        r = subprocess.run([exe] + args + ["-t", "4", str(fq)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True, env=env)
+        assert r.stdout == c.corrected
+        assert r.stderr.count(b"batch counted") > 10
+        assert (b"still in memory from the count pass" in r.stderr) == kept
+        r = subprocess.run([exe] + args + ["-1", str(fq)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True, env=env)
+        assert r.stdout == c.trimmed
+
+
 @pytest.mark.parametrize("path", ["part", "probe"])
 @pytest.mark.parametrize("b", [12, 20])
 def test_table_grows_when_regions_fill(bfc, monkeypatch, b, path):

@@ -27,14 +27,21 @@ try:
     with open(fq, "rb") as f, open(tiny, "wb") as g:
         g.write(b"".join(f.readline() for _ in range(4000)))
     exe = os.path.join(ROOT, "bfc_b200", "lib", "bfc")
-    for name, src in (("tiny", tiny), ("full", fq), ("full", fq), ("full", fq)):
+    envs = [e for e in os.environ.get("TIMELINE_ENVS", "").split(";") if e]       # e.g. "BFC_B200_EC_BATCH=40000000;BFC_B200_EC_BATCH=24000000"
+    runs = [("tiny", tiny, ""), ("full", fq, "")] + [("full", fq, e) for e in envs] + [("full", fq, "")]
+    for name, src, extra in runs:
         t0 = time.time()
-        p = subprocess.run([exe, "-k", "33", "-b", "37", "-t", "16", "-V", "4", src], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+        env = dict(os.environ)
+        for kv in extra.split(","):
+            if "=" in kv:
+                env[kv.split("=")[0]] = kv.split("=")[1]
+        name = name + ("_" + extra.replace("=", "-").replace(",", "_") if extra else "")
+        p = subprocess.run([exe] + os.environ.get("TIMELINE_FLAGS", "-k 33").split() + ["-b", "37", "-t", "16", "-V", "4", src], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, env=env)
         dt = time.time() - t0
         print(f"== {name}: wall {dt:.2f} s")
         lines = p.stderr.splitlines()
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        with open(os.path.join(ROOT, "gpurun_out", f"cli_timeline_{name}_{time.time():.0f}.log"), "w") as lf:
+        with open(os.path.join(ROOT, "gpurun_out", f"cli_timeline_{name}_{time.time():.1f}.log"), "w") as lf:
             lf.write(p.stderr)
         keep = [l for l in lines if "@" in l or "Real time" in l]
         for l in (keep if len(keep) <= 40 else keep[:8] + ["..."] + keep[-3:]):
