@@ -215,8 +215,12 @@ def cli_e2e(L, api, wl, n_reads: int) -> dict:
         subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)   # warm-up: a fresh box backs
         cold = time.time() - t0                             # its memory on first touch (seconds for the first process that pins GBs)
         t0 = time.time()
-        subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
+        r = subprocess.run(cmd[:1] + ["-V", "4"] + cmd[1:], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, check=True)
         dt = time.time() - t0
+        log = os.environ.get("BFC_BENCH_CLI_LOG")
+        if log:
+            with open(log, "wb") as fp:
+                fp.write(r.stderr)
         return {"value": n_reads / dt / 1e6, "unit": "Mreads/s", "reads": n_reads, "seconds": dt, "first_run_seconds": cold, "threads": threads,
                 "what": f"`lib/bfc {' '.join(cmd[1:-1])}` {os.path.getsize(fq) / 1e9:.2f} GB FASTQ on tmpfs -> stdout (/dev/null), wall clock of the whole process"}
     finally:
@@ -356,6 +360,16 @@ def run(args, wl):
     opt = bfc_b200.make_opt(k=wl["k"], bf_shift=args.bf_shift, filter_mode=wl["filter_mode"])
     RB = READ_LEN + 1
     trim, do_correct = bool(wl["filter_mode"]), wl["correct"]
+
+    # the command-line leg runs FIRST, while this process holds next to nothing on the GPU: device memory that one
+    # process has just released is scrubbed before another process gets it, and a child started after the 100+ GB of
+    # the resident run had been freed spent 1.3 s waiting for its 16 GiB filter (0.3 s otherwise)
+    cli = None
+    if rank == 0 and world == 1 and not args.no_cli and do_correct:
+        try:
+            cli = cli_e2e(L, api, wl, int(os.environ.get("BFC_BENCH_CLI_READS", min(n, 20_000_000))))
+        except Exception as ex:  # reported, never required
+            cli = {"value": None, "unit": "Mreads/s", "what": f"failed: {ex}"}
 
     if world == 1:
         data = DeviceData(L, api, n)
@@ -629,13 +643,6 @@ def run(args, wl):
     else:
         be.close()
         NativeShardedCount.finalize(L)
-
-    cli = None
-    if rank == 0 and world == 1 and not args.no_cli and do_correct:
-        try:
-            cli = cli_e2e(L, api, wl, int(os.environ.get("BFC_BENCH_CLI_READS", min(n, 8_000_000))))
-        except Exception as ex:  # reported, never required
-            cli = {"value": None, "unit": "Mreads/s", "what": f"failed: {ex}"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -1,15 +1,16 @@
 #!/bin/bash
-# A/B on the GPU box: device-resident bench under each of the given environment settings ("NAME=VALUE" or "-")
+# A/B of environment switches on one GPU box: tools/ab_env.sh <workload> "<ENV=..>" "<ENV=..>" ...  ("-" = no switch)
+W=$1; shift
 mkdir -p gpurun_out
 i=0
-for kv in "$@"; do
-  i=$((i+1))
-  if [ "$kv" = "-" ]; then python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/abenv_$i.json 2> gpurun_out/abenv_$i.err
-  else env $kv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/abenv_$i.json 2> gpurun_out/abenv_$i.err; fi
-  python - <<P
+for e in "$@"; do
+  [ "$e" = "-" ] && e=""
+  env $e python bench.py --workload $W --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-cli > gpurun_out/ab_$i.json 2> gpurun_out/ab_$i.err
+  python - <<PY
 import json
-d=json.loads(open("gpurun_out/abenv_$i.json").read().strip().splitlines()[-1])
-k=d["roofline"]["kernels"]
-print("$kv value", round(d["value"],2), "ms", round(d["ms_per_step"]), {n:round(v["ms"]) for n,v in k.items()}, d["stats"]["lookups_per_read"])
-P
+d = json.load(open("gpurun_out/ab_$i.json"))
+k = d["roofline"]["kernels"]
+print("$e".ljust(28), "value %.2f  ms/step %.1f " % (d["value"], d["ms_per_step"]), {n: round(v["ms"] / d["steps"], 1) for n, v in k.items()})
+PY
+  i=$((i+1))
 done

@@ -3,8 +3,8 @@
 step, keyed the way bench.py names them.  Usage: make_traffic.py profiles/r02_ncu_summary.jsonl > profiles/traffic.json"""
 import json, re, sys
 KEYS = [("k_count_part", "count_part"), ("k_tab_apply_marked", "tab_apply"), ("k_enum_count", "enum_count"), ("k_enum_lin", "enum_lin"),
-        ("k_part_bounds", "count_bounds"), ("k_rp_pass", "partition_pass"), ("k_rp_hist", "partition_hist"), ("DeviceRadixSortOnesweep", "partition_sort_pass_portion"),
-        ("k_ec_lookup", "ec_lookup"), ("k_ec_cov", "ec_cov"), ("k_ec_setup", "ec_setup"), ("k_ec_ext", "ec_ext"), ("k_ec_search", "correct"),
+        ("k_part_bounds", "count_bounds"), ("k_rp_pass", "partition_pass"), ("k_rp_hist", "partition_hist"), ("k_rp_scan", "partition_scan"), ("k_seg_scan", "enum_scan"), ("DeviceRadixSortOnesweep", "partition_sort_pass_portion"),
+        ("k_ec_lookup", "ec_lookup"), ("k_ec_cov", "ec_cov"), ("k_ec_setup", "ec_setup"), ("k_ec_rescue", "ec_rescue"), ("k_ec_ext", "ec_ext"), ("k_ec_search", "correct"),
         ("k_ec_merge", "ec_merge"), ("k_trim", "trim")]
 def num(s):
     v, u = s.split()[0], (s.split() + [""])[1]
