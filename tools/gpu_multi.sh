@@ -1,7 +1,7 @@
 #!/bin/bash
-# multi-GPU bench under torchrun with the library's exchange
+# multi-GPU bench under torchrun with the library's exchange: gpurun --gpus N -- bash tools/gpu_multi.sh N [tag]
 set -u
-N=${1:-2}; TAG=${2:-r02h}
+N=${1:-2}; TAG=${2:-r02f}
 mkdir -p gpurun_out
 env BFC_DIST_TIMING=1 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611 \
     bench.py --gpus $N --steps 2 --warmup 2 --no-cpu-baseline > gpurun_out/${TAG}_n$N.json 2> gpurun_out/${TAG}_n$N.err
