@@ -591,7 +591,7 @@ def test_cli_refine_matches_reference_golden(bfc, tmp_path):
     """`bfc -R` end to end (tag parsing, reads left alone, sticky e->ori_st, fresh tags) against the reference's stdout."""
     import subprocess
     exe = os.path.join(os.path.dirname(bfc.lib_path()), "bfc")
-    for name in ("k31_edge", "k33_rep", "k63_h7"):
+    for name in ("k31_edge", "k33_rep", "k63_h7", "k27_opts"):
         c = Case(name)
         fq = tmp_path / (name + ".fq")
         fq.write_bytes(c.fastq)

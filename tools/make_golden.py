@@ -216,6 +216,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "heavy":   # (only the case added in round 2)
         heavy_case("k15_heavy", 8, 32, 250, 0.03, 6000, 100, 0.8, 15, 20)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "opts":    # (added late in round 2: non-default -w / -c / -q together, 3 % errors)
+        synth_case("k27_opts", 15000, 1500, 120, 17, 27, 20, err=0.03, repeat=0.25, extra_args=("-w", "4", "-c", "4", "-q", "12"))
+        sys.exit(0)
     kat()
     synth_case("k21_small", 20000, 3000, 100, 11, 21, 20)
     synth_case("k31_edge", 20000, 2500, 100, 12, 31, 21, repeat=0.2, extra_edge=True)
@@ -224,3 +227,4 @@ if __name__ == "__main__":
     synth_case("k63_h7", 12000, 1000, 150, 15, 63, 19, extra_args=("-H", "7"))
     synth_case("k32_even", 12000, 1000, 100, 16, 32, 19, extra_args=("-c", "2", "-q", "30"))
     heavy_case("k15_heavy", 8, 32, 250, 0.03, 6000, 100, 0.8, 15, 20)
+    synth_case("k27_opts", 15000, 1500, 120, 17, 27, 20, err=0.03, repeat=0.25, extra_args=("-w", "4", "-c", "4", "-q", "12"))
