@@ -124,6 +124,75 @@ def test_oracle_random(bfc, monkeypatch, k, b, G, N, L, repeat, sub, path):
         o.close()
 
 
+def ragged_records(G, n, seed, max_len, err=0.015):
+    """Reads of every length from 0 to max_len (half of them short, a few very long), some in lower case, some with
+    runs of N, some without quality: what a uniform (N, L) batch never shows the kernels."""
+    from bfc_b200 import synth
+    rng = np.random.default_rng(seed)
+    genome = synth.make_genome(G, seed, 0.2)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    seqs, quals = [], []
+    for i in range(n):
+        r = rng.random()
+        L = int(rng.integers(0, 80)) if r < 0.2 else int(rng.integers(80, 400)) if r < 0.9 else int(rng.integers(400, max_len + 1))
+        L = min(L, G)
+        st = int(rng.integers(0, G - L + 1))
+        codes = genome[st:st + L].copy()
+        if rng.random() < 0.5:
+            codes = (3 - codes[::-1]).astype(np.uint8)
+        e = rng.random(L) < err
+        codes = np.where(e, (codes + rng.integers(1, 4, size=L, dtype=np.uint8)) & 3, codes).astype(np.uint8)
+        s = lut[codes].copy()
+        q = np.where(e & (rng.random(L) < 0.8), rng.integers(35, 45, size=L), rng.integers(53, 74, size=L)).astype(np.uint8)
+        if L and rng.random() < 0.1:                       # a run of N somewhere
+            a = int(rng.integers(0, L)); s[a:a + int(rng.integers(1, 6))] = ord("N")
+        if rng.random() < 0.1:
+            s = np.frombuffer(s.tobytes().lower(), dtype=np.uint8)
+        seqs.append(s.tobytes())
+        quals.append(None if rng.random() < 0.05 else q.tobytes())
+    return seqs, quals
+
+
+@pytest.mark.parametrize("k,b,max_len,path", [(21, 22, 3000, "part"), (33, 24, 3000, "part"), (55, 23, 5000, "part"), (31, 22, 1500, "probe")])
+def test_oracle_ragged_reads(bfc, monkeypatch, k, b, max_len, path):
+    """Count, correct and trim on ragged input (empty reads, reads shorter than k, reads of several thousand bases that
+    span count segments and search scratch, N runs, lower case, reads without quality) against the oracle; small
+    windows so that reads straddle window boundaries."""
+    monkeypatch.setenv("BFC_B200_COUNT", path)
+    monkeypatch.setenv("BFC_B200_COUNT_WINDOW", str(1 << 17))
+    monkeypatch.setenv("BFC_B200_SUBBATCH", str(1 << 17))
+    monkeypatch.setenv("BFC_B200_EC_BATCH", str(1 << 18))
+    seqs, quals = ragged_records(60000, 4000, 100 * k + b, max_len)
+    seq, qual, off = bfc.records_to_batch(seqs, quals)   # the C ABI marks a read without quality by 0xFF bytes,
+    oq = qual.copy()                                     # the oracle by 0 bytes (oracle.h)
+    oq[oq == 0xFF] = 0
+    for fm in (0, 1):
+        o = orc.OracleRun(orc.make_opt(k=k, bf_shift=b, filter_mode=fm))
+        e = bfc.Engine(bfc.make_opt(k=k, bf_shift=b, filter_mode=fm))
+        try:
+            o.count(seq, oq, off)
+            e.count(seq, qual, off)
+            assert np.array_equal(e.bloom_bytes(), o.bloom_bytes())
+            if fm:
+                assert np.array_equal(e.bloom_bytes(high=True), o.bloom_bytes(high=True))
+                ko, so, eo = o.trim(seq, off)
+                ke, se, ee = e.trim(seq, off)
+                assert np.array_equal(ke, ko) and np.array_equal(se, so) and np.array_equal(ee, eo)
+            else:
+                sub_o, key_o = o.table()
+                sub_e, key_e = e.table()
+                assert np.array_equal(sub_e, sub_o) and np.array_equal(key_e, key_o)
+                so, qo, ao, _ = o.correct(seq, oq, off)
+                se, qe, ae = e.correct(seq, qual, off)
+                assert np.array_equal(ae, ao)
+                qe = qe.copy()
+                qe[qual == 0xFF] = 0                     # (a read without quality keeps its marker on both sides)
+                assert np.array_equal(se, so) and np.array_equal(qe, qo)
+        finally:
+            e.close()
+            o.close()
+
+
 @pytest.mark.parametrize("k,b,H", [(31, 24, 4), (51, 25, 4), (27, 22, 9)])
 def test_oracle_random_trim(bfc, k, b, H):
     seq, qual, off = synth_batch(100000, 30000, 120, seed=k + b)
