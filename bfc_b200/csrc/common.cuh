@@ -431,6 +431,7 @@ __device__ __forceinline__ void block_add(unsigned long long *dst, unsigned long
 	if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_acc, v);
 	__syncthreads();
 	if (threadIdx.x == 0 && s_acc) atomicAdd(dst, s_acc);
+	__syncthreads(); // calls follow each other: the (speculated, predicated-off) reads of s_acc above must not meet the next call's reset
 }
 
 #endif // __CUDACC__

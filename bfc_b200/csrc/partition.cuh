@@ -157,7 +157,9 @@ __global__ void __launch_bounds__(RP_THREADS, 1) k_rp_pass(RpPassParams<VT> p)
 		// The lanes of this step that hold the same digit.  32 records over 2^bits digits: usually none do, and that is
 		// found out through the count itself -- every lane reads it, tags it with its lane number, and sees after a
 		// warp barrier whether its tag survived.  Only when some lane lost does the warp work the groups out, with one
-		// ballot per digit bit (match.any is far slower than that here).
+		// ballot per digit bit (match.any is far slower than that here).  (The tag stores of lanes with the same digit
+		// go to the same 16-bit word in the same instruction -- compute-sanitizer's racecheck reports them as write-write
+		// hazards, which they are by design: exactly one of the stores lands, whole, and the losers find out.)
 		const uint32_t before = valid ? s_wh[idx] : 0; // < 512: a warp holds 256 records of a tile
 		__syncwarp();
 		if (valid) s_wh[idx] = (uint16_t)(lane << 9 | before);
