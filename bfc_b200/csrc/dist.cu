@@ -84,7 +84,9 @@ struct DistBuf { // one of the two buffer sets of the pipeline
 	unsigned long long *skey, *rkey;   // sorted records to send / records received (keys)
 	uint8_t *sval, *rval;              // ... and their values (vb bytes each)
 	uint64_t scap, rcap;               // capacities in records
-	cudaEvent_t sorted, received;      // engine stream: send buffer complete; exchange stream: receive buffer complete
+	uint8_t *stage_seq, *stage_qual;   // a HOST piece lands here, copied on the copy stream while the engine stream still
+	uint64_t stage_cap;                //   runs the cascade of the chunk before (the scratch arena is busy with that)
+	cudaEvent_t sorted, received, staged; // engine stream: send buffer complete; exchange stream: receive buffer complete; copy stream: piece on the device
 	uint64_t run_counts[DIST_MAX];     // records received from every rank
 	bool pending;                      // received (or being received), not counted yet
 	int vb;
@@ -174,6 +176,7 @@ int bfcg_dist_init(int rank, int world, const void *id)
 	for (int i = 0; i < 2; ++i) {
 		BFCG_CUDA(cudaEventCreateWithFlags(&d->buf[i].sorted, cudaEventDisableTiming));
 		BFCG_CUDA(cudaEventCreateWithFlags(&d->buf[i].received, cudaEventDisableTiming));
+		BFCG_CUDA(cudaEventCreateWithFlags(&d->buf[i].staged, cudaEventDisableTiming));
 		d->buf[i].vb = -1;
 	}
 	BFCG_CUDA(cudaMalloc(&d->d_cnt, (DIST_MAX + DIST_MAX * DIST_MAX) * 8));
@@ -190,7 +193,8 @@ void bfcg_dist_finalize(void)
 	for (int i = 0; i < 2; ++i) {
 		DistBuf &b = d->buf[i];
 		cudaFree(b.skey); cudaFree(b.sval); cudaFree(b.rkey); cudaFree(b.rval);
-		cudaEventDestroy(b.sorted); cudaEventDestroy(b.received);
+		cudaFree(b.stage_seq); cudaFree(b.stage_qual);
+		cudaEventDestroy(b.sorted); cudaEventDestroy(b.received); cudaEventDestroy(b.staged);
 	}
 	cudaFree(d->d_cnt); cudaFreeHost(d->h_cnt);
 	g_nccl.CommDestroy(d->comm);
@@ -244,6 +248,27 @@ int bfcg_dist_count_piece(const bfc_opt_t *opt, bfc_bf_t *bf, bfc_bf_t *bf_high,
 	uint64_t counts[DIST_MAX];
 	memset(counts, 0, sizeof(counts));
 	if ((r = buf_reserve(cur, std::max<uint64_t>(piece->n_bytes, 1), 0, vb)) != BFCG_OK) return r;
+	bfcg_batch_t staged_piece;
+	if (piece->where == BFCG_HOST && piece->n_bytes) {
+		// (this set's staging buffers were last read by E(c-2), which the host has waited for)
+		if (piece->n_bytes > cur.stage_cap) {
+			cudaFree(cur.stage_seq); cudaFree(cur.stage_qual);
+			cur.stage_seq = cur.stage_qual = 0;
+			cur.stage_cap = piece->n_bytes + piece->n_bytes / 8;
+			if (cudaMalloc(&cur.stage_seq, cur.stage_cap) != cudaSuccess || cudaMalloc(&cur.stage_qual, cur.stage_cap) != cudaSuccess) {
+				cur.stage_cap = 0;
+				return bfcg_fail(__func__, "cudaMalloc(piece staging)", cudaErrorMemoryAllocation);
+			}
+		}
+		BFCG_CUDA(cudaMemcpyAsync(cur.stage_seq, piece->seq, piece->n_bytes, cudaMemcpyHostToDevice, rt.copy_in));
+		if (piece->qual) BFCG_CUDA(cudaMemcpyAsync(cur.stage_qual, piece->qual, piece->n_bytes, cudaMemcpyHostToDevice, rt.copy_in));
+		BFCG_CUDA(cudaEventRecord(cur.staged, rt.copy_in));
+		BFCG_CUDA(cudaStreamWaitEvent(rt.stream, cur.staged, 0));
+		staged_piece = *piece;
+		staged_piece.where = BFCG_DEVICE, staged_piece.seq = cur.stage_seq, staged_piece.qual = piece->qual ? cur.stage_qual : 0;
+		staged_piece.off = 0; // (the enumeration goes by the terminators, not by offsets)
+		piece = &staged_piece;
+	}
 	if (piece->n_bytes && (r = bfcg_enum_part_records_fmt(opt, piece, d->owner_bits, vb, (uint64_t*)cur.skey, cur.sval, counts)) != BFCG_OK) return r;
 	BFCG_CUDA(cudaEventRecord(cur.sorted, rt.stream));
 
