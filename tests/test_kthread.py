@@ -4,6 +4,8 @@ hands batches to every step in order, and stops when step 0 returns NULL."""
 import ctypes as C
 import threading
 
+import pytest
+
 import bfc_b200
 
 
@@ -29,11 +31,15 @@ def test_kt_for_covers_every_index_once():
         assert tids <= set(range(threads))
 
 
-def test_kt_pipeline_order_and_exclusion():
+@pytest.mark.parametrize("n_steps", [2, 3, 4])
+def test_kt_pipeline_order_and_exclusion(n_steps):
+    """Batches pass every step in order, no step runs concurrently with itself, and never more than n_threads batches
+    are in flight -- what the drivers' rings of pinned buffers (count_host.c, correct_host.c: N_FLAT) rely on."""
     L = C.CDLL(bfc_b200.lib_path())
     FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_int, C.c_void_p)
-    n_batches, n_steps = 25, 3
+    n_batches = 25
     lock = threading.Lock()
+    in_flight, max_in_flight = [0], [0]
     running = [0] * n_steps
     seen = [[] for _ in range(n_steps)]
     made = [0]
@@ -50,8 +56,14 @@ def test_kt_pipeline_order_and_exclusion():
                     return None
                 made[0] += 1
                 b = made[0]          # batch ids 1..n (a non-NULL pointer value)
+                with lock:
+                    in_flight[0] += 1
+                    max_in_flight[0] = max(max_in_flight[0], in_flight[0])
             else:
                 b = data
+            if s == n_steps - 1:
+                with lock:
+                    in_flight[0] -= 1
             seen[s].append(b)
             for _ in range(2000):    # some work, so that the steps of neighbouring batches overlap
                 pass
@@ -62,11 +74,13 @@ def test_kt_pipeline_order_and_exclusion():
 
     cb = FN(step)
     L.kt_pipeline.argtypes = [C.c_int, FN, C.c_void_p, C.c_int]
-    for threads in (1, 2, 3):
+    for threads in (1, 2, 3, 4):
         made[0] = 0
+        in_flight[0] = max_in_flight[0] = 0
         for s in range(n_steps):
             seen[s].clear()
         L.kt_pipeline(threads, cb, None, n_steps)
         assert not errors
+        assert in_flight[0] == 0 and 1 <= max_in_flight[0] <= threads, (threads, max_in_flight[0])
         for s in range(n_steps):
             assert seen[s] == list(range(1, n_batches + 1)), (threads, s)
