@@ -14,7 +14,7 @@ bseq_file_t *bseq_open_from(void *gz, unsigned char *pre, size_t pre_len, const 
 int bseq_at_eof(const bseq_file_t *f);
 
 /* ---------------------------------------------------------------- recycled large buffers
- * A batch is about a gigabyte of text plus a few hundred megabytes of offsets and as much formatted output again.
+ * A batch is a quarter of a gigabyte of text plus tens of megabytes of offsets and as much formatted output again.
  * Fresh from malloc, every one of those pages is mapped, zeroed and faulted in on first touch and unmapped on free --
  * per batch -- which cost more than reading and splitting the text.  Large buffers therefore go back to a small pool
  * and are handed out again (first fit within 2x), up to a fixed total. */

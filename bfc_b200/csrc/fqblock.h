@@ -5,7 +5,9 @@
  * the printf-per-read writer (reference correct.c:591-616).  Input is read in blocks of
  * text; a block that is plain four-line FASTQ -- every record "@name[ comment]", one
  * sequence line, "+...", one quality line of the same length, "\n" line ends -- is split
- * by all -t threads at once (newline index, then one record per work item).  Anything
+ * by all -t threads at once (the newlines of every 2 MB piece are counted while it is read; the counts give the
+ * line number of every piece's first byte; each piece then parses the records that start in it -- one pass over the
+ * text, no index of line starts).  Anything
  * else (FASTA, multi-line records, "\r\n", blank lines, a truncated tail) switches the
  * reader, from the start of that block on, to the tolerant sequential parser in bseq.c,
  * so the records delivered are always exactly those bseq_read() would deliver, including
